@@ -1,0 +1,155 @@
+/* pcab200 -- C ABI of the B200 (sm_100a) hot path of prs-eth/PCAccumulation.
+ *
+ * One entry point per fused stage of MotionNet.forward (reference models/motionnet.py:137-262), the
+ * voxeliser (libs/voxel_generator.py) and the Chamfer extension (chamfer_distance/).  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (torch-owned memory in the Python host),
+ *     except the small `const float* range6 / voxel_size3` geometry arrays, which are HOST pointers;
+ *   - the library allocates nothing and keeps no state besides the thread-local error string;
+ *   - calls are asynchronous on `stream`, never synchronise the device, return 0 on success or a negative
+ *     PCAB_ERR_* code (pcab_last_error() gives the message); nothing is printed, nothing exits;
+ *   - scratch memory is passed in; each pcab_*_workspace() returns the bytes the matching call needs;
+ *   - activations are NHWC float32; integer outputs are bit-exact with the reference.
+ *
+ * The reference interface each entry replaces is cited as file:line (relative to the reference root).
+ */
+#ifndef PCAB200_H_
+#define PCAB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* pcab_stream_t; /* == cudaStream_t */
+
+const char* pcab_last_error(void);
+int pcab_version(void);
+
+/* ---- voxeliser: libs/voxel_generator.py:4-61,117-154 + libs/dataloader.py:33-38 ------------------------ */
+size_t pcab_voxelize_workspace(int n_points, long long n_cells);
+int pcab_voxelize(const float* points4 /* [N,4] x,y,z,t */, const int* point_batch /* [N] or NULL */, int n_points,
+                  int batch_size, const float* range6 /* host */, const float* voxel_size3 /* host */, int n_sweeps,
+                  int* coords_zyxt /* [>=M,4] */, int* pillar_batch /* [>=M] */, int* p2v /* [N], -1 = rejected */,
+                  int* num_voxels /* [B] */, int* total_voxels /* [1] */, void* workspace, size_t workspace_bytes,
+                  pcab_stream_t stream);
+
+/* stable sort of the points by pillar + segment table (replaces the torch_scatter index plumbing) */
+size_t pcab_pillar_index_workspace(int n_points);
+int pcab_pillar_index(const int* p2v, int n_points, int n_pillars, int* order /* [N] */, int* pstart /* [M+1] */,
+                      void* workspace, size_t workspace_bytes, pcab_stream_t stream);
+
+/* models/motionnet.py:159-160: scatter(mean) of xyz, scatter(max) of the GT foreground label */
+int pcab_pillar_stats(const float* xyz, const long long* fb_labels /* or NULL */, const int* order, const int* pstart,
+                      int n_pillars, float* pillar_mean /* [M,3] */, int* fb_sub /* [M] or NULL */,
+                      pcab_stream_t stream);
+
+/* canvas cell of each pillar, models/pillar_encoder.py:158; cell_to_pillar must be pre-filled with -1 */
+int pcab_pillar_cells(const int* coords_zyxt, const int* pillar_batch, int n_pillars, int n_sweeps, int ny, int nx,
+                      int* pillar_cell /* [M] */, int* pillar_frame /* [M] = b*T+t, or NULL */,
+                      int* cell_to_pillar /* [B*T*ny*nx] or NULL */, pcab_stream_t stream);
+
+/* models/pillar_encoder.py:97-122 (PillarFeatureNet) + :125-174 (scatter to the [B*T,ny,nx,32] canvas) */
+int pcab_pfn_pack_size(void);
+size_t pcab_pillar_encode_workspace(int n_points, int n_pillars);
+int pcab_pillar_encode(const float* xyz, const int* point_time, const int* order, const int* p2v, const int* pstart,
+                       const int* coords_zyxt, const int* pillar_cell, const float* pillar_mean,
+                       const float* weight_pack, int n_points, int n_pillars, const float* range6 /* host */,
+                       const float* voxel_size3 /* host */, int n_sweeps, float* pillar_feats /* [M,32] */,
+                       float* canvas_nhwc /* zero-filled by the caller */, void* workspace, size_t workspace_bytes,
+                       pcab_stream_t stream);
+
+/* ---- convolutions: models/unet.py:11-113, models/stpn.py:13-22,80 ---------------------------------------- */
+/* FP32 CUDA-core path; sources accumulate into one output (concat / temporal 3x3x3) */
+int pcab_conv3x3_f32(const float* src0, int c0, const float* src1, int c1, const float* src2, int c2, int temporal_T,
+                     const float* weight_packed /* per source [9][C_s][Cout] */, const float* bias,
+                     const float* bn_scale, const float* bn_shift, int relu, float* out, int n_images, int H, int W,
+                     int Cout, int out_cstride, int out_coff, pcab_stream_t stream);
+int pcab_convT2x2_f32(const float* in, const float* weight_packed /* [4][Cin][Cout] */, const float* bias, float* out,
+                      int n_images, int H, int W, int Cin, int Cout, int out_cstride, int out_coff,
+                      pcab_stream_t stream);
+int pcab_maxpool2x2(const float* in, float* out, int n_images, int H, int W, int C, pcab_stream_t stream);
+int pcab_temporal_max(const float* in, float* out, int B, int T, int H, int W, int C, pcab_stream_t stream);
+
+/* tcgen05 tensor-core path (3xTF32 split, FP32 accumulate in TMEM); same semantics as pcab_conv3x3_f32 */
+int pcab_conv3x3_tc_supported(int n_sources, int c0, int c1, int c2, int Cout, int H, int W);
+size_t pcab_conv3x3_tc_pack_floats(int cin_total, int Cout);
+int pcab_conv3x3_tc(const float* src0, int c0, const float* src1, int c1, const float* src2, int c2, int temporal_T,
+                    const float* weight_tc_packed, const float* bias, const float* bn_scale, const float* bn_shift,
+                    int relu, float* out, int n_images, int H, int W, int Cout, int out_cstride, int out_coff,
+                    pcab_stream_t stream);
+
+/* ---- heads / BEV ops: models/motionnet.py:45-135,167-170,188-194 ------------------------------------------ */
+int pcab_head2_conv(const float* in_nhwc, int cin, const float* weight_packed /* [9][cin][2] */, const float* bias,
+                    int n_images, int H, int W, float* logits_nchw /* [n,2,H,W] */, int* argmax_map /* [n,H,W] */,
+                    pcab_stream_t stream);
+int pcab_fb_per_point(const int* fb_map, const int* pillar_cell, const int* p2v, int n_points,
+                      long long* fb_per_point, pcab_stream_t stream);
+int pcab_canvases(const int* pillar_cell, const int* fb_sub, const float* pillar_mean, int n_pillars, int H, int W,
+                  float* occ_map, long long* fb_map, float* mean_map /* [B*T,3,H,W] */, pcab_stream_t stream);
+int pcab_warp_bev(const float* bev_nhwc, const float* pose /* [B*T,4,4] */, int B, int T, int H, int W, int C, float vx,
+                  float vy, float x_min, float y_min, float* out_nhwc, pcab_stream_t stream);
+int pcab_transform_points(const float* xyz, const int* point_frame, const float* pose, int n_points, float* out,
+                          pcab_stream_t stream);
+
+/* ---- ego motion: models/egomotion.py:100-469, toolbox/register_utils.py:19-56,184-197,247-318 ------------- */
+size_t pcab_bg_compact_workspace(long long n_cells);
+int pcab_bg_compact(const int* cell_to_pillar, const int* fb_est, int n_frames, int H, int W, int* bg_cells,
+                    int* frame_off /* [n_frames+1] */, void* workspace, size_t workspace_bytes, pcab_stream_t stream);
+size_t pcab_ego_pairs_workspace(int npairs);
+int pcab_ego_pairs(const float* geo_nhwc /* [B*T,H,W,64] */, const int* cell_to_pillar, const float* pillar_mean,
+                   const int* pillar_frame, int n_pillars, const int* bg_cells, const int* frame_off,
+                   const int* pair_frames /* [P,2] source,target frame */, const int* choice /* [P,2,1024] */,
+                   const float* thr2 /* [P] */, int npairs, const float* alpha, const float* beta, int sinkhorn_iters,
+                   const float* ego_gt /* [B*T,4,4] */, const int* chain_pair /* [B*T] */, int B, int T, int chain_mode,
+                   float* perm_out /* [P,1024,1024] */, float* pose_pairs /* [P,4,4] */, float* ego_est /* [B*T,4,4] */,
+                   float* ego_gt_out /* [B*T,4,4] */, float* scalars /* l1,l2,rot_err,trans_err */, void* workspace,
+                   size_t workspace_bytes, pcab_stream_t stream);
+
+/* ---- per-point stages: models/pillar_encoder.py:206-267, models/stpn.py:91-103 ---------------------------- */
+size_t pcab_select_workspace(int n);
+int pcab_select_indices(const int* flags, const long long* values, long long value, int n, int* idx, int* count,
+                        void* workspace, size_t workspace_bytes, pcab_stream_t stream);
+int pcab_ungrid(const float* feats_nhwc, int C, int H, int W, const float* xyz, const int* frame_of_point,
+                const int* idx, int k, float x_abs, float y_abs, float* out /* [k,C] */, pcab_stream_t stream);
+int pcab_stpn_head_pack_size(void);
+int pcab_init_point_outputs(int n_points, float* mos, float* offset, pcab_stream_t stream);
+int pcab_stpn_head(const float* mos_feats_nhwc /* [B,H,W,64] */, int H, int W, const float* transformed_points,
+                   const int* point_batch, const int* fg_idx, int n_fg, const float* weight_pack, float x_abs,
+                   float y_abs, float* mos_out /* [N,2] */, float* offset_out /* [N,2] */, pcab_stream_t stream);
+
+/* ---- clustering: models/cluster.py:9-110 (sparse_quantize + sklearn DBSCAN + canonicalise) ---------------- */
+int pcab_dynamic_flags(const float* mos, int n0, int n, int* flags, pcab_stream_t stream);
+size_t pcab_cluster_workspace(int n_selected);
+int pcab_cluster_scene(const float* transformed_points, const float* offset, const int* sel, int n0, int n_selected,
+                       float dedupe_voxel, double eps, int min_samples, int min_p_cluster, long long* inst_out,
+                       int* n_instances_out, void* workspace, size_t workspace_bytes, pcab_stream_t stream);
+
+/* ---- TubeNet: models/tpointnet.py:211-305, toolbox/register_utils.py:72-93 -------------------------------- */
+int pcab_tpn_static_embed(const float* mos_feat /* [n_src,64] */, const float* geo_feat /* [n_src,32] */,
+                          const int* src_idx /* [n] row of each (padded) point */, const int* inst, int n, int K,
+                          const float* pack_motion, const float* pack_geo, float* mos_emb /* [K,128] */,
+                          float* geo_emb /* [K,128] */, pcab_stream_t stream);
+size_t pcab_tpn_iteration_workspace(int K, int T);
+int pcab_tpn_iteration(const float* points, const int* inst, const int* tidx, int n, int K, int T, const float* mos_emb,
+                       const float* geo_emb, const float* pack_pos, const float* pack_regressor,
+                       float* pose_out /* [K*T,4,4] */, float* pose_centered_out /* or NULL */,
+                       float* rep_out /* [K*T,7] or NULL */, void* workspace, size_t workspace_bytes,
+                       pcab_stream_t stream);
+int pcab_apply_seg_pose(const float* points, const int* seg, const float* pose, int n, float* out,
+                        pcab_stream_t stream);
+int pcab_scatter_rows3(const float* src, const int* idx, int k, float* dst, pcab_stream_t stream);
+
+/* ---- Chamfer distance: chamfer_distance/chamfer_distance.cpp:27-56 (forward_cuda / backward_cuda) --------- */
+size_t pcab_chamfer_workspace(int B, int n, int m);
+int pcab_chamfer_forward(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1, float* dist2,
+                         int* idx1, int* idx2, void* workspace, size_t workspace_bytes, pcab_stream_t stream);
+int pcab_chamfer_backward(const float* xyz1, const float* xyz2, int B, int n, int m, const float* grad_dist1,
+                          const float* grad_dist2, const int* idx1, const int* idx2, float* grad_xyz1,
+                          float* grad_xyz2, pcab_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCAB200_H_ */

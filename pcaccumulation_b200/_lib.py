@@ -1,0 +1,91 @@
+"""ctypes binding of libpcab200.so (the C ABI declared in include/pcab200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, an exception is
+raised.  Only raw device pointers, sizes and the current CUDA stream cross this boundary.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcab200.so")
+
+_lib = None
+
+
+class PcabError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PcabError(
+                f"{LIB_PATH} is missing: build it with `python -m pcaccumulation_b200.build` "
+                "(there is no CPU or PyTorch fallback for the hot path)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.pcab_last_error.restype = ctypes.c_char_p
+        for name in SIZE_T_FUNCS:
+            getattr(_lib, name).restype = ctypes.c_size_t
+    return _lib
+
+
+SIZE_T_FUNCS = [
+    "pcab_voxelize_workspace", "pcab_pillar_index_workspace", "pcab_pillar_encode_workspace",
+    "pcab_bg_compact_workspace", "pcab_ego_pairs_workspace", "pcab_select_workspace", "pcab_cluster_workspace",
+    "pcab_tpn_iteration_workspace", "pcab_chamfer_workspace", "pcab_conv3x3_tc_pack_floats",
+]
+
+# every symbol include/pcab200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "pcab_last_error", "pcab_version", "pcab_voxelize_workspace", "pcab_voxelize", "pcab_pillar_index_workspace",
+    "pcab_pillar_index", "pcab_pillar_stats", "pcab_pillar_cells", "pcab_pfn_pack_size",
+    "pcab_pillar_encode_workspace", "pcab_pillar_encode", "pcab_conv3x3_f32", "pcab_convT2x2_f32", "pcab_maxpool2x2",
+    "pcab_temporal_max", "pcab_conv3x3_tc_supported", "pcab_conv3x3_tc_pack_floats", "pcab_conv3x3_tc",
+    "pcab_head2_conv", "pcab_fb_per_point", "pcab_canvases", "pcab_warp_bev", "pcab_transform_points",
+    "pcab_bg_compact_workspace", "pcab_bg_compact", "pcab_ego_pairs_workspace", "pcab_ego_pairs",
+    "pcab_select_workspace", "pcab_select_indices", "pcab_ungrid", "pcab_stpn_head_pack_size",
+    "pcab_init_point_outputs", "pcab_stpn_head", "pcab_dynamic_flags", "pcab_cluster_workspace", "pcab_cluster_scene",
+    "pcab_tpn_static_embed", "pcab_tpn_iteration_workspace", "pcab_tpn_iteration", "pcab_apply_seg_pose",
+    "pcab_scatter_rows3", "pcab_chamfer_workspace", "pcab_chamfer_forward", "pcab_chamfer_backward",
+]
+
+
+def P(t):
+    """Device (or host, for numpy-backed ctypes arrays) pointer argument."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    if isinstance(t, torch.Tensor):
+        return ctypes.c_void_p(t.data_ptr())
+    return ctypes.cast(t, ctypes.c_void_p)
+
+
+I = ctypes.c_int
+F = ctypes.c_float
+D = ctypes.c_double
+L = ctypes.c_longlong
+Z = ctypes.c_size_t
+
+
+def host_floats(values):
+    return (ctypes.c_float * len(values))(*[float(v) for v in values])
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise PcabError(f"{name} failed ({rc}): {lib().pcab_last_error().decode()}")
+
+
+def size(name, *args):
+    return int(getattr(lib(), name)(*args))
+
+
+def scratch(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

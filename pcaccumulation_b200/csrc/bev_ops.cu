@@ -1,0 +1,218 @@
+// BEV-map utilities: 2-class head conv + argmax, label scatter-back, pose warp, point transform,
+// occupancy / label / mean canvases.
+//
+// Replaces models/motionnet.py:45-114 (warp_feats), :117-135 (transform_points), :167-170 (canvases),
+// :188-194 (FB decision + inverse scatter), models/pillar_encoder.py:177-204 and the second conv of
+// SegHead2D (models/unet.py:268) for the 2-class semseg head.
+#include "common.cuh"
+#include "pcab200.h"
+
+namespace {
+
+// conv3x3 Cin -> 2 (pad 1), NHWC input, planar NCHW logits out [n][2][H][W] + argmax (first max wins)
+template <int CIN>
+__global__ void __launch_bounds__(256) k_head2(const float* __restrict__ in, const float* __restrict__ w /* [9][CIN][2] */,
+                                               const float* __restrict__ bias, int N, int H, int W,
+                                               float* __restrict__ logits, int* __restrict__ argmax) {
+  __shared__ float sw[9 * CIN * 2];
+  for (int i = threadIdx.x; i < 9 * CIN * 2; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  long long total = (long long)N * H * W;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
+    int x = (int)(e % W);
+    int y = (int)((e / W) % H);
+    int n = (int)(e / ((long long)W * H));
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      int gy = y + ky - 1;
+      if (gy < 0 || gy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        int gx = x + kx - 1;
+        if (gx < 0 || gx >= W) continue;
+        const float4* p = reinterpret_cast<const float4*>(in + (((size_t)n * H + gy) * W + gx) * CIN);
+        const float* ww = sw + (ky * 3 + kx) * CIN * 2;
+#pragma unroll
+        for (int c4 = 0; c4 < CIN / 4; ++c4) {
+          float4 v = p[c4];
+          a0 = fmaf(v.x, ww[8 * c4 + 0], a0), a1 = fmaf(v.x, ww[8 * c4 + 1], a1);
+          a0 = fmaf(v.y, ww[8 * c4 + 2], a0), a1 = fmaf(v.y, ww[8 * c4 + 3], a1);
+          a0 = fmaf(v.z, ww[8 * c4 + 4], a0), a1 = fmaf(v.z, ww[8 * c4 + 5], a1);
+          a0 = fmaf(v.w, ww[8 * c4 + 6], a0), a1 = fmaf(v.w, ww[8 * c4 + 7], a1);
+        }
+      }
+    }
+    a0 += bias[0], a1 += bias[1];
+    size_t hw = (size_t)H * W;
+    logits[(size_t)n * 2 * hw + (size_t)y * W + x] = a0;
+    logits[(size_t)n * 2 * hw + hw + (size_t)y * W + x] = a1;
+    argmax[e] = a1 > a0 ? 1 : 0;
+  }
+}
+
+__global__ void k_fb_per_point(const int* __restrict__ fb_map, const int* __restrict__ pillar_cell,
+                               const int* __restrict__ p2v, int n, long long* __restrict__ fb_pp) {
+  int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) fb_pp[i] = fb_map[pillar_cell[p2v[i]]];
+}
+
+// occupancy f32, GT label i64 and pillar-mean f32 canvases ([B*T,H,W] planar; mean is [B*T,3,H,W])
+__global__ void k_canvases(const int* __restrict__ pillar_cell, const int* __restrict__ fb_sub,
+                           const float* __restrict__ pmean, int m, int hw, float* __restrict__ occ,
+                           long long* __restrict__ fb_map, float* __restrict__ mean_map) {
+  int stride = gridDim.x * blockDim.x;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < m; p += stride) {
+    int cell = pillar_cell[p];
+    occ[cell] = 1.f;
+    fb_map[cell] = fb_sub[p];
+    int f = cell / hw, r = cell % hw;
+    mean_map[((size_t)f * 3 + 0) * hw + r] = pmean[3 * p];
+    mean_map[((size_t)f * 3 + 1) * hw + r] = pmean[3 * p + 1];
+    mean_map[((size_t)f * 3 + 2) * hw + r] = pmean[3 * p + 2];
+  }
+}
+
+// rows 0,1 of inv(M) for a 4x4 in double (torch.linalg.inv), out = {i00,i01,i03,i10,i11,i13}
+__device__ void inv4_rows01(const float* P, float* out6) {
+  double a[4][8];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) a[i][j] = P[4 * i + j], a[i][4 + j] = (i == j);
+  for (int c = 0; c < 4; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 4; ++r)
+      if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+    for (int j = 0; j < 8; ++j) {
+      double tmp = a[c][j];
+      a[c][j] = a[piv][j], a[piv][j] = tmp;
+    }
+    double d = a[c][c];
+    for (int j = 0; j < 8; ++j) a[c][j] /= d;
+    for (int r = 0; r < 4; ++r)
+      if (r != c) {
+        double fct = a[r][c];
+        for (int j = 0; j < 8; ++j) a[r][j] -= fct * a[c][j];
+      }
+  }
+  out6[0] = (float)a[0][4], out6[1] = (float)a[0][5], out6[2] = (float)a[0][7];
+  out6[3] = (float)a[1][4], out6[4] = (float)a[1][5], out6[5] = (float)a[1][7];
+}
+
+constexpr int kMaxWarpFrames = 256;
+
+// bilinear warp of frames 1..T-1 by inv(pose) (zeros padding, align_corners=False); slot 0 = frame T-1 (quirk Q1)
+__global__ void __launch_bounds__(256) k_warp(const float* __restrict__ bev, const float* __restrict__ pose, int B,
+                                              int T, int H, int W, int C4, float vx, float vy, float x_min, float y_min,
+                                              float* __restrict__ out) {
+  __shared__ float s_inv[kMaxWarpFrames][6];
+  for (int f = threadIdx.x; f < B * T; f += blockDim.x) inv4_rows01(pose + (size_t)f * 16, s_inv[f]);
+  __syncthreads();
+  long long total = (long long)B * T * H * W;
+  int lane_c = threadIdx.x % C4;  // threads of a pixel cover its channels (float4 each)
+  int pix_per_block = blockDim.x / C4;
+  for (long long pix = (long long)blockIdx.x * pix_per_block + threadIdx.x / C4; pix < total;
+       pix += (long long)gridDim.x * pix_per_block) {
+    int x = (int)(pix % W);
+    int y = (int)((pix / W) % H);
+    int f = (int)(pix / ((long long)W * H));
+    int b = f / T, t = f % T;
+    float4* dst = reinterpret_cast<float4*>(out) + pix * C4 + lane_c;
+    if (t == 0) {
+      *dst = reinterpret_cast<const float4*>(bev)[(((size_t)(b * T + T - 1) * H + y) * W + x) * C4 + lane_c];
+      continue;
+    }
+    const float* iv = s_inv[f];
+    float gx = ((float)x + 0.5f) * vx + x_min;
+    float gy = ((float)y + 0.5f) * vy + y_min;
+    float u = (iv[0] * gx + iv[1] * gy + iv[2]) / fabsf(x_min);
+    float v = (iv[3] * gx + iv[4] * gy + iv[5]) / fabsf(y_min);
+    float ix = ((u + 1.f) * W - 1.f) / 2.f;
+    float iy = ((v + 1.f) * H - 1.f) / 2.f;
+    float fx0 = floorf(ix), fy0 = floorf(iy);
+    float wx0 = (fx0 + 1.f) - ix, wx1 = ix - fx0, wy0 = (fy0 + 1.f) - iy, wy1 = iy - fy0;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (fx0 >= -1.f && fx0 <= (float)W && fy0 >= -1.f && fy0 <= (float)H) {
+      int x0 = (int)fx0, y0 = (int)fy0;
+      const float4* src = reinterpret_cast<const float4*>(bev) + (size_t)f * H * W * C4 + lane_c;
+      auto tap = [&](int xx, int yy, float wgt) {
+        if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
+          float4 s = src[((size_t)yy * W + xx) * C4];
+          r.x = fmaf(s.x, wgt, r.x), r.y = fmaf(s.y, wgt, r.y), r.z = fmaf(s.z, wgt, r.z), r.w = fmaf(s.w, wgt, r.w);
+        }
+      };
+      tap(x0, y0, wx0 * wy0);
+      tap(x0 + 1, y0, wx1 * wy0);
+      tap(x0, y0 + 1, wx0 * wy1);
+      tap(x0 + 1, y0 + 1, wx1 * wy1);
+    }
+    *dst = r;
+  }
+}
+
+__global__ void k_transform_points(const float* __restrict__ xyz, const int* __restrict__ pframe,
+                                   const float* __restrict__ pose, int n, float* __restrict__ out) {
+  int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float* P = pose + (size_t)pframe[i] * 16;
+    float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      // (R @ p^T) + t : dot product of three terms, then the translation
+      float d = P[4 * r] * x;
+      d = fmaf(P[4 * r + 1], y, d);
+      d = fmaf(P[4 * r + 2], z, d);
+      out[3 * i + r] = d + P[4 * r + 3];
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int pcab_head2_conv(const float* in_nhwc, int cin, const float* weight_packed, const float* bias,
+                               int n_images, int H, int W, float* logits_nchw, int* argmax_map, cudaStream_t stream) {
+  long long total = (long long)n_images * H * W;
+  if (cin == 32)
+    k_head2<32><<<grid_for(total, 256, 16), 256, 0, stream>>>(in_nhwc, weight_packed, bias, n_images, H, W, logits_nchw,
+                                                             argmax_map);
+  else {
+    pcab_set_error("pcab_head2_conv: unsupported cin %d", cin);
+    return PCAB_ERR_ARG;
+  }
+  PCAB_CHECK_LAUNCH("pcab_head2_conv");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_fb_per_point(const int* fb_map, const int* pillar_cell, const int* p2v, int n_points,
+                                 long long* fb_per_point, cudaStream_t stream) {
+  k_fb_per_point<<<grid_for(n_points, 256), 256, 0, stream>>>(fb_map, pillar_cell, p2v, n_points, fb_per_point);
+  PCAB_CHECK_LAUNCH("pcab_fb_per_point");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_canvases(const int* pillar_cell, const int* fb_sub, const float* pillar_mean, int n_pillars, int H,
+                             int W, float* occ_map, long long* fb_map, float* mean_map, cudaStream_t stream) {
+  k_canvases<<<grid_for(n_pillars, 256), 256, 0, stream>>>(pillar_cell, fb_sub, pillar_mean, n_pillars, H * W, occ_map,
+                                                          fb_map, mean_map);
+  PCAB_CHECK_LAUNCH("pcab_canvases");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_warp_bev(const float* bev_nhwc, const float* pose, int B, int T, int H, int W, int C, float vx,
+                             float vy, float x_min, float y_min, float* out_nhwc, cudaStream_t stream) {
+  PCAB_REQUIRE(C % 4 == 0 && 256 % (C / 4) == 0, "C/4 must divide 256");
+  PCAB_REQUIRE(B * T <= kMaxWarpFrames, "too many frames per call");
+  long long total = (long long)B * T * H * W;
+  int pix_per_block = 256 / (C / 4);
+  k_warp<<<grid_for(total, pix_per_block, 16), 256, 0, stream>>>(bev_nhwc, pose, B, T, H, W, C / 4, vx, vy, x_min, y_min,
+                                                                out_nhwc);
+  PCAB_CHECK_LAUNCH("pcab_warp_bev");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_transform_points(const float* xyz, const int* point_frame, const float* pose, int n_points,
+                                     float* out, cudaStream_t stream) {
+  k_transform_points<<<grid_for(n_points, 256), 256, 0, stream>>>(xyz, point_frame, pose, n_points, out);
+  PCAB_CHECK_LAUNCH("pcab_transform_points");
+  return PCAB_OK;
+}

@@ -1,0 +1,123 @@
+// Chamfer distance: brute-force bidirectional nearest neighbour (squared distance + argmin) and its
+// gradient.  Replaces chamfer_distance/chamfer_distance.cu:6-155 (forward) and :158-209 (backward); results
+// follow the reference's CPU path bit for bit (chamfer_distance.cpp:59-84): d = (dx*dx + dy*dy) + dz*dz in
+// float32 without contraction, strict '<' so the LOWEST index wins ties.
+//
+// Parallelisation: queries across threads, the target set streamed through shared memory in tiles; the
+// target range is additionally split across blockIdx.y and the partial results are merged with one 64-bit
+// atomicMin on (distance bits << 32 | index), which preserves the lowest-index tie rule because squared
+// distances are non-negative (their IEEE bit patterns order like the values).
+#include "common.cuh"
+#include "pcab200.h"
+
+namespace {
+
+constexpr int TILE = 1024;
+
+__global__ void __launch_bounds__(256) k_chamfer_nn(const float* __restrict__ q, int n, const float* __restrict__ t,
+                                                    int m, int chunk, unsigned long long* __restrict__ best) {
+  __shared__ float sx[TILE], sy[TILE], sz[TILE];
+  const int b = blockIdx.z;
+  const float* qb = q + (size_t)b * n * 3;
+  const float* tb = t + (size_t)b * m * 3;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k_begin = blockIdx.y * chunk;
+  const int k_end = min(m, k_begin + chunk);
+  float x1 = 0.f, y1 = 0.f, z1 = 0.f;
+  if (j < n) x1 = qb[3 * j], y1 = qb[3 * j + 1], z1 = qb[3 * j + 2];
+  float bd = INFINITY;
+  int bi = 0;
+  for (int k0 = k_begin; k0 < k_end; k0 += TILE) {
+    int cnt = min(TILE, k_end - k0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+      sx[e] = tb[3 * (size_t)(k0 + e)];
+      sy[e] = tb[3 * (size_t)(k0 + e) + 1];
+      sz[e] = tb[3 * (size_t)(k0 + e) + 2];
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int e = 0; e < cnt; ++e) {
+      float dx = __fsub_rn(sx[e], x1), dy = __fsub_rn(sy[e], y1), dz = __fsub_rn(sz[e], z1);
+      float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (d < bd) bd = d, bi = k0 + e;
+    }
+  }
+  if (j < n && k_begin < k_end) {
+    unsigned long long packed = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned int)bi;
+    atomicMin(best + (size_t)b * n + j, packed);
+  }
+}
+
+__global__ void k_unpack(const unsigned long long* __restrict__ best, long long total, float* __restrict__ dist,
+                         int* __restrict__ idx) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+    unsigned long long p = best[i];
+    dist[i] = __uint_as_float((unsigned int)(p >> 32));
+    idx[i] = (int)(unsigned int)(p & 0xffffffffu);
+  }
+}
+
+// grad_a[j] += 2 g[j] (a_j - b_idx[j]);  grad_b[idx[j]] -= the same  (chamfer_distance.cu:158-187)
+__global__ void k_chamfer_grad(const float* __restrict__ a, int n, const float* __restrict__ bpts, int m,
+                               const float* __restrict__ g, const int* __restrict__ idx, int B,
+                               float* __restrict__ grad_a, float* __restrict__ grad_b) {
+  long long total = (long long)B * n;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
+    long long bi = e / n;
+    int j2 = idx[e];
+    const float* pa = a + 3 * e;
+    const float* pb = bpts + 3 * ((size_t)bi * m + j2);
+    float gg = g[e] * 2.f;
+    float dx = gg * (pa[0] - pb[0]), dy = gg * (pa[1] - pb[1]), dz = gg * (pa[2] - pb[2]);
+    atomicAdd(grad_a + 3 * e, dx), atomicAdd(grad_a + 3 * e + 1, dy), atomicAdd(grad_a + 3 * e + 2, dz);
+    float* gb = grad_b + 3 * ((size_t)bi * m + j2);
+    atomicAdd(gb, -dx), atomicAdd(gb + 1, -dy), atomicAdd(gb + 2, -dz);
+  }
+}
+
+int one_way(const float* q, int n, const float* t, int m, int B, float* dist, int* idx, unsigned long long* scratch,
+            cudaStream_t stream) {
+  cudaMemsetAsync(scratch, 0xff, (size_t)B * n * 8, stream);
+  int qblocks = cdiv(n, 256);
+  // enough CTAs for ~4 waves of 148 SMs x 8 resident blocks, but at least one tile per split
+  int want = (148 * 8 * 4 + qblocks * B - 1) / (qblocks * B);
+  int max_splits = cdiv(m, TILE);
+  int splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
+  if (splits > 65535) splits = 65535;
+  int chunk = cdiv(cdiv(m, splits), TILE) * TILE;
+  splits = cdiv(m, chunk);
+  k_chamfer_nn<<<dim3(qblocks, splits, B), 256, 0, stream>>>(q, n, t, m, chunk, scratch);
+  k_unpack<<<grid_for((long long)B * n, 256), 256, 0, stream>>>(scratch, (long long)B * n, dist, idx);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t pcab_chamfer_workspace(int B, int n, int m) { return (size_t)B * (n > m ? n : m) * 8 + 256; }
+
+extern "C" int pcab_chamfer_forward(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1,
+                                    float* dist2, int* idx1, int* idx2, void* workspace, size_t workspace_bytes,
+                                    cudaStream_t stream) {
+  PCAB_REQUIRE(B > 0 && n > 0 && m > 0, "empty point sets");
+  PCAB_REQUIRE(workspace_bytes >= pcab_chamfer_workspace(B, n, m), "workspace too small");
+  one_way(xyz1, n, xyz2, m, B, dist1, idx1, (unsigned long long*)workspace, stream);
+  one_way(xyz2, m, xyz1, n, B, dist2, idx2, (unsigned long long*)workspace, stream);
+  PCAB_CHECK_LAUNCH("pcab_chamfer_forward");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_chamfer_backward(const float* xyz1, const float* xyz2, int B, int n, int m, const float* grad_dist1,
+                                     const float* grad_dist2, const int* idx1, const int* idx2, float* grad_xyz1,
+                                     float* grad_xyz2, cudaStream_t stream) {
+  PCAB_CUDA(cudaMemsetAsync(grad_xyz1, 0, (size_t)B * n * 12, stream));
+  PCAB_CUDA(cudaMemsetAsync(grad_xyz2, 0, (size_t)B * m * 12, stream));
+  k_chamfer_grad<<<grid_for((long long)B * n, 256), 256, 0, stream>>>(xyz1, n, xyz2, m, grad_dist1, idx1, B, grad_xyz1,
+                                                                     grad_xyz2);
+  k_chamfer_grad<<<grid_for((long long)B * m, 256), 256, 0, stream>>>(xyz2, m, xyz1, n, grad_dist2, idx2, B, grad_xyz2,
+                                                                     grad_xyz1);
+  PCAB_CHECK_LAUNCH("pcab_chamfer_backward");
+  return PCAB_OK;
+}

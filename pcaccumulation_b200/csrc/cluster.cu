@@ -1,0 +1,335 @@
+// Instance proposal on the GPU: offset-shifted dynamic points -> 5 cm hash de-duplication -> DBSCAN
+// (eps / min_samples) with sklearn's label semantics -> small-cluster rejection -> canonical labels.
+//
+// Replaces models/cluster.py:9-13 (voxel_downsample), :23-49 (cluster), :52-84 (cluster_per_batch),
+// torchsparse.utils.quantize.sparse_quantize (spec: dataset_toolbox/prep_nuscene_waymo_sf/libs/
+// spv_utils.py:7-20,57-60,81), sklearn.cluster.DBSCAN and toolbox/utils.py:237-250
+// (canonicalise_random_indice).  The reference round-trips through host numpy/sklearn here; this
+// version stays on the device.
+//
+// Semantics reproduced exactly:
+//   * de-dup key = ravel hash of floor(round(q / 0.05)) over x,y,z; survivor = FIRST occurrence of each key,
+//     survivors ordered by ascending key (np.unique);
+//   * DBSCAN on the survivors with z := 0: core = >= min_samples neighbours within eps INCLUDING self
+//     (float64 distances); clusters numbered by ascending index of their lowest-index core point; a border
+//     point joins the lowest-numbered cluster that has a core neighbour of it; noise = -1;
+//   * clusters with < min_p_cluster survivors -> noise; kept clusters renumbered 1..L in ascending order,
+//     noise/background = 0.
+#include <cub/cub.cuh>
+#include "common.cuh"
+#include "pcab200.h"
+
+namespace {
+
+struct Counts {  // device-side bookkeeping
+  int mn[3], mx[3];
+  int n_unique;
+  int n_clusters;
+  int n_kept;
+};
+
+__global__ void k_dyn_flag(const float* __restrict__ mos, int n0, int n, int* __restrict__ flag) {
+  int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    flag[i] = mos[2 * (n0 + i) + 1] > mos[2 * (n0 + i)] ? 1 : 0;  // argmax == 1 (first max wins ties)
+}
+
+__global__ void k_quant(const float* __restrict__ tp, const float* __restrict__ off, const int* __restrict__ sel, int n0,
+                        int s, float voxel, float* __restrict__ q, int* __restrict__ c, Counts* cnt) {
+  int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < s; j += stride) {
+    int i = n0 + sel[j];
+    float x = __fadd_rn(tp[3 * i], off[2 * i]), y = __fadd_rn(tp[3 * i + 1], off[2 * i + 1]), z = tp[3 * i + 2];
+    q[3 * j] = x, q[3 * j + 1] = y, q[3 * j + 2] = z;
+    int cx = (int)rintf(__fdiv_rn(x, voxel)), cy = (int)rintf(__fdiv_rn(y, voxel)), cz = (int)rintf(__fdiv_rn(z, voxel));
+    c[3 * j] = cx, c[3 * j + 1] = cy, c[3 * j + 2] = cz;
+    atomicMin(&cnt->mn[0], cx), atomicMin(&cnt->mn[1], cy), atomicMin(&cnt->mn[2], cz);
+    atomicMax(&cnt->mx[0], cx), atomicMax(&cnt->mx[1], cy), atomicMax(&cnt->mx[2], cz);
+  }
+}
+
+__global__ void k_init_counts(Counts* c) {
+  for (int k = 0; k < 3; ++k) c->mn[k] = INT_MAX, c->mx[k] = INT_MIN;
+  c->n_unique = c->n_clusters = c->n_kept = 0;
+}
+
+__global__ void k_hash(const int* __restrict__ c, int s, const Counts* __restrict__ cnt,
+                       unsigned long long* __restrict__ key, int* __restrict__ val) {
+  int stride = gridDim.x * blockDim.x;
+  unsigned long long ry = (unsigned long long)(cnt->mx[1] - cnt->mn[1]) + 1ull;
+  unsigned long long rz = (unsigned long long)(cnt->mx[2] - cnt->mn[2]) + 1ull;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < s; j += stride) {
+    unsigned long long h = (unsigned long long)(c[3 * j] - cnt->mn[0]);
+    h *= ry;
+    h += (unsigned long long)(c[3 * j + 1] - cnt->mn[1]);
+    h *= rz;
+    h += (unsigned long long)(c[3 * j + 2] - cnt->mn[2]);
+    key[j] = h;
+    val[j] = j;
+  }
+}
+
+__global__ void k_heads(const unsigned long long* __restrict__ key_sorted, int s, int* __restrict__ head) {
+  int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < s; j += stride)
+    head[j] = (j == 0 || key_sorted[j] != key_sorted[j - 1]) ? 1 : 0;
+}
+
+// uid[j] (inclusive-scan(head) - 1) -> survivors (xy of the run head) and inverse map
+__global__ void k_unique(const int* __restrict__ head, const int* __restrict__ rank_excl,
+                         const int* __restrict__ val_sorted, const float* __restrict__ q, int s, float* __restrict__ pxy,
+                         int* __restrict__ inverse, Counts* cnt) {
+  int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < s; j += stride) {
+    int u = rank_excl[j] + head[j] - 1;
+    int orig = val_sorted[j];
+    inverse[orig] = u;
+    if (head[j]) pxy[2 * u] = q[3 * orig], pxy[2 * u + 1] = q[3 * orig + 1];
+    if (j == s - 1) cnt->n_unique = u + 1;
+  }
+}
+
+__device__ __forceinline__ unsigned int cell_key(int cx, int cy) { return ((unsigned int)cy << 16) | (unsigned int)cx; }
+
+__global__ void k_cellkeys(const float* __restrict__ pxy, const Counts* __restrict__ cnt, float voxel, float eps,
+                           int cap, unsigned int* __restrict__ ckey, int* __restrict__ cval) {
+  int U = cnt->n_unique;
+  float x0 = (float)cnt->mn[0] * voxel - 1.f, y0 = (float)cnt->mn[1] * voxel - 1.f;
+  int stride = gridDim.x * blockDim.x;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < cap; u += stride) {
+    if (u < U) {
+      int cx = (int)floorf((pxy[2 * u] - x0) / eps) + 1, cy = (int)floorf((pxy[2 * u + 1] - y0) / eps) + 1;
+      ckey[u] = cell_key(cx, cy);
+    } else {
+      ckey[u] = 0xffffffffu;  // padding sorts last
+    }
+    cval[u] = u;
+  }
+}
+
+__device__ __forceinline__ int lower_bound(const unsigned int* a, int n, unsigned int v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <typename F>
+__device__ __forceinline__ void for_neighbors(int u, const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
+                                              const int* __restrict__ cval_sorted, int U, unsigned int mykey, double eps,
+                                              F&& fn) {
+  int cx = mykey & 0xffff, cy = mykey >> 16;
+  double x = pxy[2 * u], y = pxy[2 * u + 1];
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      unsigned int k = cell_key(cx + dx, cy + dy);
+      for (int j = lower_bound(ckey_sorted, U, k); j < U && ckey_sorted[j] == k; ++j) {
+        int v = cval_sorted[j];
+        double ex = (double)pxy[2 * v] - x, ey = (double)pxy[2 * v + 1] - y;
+        if (sqrt(ex * ex + ey * ey) <= eps) fn(v);
+      }
+    }
+}
+
+__global__ void k_core(const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
+                       const int* __restrict__ cval_sorted, const Counts* __restrict__ cnt, double eps, int min_samples,
+                       int* __restrict__ key_of /* unsorted cell key per point */, int* __restrict__ core,
+                       int* __restrict__ parent) {
+  int U = cnt->n_unique;
+  int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < U; j += stride) {
+    int u = cval_sorted[j];
+    key_of[u] = (int)ckey_sorted[j];
+    int c = 0;
+    for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, ckey_sorted[j], eps, [&](int) { ++c; });
+    core[u] = c >= min_samples;
+    parent[u] = u;
+  }
+}
+
+__device__ int uf_find(int* parent, int i) {
+  while (true) {
+    int p = parent[i];
+    if (p == i) return i;
+    int gp = parent[p];
+    if (gp != p) parent[i] = gp;
+    i = p;
+  }
+}
+
+__device__ void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a), b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }  // link the larger root under the smaller one
+    int old = atomicCAS(parent + a, a, b);
+    if (old == a) return;
+  }
+}
+
+__global__ void k_union(const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
+                        const int* __restrict__ cval_sorted, const Counts* __restrict__ cnt, double eps,
+                        const int* __restrict__ key_of, const int* __restrict__ core, int* __restrict__ parent) {
+  int U = cnt->n_unique;
+  int stride = gridDim.x * blockDim.x;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += stride) {
+    if (!core[u]) continue;
+    for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, (unsigned int)key_of[u], eps, [&](int v) {
+      if (v < u && core[v]) uf_union(parent, u, v);
+    });
+  }
+}
+
+__global__ void k_roots(const Counts* __restrict__ cnt, const int* __restrict__ core, int* __restrict__ parent,
+                        int* __restrict__ is_root, int cap) {
+  int U = cnt->n_unique;
+  int stride = gridDim.x * blockDim.x;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < cap; u += stride) {
+    int r = 0;
+    if (u < U && core[u]) {
+      int root = uf_find(parent, u);
+      parent[u] = root;
+      r = root == u;
+    }
+    is_root[u] = r;
+  }
+}
+
+// label[u]: core -> cluster number of its root; border -> min cluster number among core neighbours; noise -> -1
+__global__ void k_labels(const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
+                         const int* __restrict__ cval_sorted, Counts* cnt, double eps, const int* __restrict__ key_of,
+                         const int* __restrict__ core, const int* __restrict__ parent, const int* __restrict__ root_rank,
+                         const int* __restrict__ is_root, int cap, int* __restrict__ label, int* __restrict__ size) {
+  int U = cnt->n_unique;
+  int stride = gridDim.x * blockDim.x;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += stride) {
+    int l = -1;
+    if (core[u]) {
+      l = root_rank[parent[u]];
+    } else {
+      int best = INT_MAX;
+      for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, (unsigned int)key_of[u], eps, [&](int v) {
+        if (core[v]) best = min(best, root_rank[parent[v]]);
+      });
+      if (best != INT_MAX) l = best;
+    }
+    label[u] = l;
+    if (l >= 0) atomicAdd(size + l, 1);
+    if (u == 0) cnt->n_clusters = root_rank[cap - 1] + is_root[cap - 1];
+  }
+}
+
+__global__ void k_keep(const int* __restrict__ size, const Counts* __restrict__ cnt, int min_p, int cap,
+                       int* __restrict__ keep) {
+  int stride = gridDim.x * blockDim.x;
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < cap; l += stride)
+    keep[l] = (l < cnt->n_clusters && size[l] >= min_p) ? 1 : 0;
+}
+
+__global__ void k_final(const int* __restrict__ label, const int* __restrict__ keep, const int* __restrict__ keep_rank,
+                        const int* __restrict__ inverse, const int* __restrict__ sel, int n0, int s, int cap, Counts* cnt,
+                        long long* __restrict__ inst_out) {
+  int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < s; j += stride) {
+    int l = label[inverse[j]];
+    inst_out[n0 + sel[j]] = (l >= 0 && keep[l]) ? (long long)(keep_rank[l] + 1) : 0;
+    if (j == 0) cnt->n_kept = keep_rank[cap - 1] + keep[cap - 1];
+  }
+}
+
+size_t alc(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" size_t pcab_cluster_workspace(int s) {
+  size_t sort64 = 0, sort32 = 0, scan = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort64, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (int*)nullptr, (int*)nullptr, s);
+  cub::DeviceRadixSort::SortPairs(nullptr, sort32, (unsigned int*)nullptr, (unsigned int*)nullptr, (int*)nullptr,
+                                  (int*)nullptr, s);
+  cub::DeviceScan::ExclusiveSum(nullptr, scan, (int*)nullptr, (int*)nullptr, s);
+  size_t tmp = sort64 > sort32 ? sort64 : sort32;
+  if (scan > tmp) tmp = scan;
+  // q 3s f | c 3s i | key 2x s u64 | val 2x s | head,rank s | pxy 2s f | inverse s | ckey 2x s | cval 2x s |
+  // key_of, core, parent, is_root, root_rank, label, size, keep, keep_rank (9 s) | counts
+  return alc((size_t)s * 12) * 2 + alc((size_t)s * 8) * 2 + alc((size_t)s * 4) * 20 + alc(tmp) + alc(sizeof(Counts)) + 1024;
+}
+
+// flags[i] = argmax(mos[n0+i]) == 1 for i in [0, n)
+extern "C" int pcab_dynamic_flags(const float* mos, int n0, int n, int* flags, cudaStream_t stream) {
+  k_dyn_flag<<<grid_for(n, 256), 256, 0, stream>>>(mos, n0, n, flags);
+  PCAB_CHECK_LAUNCH("pcab_dynamic_flags");
+  return PCAB_OK;
+}
+
+// sel[0..s): ascending indices (relative to n0) of the selected points of one scene.  Writes inst_out[n0+sel[j]]
+// (the caller zero-fills inst_out) and counts_out[0] = number of kept clusters (device int).
+extern "C" int pcab_cluster_scene(const float* transformed_points, const float* offset, const int* sel, int n0, int s,
+                                  float dedupe_voxel, double eps, int min_samples, int min_p_cluster,
+                                  long long* inst_out, int* n_instances_out, void* workspace, size_t workspace_bytes,
+                                  cudaStream_t stream) {
+  PCAB_REQUIRE(s > 0, "empty selection");
+  PCAB_REQUIRE(workspace_bytes >= pcab_cluster_workspace(s), "workspace too small");
+  char* w = (char*)workspace;
+  auto take = [&](size_t bytes) {
+    char* p = w;
+    w += alc(bytes);
+    return (void*)p;
+  };
+  float* q = (float*)take((size_t)s * 12);
+  int* c = (int*)take((size_t)s * 12);
+  unsigned long long* key = (unsigned long long*)take((size_t)s * 8);
+  unsigned long long* key_s = (unsigned long long*)take((size_t)s * 8);
+  int* val = (int*)take((size_t)s * 4);
+  int* val_s = (int*)take((size_t)s * 4);
+  int* head = (int*)take((size_t)s * 4);
+  int* rank = (int*)take((size_t)s * 4);
+  float* pxy = (float*)take((size_t)s * 8);
+  (void)take((size_t)s * 4);
+  int* inverse = (int*)take((size_t)s * 4);
+  unsigned int* ckey = (unsigned int*)take((size_t)s * 4);
+  unsigned int* ckey_s = (unsigned int*)take((size_t)s * 4);
+  int* cval = (int*)take((size_t)s * 4);
+  int* cval_s = (int*)take((size_t)s * 4);
+  int* key_of = (int*)take((size_t)s * 4);
+  int* core = (int*)take((size_t)s * 4);
+  int* parent = (int*)take((size_t)s * 4);
+  int* is_root = (int*)take((size_t)s * 4);
+  int* root_rank = (int*)take((size_t)s * 4);
+  int* label = (int*)take((size_t)s * 4);
+  int* size = (int*)take((size_t)s * 4);
+  int* keep = (int*)take((size_t)s * 4);
+  int* keep_rank = (int*)take((size_t)s * 4);
+  Counts* cnt = (Counts*)take(sizeof(Counts));
+  size_t sort64 = 0, sort32 = 0, scan = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort64, key, key_s, val, val_s, s);
+  cub::DeviceRadixSort::SortPairs(nullptr, sort32, ckey, ckey_s, cval, cval_s, s);
+  cub::DeviceScan::ExclusiveSum(nullptr, scan, head, rank, s);
+  void* tmp = w;
+
+  const int B = 256;
+  int g = grid_for(s, B);
+  k_init_counts<<<1, 1, 0, stream>>>(cnt);
+  k_quant<<<g, B, 0, stream>>>(transformed_points, offset, sel, n0, s, dedupe_voxel, q, c, cnt);
+  k_hash<<<g, B, 0, stream>>>(c, s, cnt, key, val);
+  PCAB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, sort64, key, key_s, val, val_s, s, 0, 64, stream));
+  k_heads<<<g, B, 0, stream>>>(key_s, s, head);
+  PCAB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, scan, head, rank, s, stream));
+  k_unique<<<g, B, 0, stream>>>(head, rank, val_s, q, s, pxy, inverse, cnt);
+  k_cellkeys<<<g, B, 0, stream>>>(pxy, cnt, dedupe_voxel, (float)eps * 1.001f, s, ckey, cval);
+  PCAB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, sort32, ckey, ckey_s, cval, cval_s, s, 0, 32, stream));
+  k_core<<<g, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, min_samples, key_of, core, parent);
+  k_union<<<g, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, key_of, core, parent);
+  k_roots<<<g, B, 0, stream>>>(cnt, core, parent, is_root, s);
+  PCAB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, scan, is_root, root_rank, s, stream));
+  PCAB_CUDA(cudaMemsetAsync(size, 0, (size_t)s * 4, stream));
+  k_labels<<<g, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, key_of, core, parent, root_rank, is_root, s, label, size);
+  k_keep<<<g, B, 0, stream>>>(size, cnt, min_p_cluster, s, keep);
+  PCAB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, scan, keep, keep_rank, s, stream));
+  k_final<<<g, B, 0, stream>>>(label, keep, keep_rank, inverse, sel, n0, s, s, cnt, inst_out);
+  PCAB_CUDA(cudaMemcpyAsync(n_instances_out, &cnt->n_kept, sizeof(int), cudaMemcpyDeviceToDevice, stream));
+  PCAB_CHECK_LAUNCH("pcab_cluster_scene");
+  return PCAB_OK;
+}

@@ -1,0 +1,321 @@
+// FP32 CUDA-core convolutions on NHWC activations: exact-order-free but full-precision path.
+//
+// conv3x3 (pad 1) with up to three input sources accumulated into one output.  The multi-source form
+// covers, without materialising anything:
+//   * plain Conv2d                                  (models/unet.py:11-20)           1 source
+//   * Conv2d over torch.cat((up, skip), 1)          (models/unet.py:106-111)         2 sources
+//   * Conv3d 3x3x3 over [B,C,T,H,W]                 (models/stpn.py:13-22)           3 sources = frames t-1,t,t+1
+// plus ConvTranspose2d(k=2,s=2) (models/unet.py:22-28), MaxPool2d(2) and the temporal max of
+// models/stpn.py:80.  Epilogue: bias, optional BatchNorm(eval) scale/shift (models/unet.py:264-269), ReLU.
+//
+// These kernels are the full-precision reference path inside the product (used for layers whose shape
+// does not suit the tcgen05 tiles and as the on-device cross-check of the tensor-core path).
+#include "common.cuh"
+#include "pcab200.h"
+
+namespace {
+
+constexpr int CK = 16;  // input channels staged per chunk
+
+struct ConvArgs {
+  const float* src[3];
+  int src_c[3];      // channels of each source
+  int frame_shift[3];  // conv3d: source image index = n + shift, valid iff 0 <= (n % T) + shift < T
+  int nsrc;
+  int T;             // frames per scene for the temporal validity test (1 = plain 2-D)
+  const float* w;    // per source block [9][C_s][Cout], blocks concatenated
+  const float* bias;
+  const float* bn_scale;  // optional: y = (acc + bias) * scale + shift
+  const float* bn_shift;
+  float* out;
+  int N, H, W, Cout;
+  int out_cstride, out_coff;
+  int relu;
+};
+
+template <int TH, int TW, int COT>
+__global__ void __launch_bounds__((TH * TW / 4) * (COT / 16)) k_conv3x3(ConvArgs a) {
+  constexpr int NPG = TH * TW / 4;   // pixel groups (4 consecutive x)
+  constexpr int NT = NPG * (COT / 16);
+  constexpr int PH = TH + 2, PW = TW + 4;  // patch pitch padded to a multiple of 4
+  extern __shared__ float smem[];
+  float* s_in = smem;                      // [CK][PH][PW]
+  float* s_w = smem + CK * PH * PW;        // [9][CK][COT]
+
+  const int tiles_x = (a.W + TW - 1) / TW;
+  const int tile = blockIdx.x;
+  const int ty0 = (tile / tiles_x) * TH, tx0 = (tile % tiles_x) * TW;
+  const int n = blockIdx.z;
+  const int co0 = blockIdx.y * COT;
+  const int tid = threadIdx.x;
+  const int pg = tid % NPG, cg = tid / NPG;
+  const int py = pg / (TW / 4), px = (pg % (TW / 4)) * 4;
+
+  float acc[4][16];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[p][o] = 0.f;
+
+  int w_row0 = 0;  // running row offset (in units of [C_s] rows) into the packed weights
+  size_t w_base = 0;
+  for (int s = 0; s < a.nsrc; ++s) {
+    const int Cs = a.src_c[s];
+    const int tt = (a.T > 1) ? (n % a.T) + a.frame_shift[s] : 0;
+    const bool valid = (a.T <= 1) || (tt >= 0 && tt < a.T);
+    if (valid) {
+      const float* img = a.src[s] + (size_t)(n + a.frame_shift[s]) * a.H * a.W * Cs;
+      for (int c0 = 0; c0 < Cs; c0 += CK) {
+        __syncthreads();
+        // stage the input patch: (TH+2) x (TW+2) pixels x CK channels, channel-planar in smem
+        for (int e = tid; e < PH * (TW + 2) * (CK / 4); e += NT) {
+          int q = e % (CK / 4);
+          int pix = e / (CK / 4);
+          int r = pix / (TW + 2), cx = pix % (TW + 2);
+          int gy = ty0 + r - 1, gx = tx0 + cx - 1;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && c0 + 4 * q < Cs)
+            v = *reinterpret_cast<const float4*>(img + ((size_t)gy * a.W + gx) * Cs + c0 + 4 * q);
+          float* d = s_in + (4 * q) * PH * PW + r * PW + cx;
+          d[0] = v.x, d[PH * PW] = v.y, d[2 * PH * PW] = v.z, d[3 * PH * PW] = v.w;
+        }
+        // stage weights [9][CK][COT]
+        for (int e = tid; e < 9 * CK * (COT / 4); e += NT) {
+          int o4 = e % (COT / 4);
+          int k = (e / (COT / 4)) % CK;
+          int tap = e / ((COT / 4) * CK);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c0 + k < Cs && co0 + 4 * o4 < a.Cout)
+            v = *reinterpret_cast<const float4*>(a.w + w_base + ((size_t)tap * Cs + c0 + k) * a.Cout + co0 + 4 * o4);
+          *reinterpret_cast<float4*>(s_w + (tap * CK + k) * COT + 4 * o4) = v;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int k = 0; k < CK; ++k) {
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const float* row = s_in + k * PH * PW + (py + ky) * PW + px;
+            float4 i0 = *reinterpret_cast<const float4*>(row);
+            float2 i1 = *reinterpret_cast<const float2*>(row + 4);
+            float in[6] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y};
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const float4* w4 = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * CK + k) * COT + cg * 16);
+#pragma unroll
+              for (int o4 = 0; o4 < 4; ++o4) {
+                float4 w = w4[o4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                  float x = in[p + kx];
+                  acc[p][4 * o4 + 0] = fmaf(x, w.x, acc[p][4 * o4 + 0]);
+                  acc[p][4 * o4 + 1] = fmaf(x, w.y, acc[p][4 * o4 + 1]);
+                  acc[p][4 * o4 + 2] = fmaf(x, w.z, acc[p][4 * o4 + 2]);
+                  acc[p][4 * o4 + 3] = fmaf(x, w.w, acc[p][4 * o4 + 3]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    w_base += (size_t)9 * Cs * a.Cout;
+    w_row0 += Cs;
+  }
+  (void)w_row0;
+  // epilogue
+  const int gy = ty0 + py;
+  if (gy >= a.H) return;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    int gx = tx0 + px + p;
+    if (gx >= a.W) continue;
+    float* o = a.out + (((size_t)n * a.H + gy) * a.W + gx) * a.out_cstride + a.out_coff + co0 + cg * 16;
+#pragma unroll
+    for (int o4 = 0; o4 < 4; ++o4) {
+      int co = co0 + cg * 16 + 4 * o4;
+      if (co >= a.Cout) continue;
+      float r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v = acc[p][4 * o4 + u] + a.bias[co + u];
+        if (a.bn_scale) v = fmaf(v, a.bn_scale[co + u], a.bn_shift[co + u]);
+        r[u] = a.relu ? fmaxf(v, 0.f) : v;
+      }
+      if (co + 3 < a.Cout) {
+        *reinterpret_cast<float4*>(o + 4 * o4) = make_float4(r[0], r[1], r[2], r[3]);
+      } else {
+        for (int u = 0; u < 4 && co + u < a.Cout; ++u) o[4 * o4 + u] = r[u];
+      }
+    }
+  }
+}
+
+// ConvTranspose2d(kernel 2, stride 2): out[n, 2y+dy, 2x+dx, co] = b[co] + sum_ci in[n,y,x,ci] * W[dy*2+dx][ci][co]
+// Thread tile: 1 input pixel x 4 taps x 8 couts; CTA: 64 pixels x 32 couts, 256 threads.
+__global__ void __launch_bounds__(256) k_convT2x2(const float* __restrict__ in, const float* __restrict__ w,
+                                                  const float* __restrict__ bias, float* __restrict__ out, int npix_in,
+                                                  int H, int W, int Cin, int Cout, int out_cstride, int out_coff) {
+  __shared__ float s_in[64][CK + 1];
+  __shared__ float s_w[4][CK][32];
+  const int tid = threadIdx.x;
+  const int pl = tid & 63, cg = tid >> 6;  // 4 cout groups of 8
+  const int p0 = blockIdx.x * 64;
+  const int co0 = blockIdx.y * 32;
+  float acc[4][8];
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[t][o] = 0.f;
+  for (int c0 = 0; c0 < Cin; c0 += CK) {
+    __syncthreads();
+    for (int e = tid; e < 64 * CK; e += 256) {
+      int k = e % CK, p = e / CK;
+      s_in[p][k] = (p0 + p < npix_in) ? in[(size_t)(p0 + p) * Cin + c0 + k] : 0.f;
+    }
+    for (int e = tid; e < 4 * CK * 32; e += 256) {
+      int o = e % 32, k = (e / 32) % CK, t = e / (32 * CK);
+      s_w[t][k][o] = (co0 + o < Cout) ? w[((size_t)t * Cin + c0 + k) * Cout + co0 + o] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CK; ++k) {
+      float x = s_in[pl][k];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float4* w4 = reinterpret_cast<const float4*>(&s_w[t][k][cg * 8]);
+        float4 w0 = w4[0], w1 = w4[1];
+        acc[t][0] = fmaf(x, w0.x, acc[t][0]);
+        acc[t][1] = fmaf(x, w0.y, acc[t][1]);
+        acc[t][2] = fmaf(x, w0.z, acc[t][2]);
+        acc[t][3] = fmaf(x, w0.w, acc[t][3]);
+        acc[t][4] = fmaf(x, w1.x, acc[t][4]);
+        acc[t][5] = fmaf(x, w1.y, acc[t][5]);
+        acc[t][6] = fmaf(x, w1.z, acc[t][6]);
+        acc[t][7] = fmaf(x, w1.w, acc[t][7]);
+      }
+    }
+  }
+  int p = p0 + pl;
+  if (p >= npix_in) return;
+  int n = p / (H * W), rem = p % (H * W), y = rem / W, x = rem % W;
+  int co = co0 + cg * 8;
+  if (co >= Cout) return;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    int oy = 2 * y + (t >> 1), ox = 2 * x + (t & 1);
+    float* o = out + (((size_t)n * 2 * H + oy) * (2 * W) + ox) * out_cstride + out_coff + co;
+    float4 r0 = make_float4(acc[t][0] + bias[co], acc[t][1] + bias[co + 1], acc[t][2] + bias[co + 2],
+                            acc[t][3] + bias[co + 3]);
+    float4 r1 = make_float4(acc[t][4] + bias[co + 4], acc[t][5] + bias[co + 5], acc[t][6] + bias[co + 6],
+                            acc[t][7] + bias[co + 7]);
+    reinterpret_cast<float4*>(o)[0] = r0;
+    reinterpret_cast<float4*>(o)[1] = r1;
+  }
+}
+
+__global__ void k_maxpool2(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C) {
+  int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  long long total = (long long)N * Ho * Wo * C4;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
+    int c = (int)(e % C4);
+    long long r = e / C4;
+    int x = (int)(r % Wo);
+    r /= Wo;
+    int y = (int)(r % Ho);
+    int n = (int)(r / Ho);
+    const float4* p = reinterpret_cast<const float4*>(in + (((size_t)n * H + 2 * y) * W + 2 * x) * C) + c;
+    float4 a = p[0], b = p[C4], d = p[(size_t)W * C4], f = p[(size_t)W * C4 + C4];
+    float4 m = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, f.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, f.y)),
+                           fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, f.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, f.w)));
+    reinterpret_cast<float4*>(out)[e] = m;
+  }
+}
+
+// max over the T frames of each scene: in [B*T, HW, C] -> out [B, HW, C]
+__global__ void k_temporal_max(const float* __restrict__ in, float* __restrict__ out, int B, int T, long long hwc4) {
+  long long total = (long long)B * hwc4;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
+    long long b = e / hwc4, r = e % hwc4;
+    const float4* p = reinterpret_cast<const float4*>(in) + (size_t)b * T * hwc4 + r;
+    float4 m = p[0];
+    for (int t = 1; t < T; ++t) {
+      float4 v = p[(size_t)t * hwc4];
+      m.x = fmaxf(m.x, v.x), m.y = fmaxf(m.y, v.y), m.z = fmaxf(m.z, v.z), m.w = fmaxf(m.w, v.w);
+    }
+    reinterpret_cast<float4*>(out)[e] = m;
+  }
+}
+
+template <int TH, int TW, int COT>
+int launch_conv(const ConvArgs& a, cudaStream_t stream) {
+  constexpr int NT = (TH * TW / 4) * (COT / 16);
+  size_t smem = (size_t)(CK * (TH + 2) * (TW + 4) + 9 * CK * COT) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_conv3x3<TH, TW, COT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  dim3 grid(cdiv(a.H, TH) * cdiv(a.W, TW), cdiv(a.Cout, COT), a.N);
+  k_conv3x3<TH, TW, COT><<<grid, NT, smem, stream>>>(a);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int pcab_conv3x3_f32(const float* src0, int c0, const float* src1, int c1, const float* src2, int c2,
+                                int temporal_T, const float* weight_packed, const float* bias, const float* bn_scale,
+                                const float* bn_shift, int relu, float* out, int n_images, int H, int W, int Cout,
+                                int out_cstride, int out_coff, cudaStream_t stream) {
+  ConvArgs a;
+  a.src[0] = src0, a.src[1] = src1, a.src[2] = src2;
+  a.src_c[0] = c0, a.src_c[1] = c1, a.src_c[2] = c2;
+  a.nsrc = src2 ? 3 : (src1 ? 2 : 1);
+  a.T = temporal_T > 1 ? temporal_T : 1;
+  if (a.T > 1) {
+    PCAB_REQUIRE(a.nsrc == 3 && src0 == src1 && src1 == src2, "temporal mode takes the same tensor three times");
+    a.frame_shift[0] = -1, a.frame_shift[1] = 0, a.frame_shift[2] = 1;
+  } else {
+    a.frame_shift[0] = a.frame_shift[1] = a.frame_shift[2] = 0;
+  }
+  PCAB_REQUIRE(c0 % 4 == 0 && c1 % 4 == 0 && c2 % 4 == 0, "channel counts must be multiples of 4");
+  PCAB_REQUIRE(out_cstride % 4 == 0 && out_coff % 4 == 0 || Cout < 4, "output channel layout must be 16B aligned");
+  a.w = weight_packed, a.bias = bias, a.bn_scale = bn_scale, a.bn_shift = bn_shift, a.relu = relu;
+  a.out = out, a.N = n_images, a.H = H, a.W = W, a.Cout = Cout, a.out_cstride = out_cstride, a.out_coff = out_coff;
+  if (H * W >= 96 * 96 && Cout <= 32)
+    launch_conv<16, 32, 32>(a, stream);
+  else if (H * W >= 64 * 64)
+    launch_conv<8, 32, 64>(a, stream);
+  else
+    launch_conv<8, 16, 64>(a, stream);
+  PCAB_CHECK_LAUNCH("pcab_conv3x3_f32");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_convT2x2_f32(const float* in, const float* weight_packed, const float* bias, float* out,
+                                 int n_images, int H, int W, int Cin, int Cout, int out_cstride, int out_coff,
+                                 cudaStream_t stream) {
+  PCAB_REQUIRE(Cin % 16 == 0 && Cout % 8 == 0, "Cin%16, Cout%8");
+  int npix = n_images * H * W;
+  dim3 grid(cdiv(npix, 64), cdiv(Cout, 32));
+  k_convT2x2<<<grid, 256, 0, stream>>>(in, weight_packed, bias, out, npix, H, W, Cin, Cout, out_cstride, out_coff);
+  PCAB_CHECK_LAUNCH("pcab_convT2x2_f32");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_maxpool2x2(const float* in, float* out, int n_images, int H, int W, int C, cudaStream_t stream) {
+  PCAB_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "C%4, even H/W");
+  long long total = (long long)n_images * (H / 2) * (W / 2) * (C / 4);
+  k_maxpool2<<<grid_for(total, 256), 256, 0, stream>>>(in, out, n_images, H, W, C);
+  PCAB_CHECK_LAUNCH("pcab_maxpool2x2");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_temporal_max(const float* in, float* out, int B, int T, int H, int W, int C, cudaStream_t stream) {
+  PCAB_REQUIRE(C % 4 == 0, "C%4");
+  long long hwc4 = (long long)H * W * C / 4;
+  k_temporal_max<<<grid_for(B * hwc4, 256), 256, 0, stream>>>(in, out, B, T, hwc4);
+  PCAB_CHECK_LAUNCH("pcab_temporal_max");
+  return PCAB_OK;
+}

@@ -1,0 +1,500 @@
+// Per-point stages: index compaction, bilinear feature pickup (ungrid), the STPN point head and the
+// TubeNet (TPointNet) embeddings / pose regression / rigid reconstruction.
+//
+// Replaces models/pillar_encoder.py:206-267 (temporal_ungrid / ungrid), models/stpn.py:91-103 (point
+// decoder), models/tpointnet.py:211-305 (TPointNet.forward, batch_quat2mat :20-40),
+// toolbox/se3_utils.py:44-64 (quat2mat), toolbox/register_utils.py:72-93 (reconstruct_sequence) and the
+// torch_scatter segment max / mean calls inside them.
+#include <cub/cub.cuh>
+#include "mlp.cuh"
+#include "pcab200.h"
+
+namespace {
+
+using mlp::PTS;
+
+__global__ void k_select_write(const int* __restrict__ flag, const int* __restrict__ pos, int n, int* __restrict__ idx,
+                               int* __restrict__ count) {
+  int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (flag[i]) idx[pos[i]] = i;
+    if (i == n - 1) *count = pos[i] + (flag[i] ? 1 : 0);
+  }
+}
+
+__global__ void k_flag_eq(const long long* __restrict__ v, int n, long long value, int* __restrict__ flag) {
+  int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) flag[i] = v[i] == value;
+}
+
+// out[j][0..C) = bilinear(feats[frame_of(point)], xy(point)), border padding.  One warp per point.
+__global__ void k_ungrid(const float* __restrict__ feats, int C, int H, int W, const float* __restrict__ xyz,
+                         const int* __restrict__ frame_of_point, const int* __restrict__ idx, int k, float x_abs,
+                         float y_abs, float* __restrict__ out) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int j = warp; j < k; j += nwarp) {
+    int i = idx ? idx[j] : j;
+    mlp::Bilinear bl = mlp::bilinear_border(xyz[3 * i], xyz[3 * i + 1], x_abs, y_abs, H, W);
+    const float* base = feats + (size_t)frame_of_point[i] * H * W * C;
+    for (int c = lane; c < C; c += 32) {
+      float v = base[(size_t)bl.o00 * C + c] * bl.w00;
+      v = fmaf(base[(size_t)bl.o01 * C + c], bl.w01, v);
+      v = fmaf(base[(size_t)bl.o10 * C + c], bl.w10, v);
+      v = fmaf(base[(size_t)bl.o11 * C + c], bl.w11, v);
+      out[(size_t)j * C + c] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// STPN point head.  Weight pack ([in][out] matrices):
+//   pe0 W[3][32] b[32] | pe2 W[32][64] b[64] | fp W[128][128] b[128] |
+//   mos0 W[128][128] b[128] s[128] t[128] | mos3 W[128][2] b[2] | off0 W,b,s,t | off3 W[128][2] b[2]
+// ---------------------------------------------------------------------------------------------
+constexpr int S_PE0W = 0, S_PE0B = S_PE0W + 3 * 32, S_PE2W = S_PE0B + 32, S_PE2B = S_PE2W + 32 * 64;
+constexpr int S_FPW = S_PE2B + 64, S_FPB = S_FPW + 128 * 128;
+constexpr int S_M0W = S_FPB + 128, S_M0B = S_M0W + 128 * 128, S_M0S = S_M0B + 128, S_M0T = S_M0S + 128;
+constexpr int S_M3W = S_M0T + 128, S_M3B = S_M3W + 128 * 2;
+constexpr int S_O0W = S_M3B + 2 + 2 /*pad to 4*/, S_O0B = S_O0W + 128 * 128, S_O0S = S_O0B + 128, S_O0T = S_O0S + 128;
+constexpr int S_O3W = S_O0T + 128, S_O3B = S_O3W + 128 * 2;
+constexpr int S_PACK = S_O3B + 2 + 2;
+
+__global__ void __launch_bounds__(256) k_stpn_head(const float* __restrict__ mos_feats /* [B,H,W,64] */, int H, int W,
+                                                   const float* __restrict__ tp, const int* __restrict__ pbatch,
+                                                   const int* __restrict__ fg_idx, int k, const float* __restrict__ pk,
+                                                   float x_abs, float y_abs, float* __restrict__ mos_out,
+                                                   float* __restrict__ off_out) {
+  extern __shared__ __align__(16) float sm[];
+  float* E = sm;                  // [128][PTS]
+  float* F = E + 128 * PTS;       // [128][PTS]
+  float* G = F + 128 * PTS;       // [128][PTS]
+  float* s_w = G + 128 * PTS;     // [KC*128]
+  float* s_o = s_w + mlp::KC * 128;  // [4][PTS]
+  __shared__ int s_idx[PTS];
+  const int base = blockIdx.x * PTS;
+  if (threadIdx.x < PTS) s_idx[threadIdx.x] = (base + threadIdx.x < k) ? fg_idx[base + threadIdx.x] : -1;
+  __syncthreads();
+  // inputs: pos = p / |x_min| (all three by x scale, models/stpn.py:94), channel-major into G[0..2]
+  for (int e = threadIdx.x; e < 3 * PTS; e += 256) {
+    int c = e / PTS, p = e % PTS;
+    int i = s_idx[p];
+    G[c * PTS + p] = i >= 0 ? tp[3 * i + c] / x_abs : 0.f;
+  }
+  __syncthreads();
+  mlp::block_dense<3, 32>(G, pk + S_PE0W, pk + S_PE0B, nullptr, nullptr, true, F, s_w);
+  mlp::block_dense<32, 64>(F, pk + S_PE2W, pk + S_PE2B, nullptr, nullptr, true, E, s_w);
+  // bilinear pickup of the 64 motion-feature channels into E[64..127]
+  for (int e = threadIdx.x; e < PTS * 16; e += 256) {
+    int p = e / 16, q = e % 16;
+    int i = s_idx[p];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i >= 0) {
+      mlp::Bilinear bl = mlp::bilinear_border(tp[3 * i], tp[3 * i + 1], x_abs, y_abs, H, W);
+      const float4* b4 = reinterpret_cast<const float4*>(mos_feats + (size_t)pbatch[i] * H * W * 64) + q;
+      float4 a = b4[(size_t)bl.o00 * 16], b = b4[(size_t)bl.o01 * 16], c = b4[(size_t)bl.o10 * 16], d = b4[(size_t)bl.o11 * 16];
+      v.x = fmaf(d.x, bl.w11, fmaf(c.x, bl.w10, fmaf(b.x, bl.w01, a.x * bl.w00)));
+      v.y = fmaf(d.y, bl.w11, fmaf(c.y, bl.w10, fmaf(b.y, bl.w01, a.y * bl.w00)));
+      v.z = fmaf(d.z, bl.w11, fmaf(c.z, bl.w10, fmaf(b.z, bl.w01, a.z * bl.w00)));
+      v.w = fmaf(d.w, bl.w11, fmaf(c.w, bl.w10, fmaf(b.w, bl.w01, a.w * bl.w00)));
+    }
+    E[(64 + 4 * q + 0) * PTS + p] = v.x;
+    E[(64 + 4 * q + 1) * PTS + p] = v.y;
+    E[(64 + 4 * q + 2) * PTS + p] = v.z;
+    E[(64 + 4 * q + 3) * PTS + p] = v.w;
+  }
+  __syncthreads();
+  mlp::block_dense<128, 128>(E, pk + S_FPW, pk + S_FPB, nullptr, nullptr, true, F, s_w);
+  mlp::block_dense<128, 128>(F, pk + S_M0W, pk + S_M0B, pk + S_M0S, pk + S_M0T, true, G, s_w);
+  mlp::block_dense_small<128, 2>(G, pk + S_M3W, pk + S_M3B, s_o);
+  mlp::block_dense<128, 128>(F, pk + S_O0W, pk + S_O0B, pk + S_O0S, pk + S_O0T, true, E, s_w);
+  mlp::block_dense_small<128, 2>(E, pk + S_O3W, pk + S_O3B, s_o + 2 * PTS);
+  for (int e = threadIdx.x; e < PTS * 2; e += 256) {
+    int p = e % PTS, o = e / PTS;
+    int i = s_idx[p];
+    if (i < 0) continue;
+    mos_out[2 * i + o] = s_o[o * PTS + p];
+    float v = s_o[(2 + o) * PTS + p];
+    if (isnan(v) || isinf(v)) v = 0.f;  // safe_guard_offset (models/stpn.py:61-65)
+    off_out[2 * i + o] = fminf(fmaxf(v, -20.f), 20.f);
+  }
+}
+
+__global__ void k_init_point_outputs(int n, float* __restrict__ mos, float* __restrict__ off) {
+  int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    mos[2 * i] = 1.f, mos[2 * i + 1] = 0.f;
+    off[2 * i] = 0.f, off[2 * i + 1] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TubeNet
+// ---------------------------------------------------------------------------------------------
+// three-layer embed: IN -> H1 relu -> H2 relu -> 128, then atomic max into dst[seg[p]][128]
+template <int IN, int H1, int H2>
+__device__ void embed_and_max(float* A, float* Bf, float* s_w, const float* __restrict__ pk, const int* s_seg,
+                              float* __restrict__ dst) {
+  const float* W0 = pk;
+  const float* b0 = W0 + IN * H1;
+  const float* W1 = b0 + H1;
+  const float* b1 = W1 + H1 * H2;
+  const float* W2 = b1 + H2;
+  const float* b2 = W2 + H2 * 128;
+  mlp::block_dense<IN, H1>(A, W0, b0, nullptr, nullptr, true, Bf, s_w);
+  mlp::block_dense<H1, H2>(Bf, W1, b1, nullptr, nullptr, true, A, s_w);
+  mlp::block_dense<H2, 128>(A, W2, b2, nullptr, nullptr, false, Bf, s_w);
+  for (int e = threadIdx.x; e < PTS * 128; e += 256) {
+    int p = e % PTS, c = e / PTS;
+    int s = s_seg[p];
+    if (s >= 0) mlp::atomic_max_float(dst + (size_t)s * 128 + c, Bf[c * PTS + p]);
+  }
+  __syncthreads();
+}
+
+// motion (64->64->128->128) and geometry (32->32->64->128) embeddings, max-pooled per instance
+__global__ void __launch_bounds__(256) k_tpn_static_embed(const float* __restrict__ mos_feat,
+                                                          const float* __restrict__ geo_feat,
+                                                          const int* __restrict__ src_idx, const int* __restrict__ inst,
+                                                          int n, const float* __restrict__ pk_motion,
+                                                          const float* __restrict__ pk_geo, float* __restrict__ mos_emb,
+                                                          float* __restrict__ geo_emb) {
+  extern __shared__ __align__(16) float sm[];
+  float* A = sm;
+  float* Bf = A + 128 * PTS;
+  float* s_w = Bf + 128 * PTS;
+  __shared__ int s_seg[PTS], s_src[PTS];
+  int base = blockIdx.x * PTS;
+  if (threadIdx.x < PTS) {
+    int j = base + threadIdx.x;
+    s_seg[threadIdx.x] = j < n ? inst[j] : -1;
+    s_src[threadIdx.x] = j < n ? src_idx[j] : -1;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < PTS * 64; e += 256) {
+    int p = e / 64, c = e % 64;
+    A[c * PTS + p] = s_src[p] >= 0 ? mos_feat[(size_t)s_src[p] * 64 + c] : 0.f;
+  }
+  __syncthreads();
+  embed_and_max<64, 64, 128>(A, Bf, s_w, pk_motion, s_seg, mos_emb);
+  for (int e = threadIdx.x; e < PTS * 32; e += 256) {
+    int p = e / 32, c = e % 32;
+    A[c * PTS + p] = s_src[p] >= 0 ? geo_feat[(size_t)s_src[p] * 32 + c] : 0.f;
+  }
+  __syncthreads();
+  embed_and_max<32, 32, 64>(A, Bf, s_w, pk_geo, s_seg, geo_emb);
+}
+
+// per (instance, frame) sums of the points (double) and counts
+__global__ void k_tpn_frame_sums(const float* __restrict__ pts, const int* __restrict__ inst,
+                                 const int* __restrict__ tidx, int T, int n, double* __restrict__ sums /* [KT][4] */) {
+  int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    double* s = sums + ((size_t)inst[j] * T + tidx[j]) * 4;
+    atomicAdd(s, (double)pts[3 * j]), atomicAdd(s + 1, (double)pts[3 * j + 1]), atomicAdd(s + 2, (double)pts[3 * j + 2]);
+    atomicAdd(s + 3, 1.0);
+  }
+}
+
+// positional embedding of [p - anchor_centroid(inst), t/T] (4->32->64->128), max-pooled per (inst, frame)
+__global__ void __launch_bounds__(256) k_tpn_pos_embed(const float* __restrict__ pts, const int* __restrict__ inst,
+                                                       const int* __restrict__ tidx, int n, int T,
+                                                       const double* __restrict__ sums, const float* __restrict__ pk_pos,
+                                                       float* __restrict__ frame_emb) {
+  extern __shared__ __align__(16) float sm[];
+  float* A = sm;
+  float* Bf = A + 128 * PTS;
+  float* s_w = Bf + 128 * PTS;
+  __shared__ int s_seg[PTS];
+  int base = blockIdx.x * PTS;
+  if (threadIdx.x < PTS) {
+    int j = base + threadIdx.x;
+    int p = threadIdx.x;
+    if (j < n) {
+      int k = inst[j], t = tidx[j];
+      s_seg[p] = k * T + t;
+      const double* s = sums + (size_t)k * T * 4;  // anchor frame (t = 0) of the instance
+      double cnt = s[3] > 0 ? s[3] : 1.0;
+      A[0 * PTS + p] = pts[3 * j] - (float)(s[0] / cnt);
+      A[1 * PTS + p] = pts[3 * j + 1] - (float)(s[1] / cnt);
+      A[2 * PTS + p] = pts[3 * j + 2] - (float)(s[2] / cnt);
+      A[3 * PTS + p] = (float)((double)t / (double)T);
+    } else {
+      s_seg[p] = -1;
+      A[p] = A[PTS + p] = A[2 * PTS + p] = A[3 * PTS + p] = 0.f;
+    }
+  }
+  __syncthreads();
+  embed_and_max<4, 32, 64>(A, Bf, s_w, pk_pos, s_seg, frame_emb);
+}
+
+__global__ void k_fix_neg_inf(float* __restrict__ a, long long n) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+    if (a[i] == -INFINITY) a[i] = 0.f;  // torch_scatter leaves empty segments at 0
+}
+
+// regressor input rows [K*T][512] = [geo(k), mos(k), frame(k,t), frame(k,0)]
+__global__ void k_tpn_regressor_input(const float* __restrict__ geo_emb, const float* __restrict__ mos_emb,
+                                      const float* __restrict__ frame_emb, int KT, int T, float* __restrict__ X) {
+  long long total = (long long)KT * 512;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
+    int row = (int)(e / 512), c = (int)(e % 512);
+    int k = row / T;
+    float v;
+    if (c < 128) v = geo_emb[(size_t)k * 128 + c];
+    else if (c < 256) v = mos_emb[(size_t)k * 128 + c - 128];
+    else if (c < 384) v = frame_emb[(size_t)row * 128 + c - 256];
+    else v = frame_emb[(size_t)k * T * 128 + c - 384];
+    X[e] = v;
+  }
+}
+
+// generic small dense layer: one thread per (row, out)
+__global__ void k_linear_rows(const float* __restrict__ X, int R, int IN, int OUT, const float* __restrict__ W,
+                              const float* __restrict__ b, const float* __restrict__ scale,
+                              const float* __restrict__ shift, int relu, float* __restrict__ Y) {
+  long long total = (long long)R * OUT;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
+    int r = (int)(e / OUT), o = (int)(e % OUT);
+    const float* x = X + (size_t)r * IN;
+    float a = 0.f;
+    for (int k = 0; k < IN; ++k) a = fmaf(x[k], W[(size_t)k * OUT + o], a);
+    a += b[o];
+    if (scale) a = fmaf(a, scale[o], shift[o]);
+    Y[e] = relu ? fmaxf(a, 0.f) : a;
+  }
+}
+
+// rep[K*T][7] = (quat xyzw, trans) -> pose [K*T][4][4] with the centring undone and frame 0 := I
+__global__ void k_tpn_pose(const float* __restrict__ rep, const double* __restrict__ sums, int KT, int T,
+                           float* __restrict__ pose_centered, float* __restrict__ pose) {
+  int stride = gridDim.x * blockDim.x;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < KT; r += stride) {
+    const float* q = rep + (size_t)r * 7;
+    float nrm = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);  // F.normalize
+    float x = q[0] / nrm, y = q[1] / nrm, z = q[2] / nrm, w = q[3] / nrm;
+    float w2 = w * w, x2 = x * x, y2 = y * y, z2 = z * z;
+    float wx = w * x, wy = w * y, wz = w * z, xy = x * y, xz = x * z, yz = y * z;
+    float R[9] = {w2 + x2 - y2 - z2, 2 * xy - 2 * wz,   2 * wy + 2 * xz,    //
+                  2 * wz + 2 * xy,   w2 - x2 + y2 - z2, 2 * yz - 2 * wx,    //
+                  2 * xz - 2 * wy,   2 * wx + 2 * yz,   w2 - x2 - y2 + z2};
+    float t[3] = {q[4], q[5], q[6]};
+    if (pose_centered) {
+      float* P = pose_centered + (size_t)r * 16;
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) P[4 * i + j] = R[3 * i + j];
+        P[4 * i + 3] = t[i];
+      }
+      P[12] = P[13] = P[14] = 0.f, P[15] = 1.f;
+    }
+    int k = r / T;
+    const double* s = sums + (size_t)k * T * 4;
+    double cnt = s[3] > 0 ? s[3] : 1.0;
+    float c[3] = {(float)(s[0] / cnt), (float)(s[1] / cnt), (float)(s[2] / cnt)};
+    float* P = pose + (size_t)r * 16;
+    bool anchor = (r % T) == 0;
+    for (int i = 0; i < 3; ++i) {
+      float d = 0.f;
+      for (int j = 0; j < 3; ++j) {
+        float e = ((i == j) ? 1.f : 0.f) - R[3 * i + j];
+        d = fmaf(e, c[j], d);
+        P[4 * i + j] = anchor ? (i == j ? 1.f : 0.f) : R[3 * i + j];
+      }
+      P[4 * i + 3] = anchor ? 0.f : t[i] + d;
+    }
+    P[12] = P[13] = P[14] = 0.f, P[15] = 1.f;
+  }
+}
+
+// out[j] = R[seg[j]] p_j + t[seg[j]]  (reconstruct_sequence / ego_motion_compensation)
+__global__ void k_apply_seg_pose(const float* __restrict__ pts, const int* __restrict__ seg,
+                                 const float* __restrict__ pose, int n, float* __restrict__ out) {
+  int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const float* P = pose + (size_t)seg[j] * 16;
+    float x = pts[3 * j], y = pts[3 * j + 1], z = pts[3 * j + 2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float d = P[4 * r] * x;
+      d = fmaf(P[4 * r + 1], y, d);
+      d = fmaf(P[4 * r + 2], z, d);
+      out[3 * j + r] = d + P[4 * r + 3];
+    }
+  }
+}
+
+__global__ void k_scatter_rows3(const float* __restrict__ src, const int* __restrict__ idx, int k,
+                                float* __restrict__ dst) {
+  int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += stride) {
+    int i = idx[j];
+    dst[3 * i] = src[3 * j], dst[3 * i + 1] = src[3 * j + 1], dst[3 * i + 2] = src[3 * j + 2];
+  }
+}
+
+__global__ void k_fill(float* a, long long n, float v) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) a[i] = v;
+}
+
+size_t al256p(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" size_t pcab_select_workspace(int n) {
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int*)nullptr, (int*)nullptr, n);
+  return 2 * al256p((size_t)n * 4) + al256p(scan_bytes) + 256;
+}
+
+// idx = ascending indices i with flags[i] != 0 (or values[i] == value when flags is null); count on device
+extern "C" int pcab_select_indices(const int* flags, const long long* values, long long value, int n, int* idx,
+                                   int* count, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  PCAB_REQUIRE(workspace_bytes >= pcab_select_workspace(n), "workspace too small");
+  char* w = (char*)workspace;
+  int* flag = (int*)w;
+  w += al256p((size_t)n * 4);
+  int* pos = (int*)w;
+  w += al256p((size_t)n * 4);
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flag, pos, n);
+  const int* f = flags;
+  if (!f) {
+    k_flag_eq<<<grid_for(n, 256), 256, 0, stream>>>(values, n, value, flag);
+    f = flag;
+  }
+  PCAB_CUDA(cub::DeviceScan::ExclusiveSum(w, scan_bytes, f, pos, n, stream));
+  k_select_write<<<grid_for(n, 256), 256, 0, stream>>>(f, pos, n, idx, count);
+  PCAB_CHECK_LAUNCH("pcab_select_indices");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_ungrid(const float* feats_nhwc, int C, int H, int W, const float* xyz, const int* frame_of_point,
+                           const int* idx, int k, float x_abs, float y_abs, float* out, cudaStream_t stream) {
+  if (k <= 0) return PCAB_OK;
+  k_ungrid<<<grid_for((long long)k * 32, 256, 8), 256, 0, stream>>>(feats_nhwc, C, H, W, xyz, frame_of_point, idx, k,
+                                                                   x_abs, y_abs, out);
+  PCAB_CHECK_LAUNCH("pcab_ungrid");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_stpn_head_pack_size(void) { return S_PACK; }
+
+extern "C" int pcab_init_point_outputs(int n_points, float* mos, float* offset, cudaStream_t stream) {
+  k_init_point_outputs<<<grid_for(n_points, 256), 256, 0, stream>>>(n_points, mos, offset);
+  PCAB_CHECK_LAUNCH("pcab_init_point_outputs");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_stpn_head(const float* mos_feats_nhwc, int H, int W, const float* transformed_points,
+                              const int* point_batch, const int* fg_idx, int n_fg, const float* weight_pack,
+                              float x_abs, float y_abs, float* mos_out, float* offset_out, cudaStream_t stream) {
+  if (n_fg <= 0) return PCAB_OK;
+  size_t smem = (size_t)(3 * 128 * PTS + mlp::KC * 128 + 4 * PTS) * sizeof(float);
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(k_stpn_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cfg = true;
+  }
+  k_stpn_head<<<cdiv(n_fg, PTS), 256, smem, stream>>>(mos_feats_nhwc, H, W, transformed_points, point_batch, fg_idx,
+                                                      n_fg, weight_pack, x_abs, y_abs, mos_out, offset_out);
+  PCAB_CHECK_LAUNCH("pcab_stpn_head");
+  return PCAB_OK;
+}
+
+// embeds: each pack = W0[IN][H1] b0 W1[H1][H2] b1 W2[H2][128] b2
+extern "C" int pcab_tpn_static_embed(const float* mos_feat, const float* geo_feat, const int* src_idx, const int* inst,
+                                     int n, int K, const float* pack_motion, const float* pack_geo, float* mos_emb,
+                                     float* geo_emb, cudaStream_t stream) {
+  size_t smem = (size_t)(2 * 128 * PTS + mlp::KC * 128) * sizeof(float);
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(k_tpn_static_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cfg = true;
+  }
+  k_fill<<<grid_for((long long)K * 128, 256), 256, 0, stream>>>(mos_emb, (long long)K * 128, -INFINITY);
+  k_fill<<<grid_for((long long)K * 128, 256), 256, 0, stream>>>(geo_emb, (long long)K * 128, -INFINITY);
+  k_tpn_static_embed<<<cdiv(n, PTS), 256, smem, stream>>>(mos_feat, geo_feat, src_idx, inst, n, pack_motion, pack_geo,
+                                                          mos_emb, geo_emb);
+  k_fix_neg_inf<<<grid_for((long long)K * 128, 256), 256, 0, stream>>>(mos_emb, (long long)K * 128);
+  k_fix_neg_inf<<<grid_for((long long)K * 128, 256), 256, 0, stream>>>(geo_emb, (long long)K * 128);
+  PCAB_CHECK_LAUNCH("pcab_tpn_static_embed");
+  return PCAB_OK;
+}
+
+// one TPointNet iteration: frame centroids, positional embedding, regressor, pose assembly.
+// regressor pack: W0[512][256] b0 s0 t0 | W1[256][128] b1 s1 t1 | W2[128][7] b2
+// scratch floats: frame_emb KT*128 | X KT*512 | H0 KT*256 | H1 KT*128 | rep KT*7 ; doubles sums KT*4
+extern "C" size_t pcab_tpn_iteration_workspace(int K, int T) {
+  size_t kt = (size_t)K * T;
+  return al256p(kt * (128 + 512 + 256 + 128 + 8) * 4) + al256p(kt * 4 * 8) + 256;
+}
+
+extern "C" int pcab_tpn_iteration(const float* points, const int* inst, const int* tidx, int n, int K, int T,
+                                  const float* mos_emb, const float* geo_emb, const float* pack_pos,
+                                  const float* pack_regressor, float* pose_out, float* pose_centered_out,
+                                  float* rep_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  PCAB_REQUIRE(workspace_bytes >= pcab_tpn_iteration_workspace(K, T), "workspace too small");
+  size_t kt = (size_t)K * T;
+  float* f = (float*)workspace;
+  float* frame_emb = f;
+  f += kt * 128;
+  float* X = f;
+  f += kt * 512;
+  float* H0 = f;
+  f += kt * 256;
+  float* H1 = f;
+  f += kt * 128;
+  float* rep = f;
+  f += kt * 8;
+  double* sums = (double*)((char*)workspace + al256p(kt * (128 + 512 + 256 + 128 + 8) * 4));
+  PCAB_CUDA(cudaMemsetAsync(sums, 0, kt * 4 * 8, stream));
+  size_t smem = (size_t)(2 * 128 * PTS + mlp::KC * 128) * sizeof(float);
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(k_tpn_pos_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cfg = true;
+  }
+  k_tpn_frame_sums<<<grid_for(n, 256), 256, 0, stream>>>(points, inst, tidx, T, n, sums);
+  k_fill<<<grid_for((long long)kt * 128, 256), 256, 0, stream>>>(frame_emb, (long long)kt * 128, -INFINITY);
+  k_tpn_pos_embed<<<cdiv(n, PTS), 256, smem, stream>>>(points, inst, tidx, n, T, sums, pack_pos, frame_emb);
+  k_fix_neg_inf<<<grid_for((long long)kt * 128, 256), 256, 0, stream>>>(frame_emb, (long long)kt * 128);
+  k_tpn_regressor_input<<<grid_for((long long)kt * 512, 256), 256, 0, stream>>>(geo_emb, mos_emb, frame_emb, (int)kt, T, X);
+  const float* W0 = pack_regressor;
+  const float* b0 = W0 + 512 * 256;
+  const float* s0 = b0 + 256;
+  const float* t0 = s0 + 256;
+  const float* W1 = t0 + 256;
+  const float* b1 = W1 + 256 * 128;
+  const float* s1 = b1 + 128;
+  const float* t1 = s1 + 128;
+  const float* W2 = t1 + 128;
+  const float* b2 = W2 + 128 * 7;
+  k_linear_rows<<<grid_for((long long)kt * 256, 256), 256, 0, stream>>>(X, (int)kt, 512, 256, W0, b0, s0, t0, 1, H0);
+  k_linear_rows<<<grid_for((long long)kt * 128, 256), 256, 0, stream>>>(H0, (int)kt, 256, 128, W1, b1, s1, t1, 1, H1);
+  k_linear_rows<<<grid_for((long long)kt * 7, 256), 256, 0, stream>>>(H1, (int)kt, 128, 7, W2, b2, nullptr, nullptr, 0,
+                                                                      rep_out ? rep_out : rep);
+  k_tpn_pose<<<grid_for((long long)kt, 128), 128, 0, stream>>>(rep_out ? rep_out : rep, sums, (int)kt, T,
+                                                               pose_centered_out, pose_out);
+  PCAB_CHECK_LAUNCH("pcab_tpn_iteration");
+  return PCAB_OK;
+}
+
+// out[j] = R[seg[j]] p_j + t[seg[j]] with seg = a per-point index into pose[*][4][4]
+extern "C" int pcab_apply_seg_pose(const float* points, const int* seg, const float* pose, int n, float* out,
+                                   cudaStream_t stream) {
+  if (n <= 0) return PCAB_OK;
+  k_apply_seg_pose<<<grid_for(n, 256), 256, 0, stream>>>(points, seg, pose, n, out);
+  PCAB_CHECK_LAUNCH("pcab_apply_seg_pose");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_scatter_rows3(const float* src, const int* idx, int k, float* dst, cudaStream_t stream) {
+  if (k <= 0) return PCAB_OK;
+  k_scatter_rows3<<<grid_for(k, 256), 256, 0, stream>>>(src, idx, k, dst);
+  PCAB_CHECK_LAUNCH("pcab_scatter_rows3");
+  return PCAB_OK;
+}
