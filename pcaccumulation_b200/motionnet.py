@@ -225,6 +225,7 @@ class MotionNet(nn.Module):
         self.use_tensor_cores = True
         self.stages = {}  # stage-boundary tensors of the last forward (for stage-wise parity tests)
         self.keep_stages = False
+        self.conv_events = None  # when a list: (start_event, end_event, flops, path) per conv launch (bench roofline)
 
     # ------------------------------------------------------------------------------------------
     def _pack_key(self):
@@ -306,16 +307,29 @@ class MotionNet(nn.Module):
         if layer.temporal:
             s = [srcs[0]] * 3
         scale, shift = layer.bn
+        ev = self.conv_events
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        path = "f32"
         if self.use_tensor_cores and L.lib().pcab_conv3x3_tc_supported(I(len(layer.splits)), I(c[0]), I(c[1]), I(c[2]), I(layer.cout), I(H), I(W_)):
             if layer.tc_pack is None:
                 layer.tc_pack = self._pack_tc(layer)
             call("pcab_conv3x3_tc", P(s[0]), I(c[0]), P(s[1]), I(c[1]), P(s[2]), I(c[2]), I(T if layer.temporal else 1),
                  P(layer.tc_pack), P(layer.bias), P(scale), P(shift), I(int(relu)), P(out), I(n_img), I(H), I(W_),
                  I(layer.cout), I(layer.cout), I(0), stream())
+            path = "tc"
         else:
             call("pcab_conv3x3_f32", P(s[0]), I(c[0]), P(s[1]), I(c[1]), P(s[2]), I(c[2]), I(T if layer.temporal else 1),
                  P(layer.pack), P(layer.bias), P(scale), P(shift), I(int(relu)), P(out), I(n_img), I(H), I(W_),
                  I(layer.cout), I(layer.cout), I(0), stream())
+        if ev is not None:
+            e1.record()
+            if layer.temporal:
+                taps = 9 * layer.splits[0] * (3 * T - 2) * (n_img // T)
+            else:
+                taps = 9 * sum(layer.splits) * n_img
+            ev.append((e0, e1, 2.0 * taps * layer.cout * H * W_, path))
         return out
 
     def _pack_tc(self, layer):

@@ -1,0 +1,90 @@
+"""Scene runner: raw multi-sweep points -> GPU voxelise -> ``MotionNet.forward`` (the tester's inner loop).
+
+Mirrors what ``libs/tester.py:52-56`` does per scene (DataLoader sample -> ``.to(device)`` -> ``model(input_dict)``)
+except that voxelisation and collation run on the device (``libs/voxel_generator.py`` and
+``libs/dataloader.py:7-40`` are CPU code in the reference).  ``run_host`` is the end-to-end entry used by the
+benchmark: pinned host buffers in, host results out, with the H2D/D2H copies on the caller's stream.
+"""
+import numpy as np
+import torch
+
+from .motionnet import MotionNet
+from .voxel_generator import Voxelization
+
+
+class SceneRunner:
+    def __init__(self, cfg, model=None, device="cuda"):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.model = (model or MotionNet(cfg)).to(self.device).eval()
+        self.vox = Voxelization(cfg["voxel_generator"])
+        vg = cfg["voxel_generator"]
+        self.T = vg["n_sweeps"]
+        g = self.vox.grid_size
+        self.shape = torch.tensor([[int(g[0]), int(g[1]), int(g[2]), self.T]], dtype=torch.int64)
+
+    def build_input(self, points4, num_points, labels=None, ego_motion_gt=None, inst_motion_gt=None):
+        """points4: CUDA f32 [N,4] (x,y,z,t) with the scenes of a batch concatenated; num_points: list[int]."""
+        dev = points4.device
+        B = len(num_points)
+        N = points4.shape[0]
+        if B > 1:
+            pbatch = torch.repeat_interleave(torch.arange(B, device=dev, dtype=torch.int32),
+                                             torch.tensor(num_points, device=dev))
+        else:
+            pbatch = torch.zeros(N, dtype=torch.int32, device=dev)
+        v = self.vox.voxelize_batch(points4, pbatch if B > 1 else None, B)
+        if int((v["point_to_voxel_map"] < 0).sum()) != 0:  # libs/dataset.py:218 rejects such samples
+            raise ValueError("points outside the voxel range")
+        coords = torch.cat((v["pillar_batch"][:, None], v["coordinates"]), 1).double()
+        time_indice = torch.stack((pbatch.double(), points4[:, 3].double()), 1)
+        zeros = torch.zeros(N, 1, dtype=torch.int64, device=dev)
+        labels = labels or {}
+        T = self.T
+        return {
+            "input_points": points4[:, :3].contiguous(),
+            "num_points": torch.tensor(num_points, dtype=torch.int64),
+            "time_indice": time_indice,
+            "sd_labels": labels.get("sd_labels", zeros),
+            "inst_labels": labels.get("inst_labels", zeros),
+            "fb_labels": labels.get("fb_labels", zeros),
+            "ego_motion_gt": ego_motion_gt if ego_motion_gt is not None else torch.eye(4, device=dev).repeat(B, T, 1, 1),
+            "inst_motion_gt": inst_motion_gt if inst_motion_gt is not None else [torch.eye(4).repeat(1, T, 1, 1)] * B,
+            "coordinates": coords,
+            "num_voxels": v["num_voxels"].to(torch.int64),
+            "shape": self.shape.repeat(B, 1),
+            "point_to_voxel_map": v["point_to_voxel_map"].to(torch.int64)[:, None],
+        }
+
+    @torch.no_grad()
+    def run_device(self, points4, num_points, **kw):
+        return self.model(self.build_input(points4, num_points, **kw))
+
+    @torch.no_grad()
+    def run_host(self, points4_pinned, num_points, ego_motion_gt_host=None, out=None):
+        """End to end with HOST buffers: H2D of the raw points, forward, D2H of the per-point results.
+
+        ``out``: optional dict of pinned host tensors (rec_est f32[N,3], fb i64[N], mos f32[N,2], inst i64[N],
+        ego f32[B,T,4,4]) to receive the results.  Returns (results_on_device, bytes_h2d, bytes_d2h).
+        """
+        dev = self.device
+        pts = points4_pinned.to(dev, non_blocking=True)
+        h2d = points4_pinned.numel() * 4
+        ego = None
+        if ego_motion_gt_host is not None:
+            ego = ego_motion_gt_host.to(dev, non_blocking=True)
+            h2d += ego_motion_gt_host.numel() * 4
+        res = self.run_device(pts, num_points, ego_motion_gt=ego)
+        d2h = 0
+        if out is not None:
+            for key, src in (("rec_est", res["rec_est"]), ("fb", res["fb_est_per_points"][:, 0]), ("mos", res["mos_est"]),
+                             ("inst", res.get("inst_labels_est")), ("ego", res["ego_motion_est"])):
+                if src is None or key not in out:
+                    continue
+                out[key].copy_(src, non_blocking=True)
+                d2h += src.numel() * src.element_size()
+        return res, h2d, d2h
+
+
+def scene_to_points4(scene):
+    return np.concatenate((scene["input_points"], scene["time_indice"].astype(np.float32)), 1).astype(np.float32)

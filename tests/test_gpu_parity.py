@@ -1,0 +1,460 @@
+"""GPU parity tests (run on the B200 box): the CUDA path through the C ABI vs the CPU oracle / reference goldens.
+
+Bars: bit-exact for integer / index outputs (pillar ids, FG labels, instance labels, Chamfer argmin and distances);
+floating point within 1e-4 relative to the tensor's magnitude (the tolerance BASELINE.json's north_star states).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, load_golden_forward
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+
+
+def cuda_dict(d):
+    return {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+
+
+def assert_close_rel(a, b, rel=REL, name=""):
+    a = a.detach().cpu().double()
+    b = torch.as_tensor(b).detach().cpu().double()
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    scale = max(float(b.abs().max()), 1e-6)
+    err = float((a - b).abs().max())
+    assert err <= rel * scale, f"{name}: max abs err {err:.3e} > {rel:.0e} * {scale:.3e}"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pcaccumulation_b200 import _lib
+    return _lib
+
+
+def make_model(cfg, sd):
+    from pcaccumulation_b200.motionnet import MotionNet
+
+    m = MotionNet(cfg).cuda().eval()
+    m.load_state_dict(sd)
+    m.keep_stages = True
+    return m
+
+
+# -------------------------------------------------------------------------------------------------------------
+# voxeliser
+# -------------------------------------------------------------------------------------------------------------
+def _vox_case(pts4, vg):
+    from oracle import oracle
+    from pcaccumulation_b200.voxel_generator import Voxelization
+
+    ref = oracle.voxelize(pts4, vg["voxel_size"], vg["range"], vg["n_sweeps"])
+    out = Voxelization(vg)(torch.tensor(pts4).cuda())
+    assert np.array_equal(out["coordinates"].cpu().numpy(), ref["coordinates"])
+    assert np.array_equal(out["point_to_voxel_map"].cpu().numpy(), ref["point_to_voxel_map"])
+    assert int(out["num_voxels"][0]) == int(ref["num_voxels"][0])
+    assert out["shape"].tolist() == ref["shape"].tolist()
+    return ref
+
+
+def test_voxelize_bit_exact_scene_and_edge_cases():
+    from pcaccumulation_b200 import config, synth
+
+    cfg = config.workload_config("C1")
+    vg = cfg["voxel_generator"]
+    s = synth.make_workload_scene("C1", 1)
+    pts4 = np.concatenate((s["input_points"], s["time_indice"]), 1).astype(np.float32)
+    _vox_case(pts4, vg)
+    rng = np.random.default_rng(0)
+    # ragged: many rejected points (outside x/y/z range), exact cell-boundary coordinates, duplicates
+    wild = np.concatenate([rng.uniform(-45, 45, (5000, 2)), rng.uniform(-4, 8, (5000, 1)), rng.integers(0, 5, (5000, 1))], 1).astype(np.float32)
+    wild[:200, 0] = np.round(wild[:200, 0] * 4) / 4  # on voxel boundaries
+    wild[200:400] = wild[:200]
+    wild[400, :3] = [-36.0, -36.0, -2.0]
+    wild[401, :3] = [36.0, 0.0, 0.0]  # x == upper bound -> rejected
+    ref = _vox_case(wild, vg)
+    assert (ref["point_to_voxel_map"] == -1).sum() > 100
+    _vox_case(wild[:1], vg)  # single point
+    _vox_case(np.repeat(wild[5:6], 64, 0), vg)  # one pillar, many points
+
+
+def test_voxelize_batched_offsets_match_collate():
+    from oracle import oracle
+    from pcaccumulation_b200 import config, synth
+    from pcaccumulation_b200.voxel_generator import Voxelization
+
+    cfg = config.workload_config("C1")
+    vg = cfg["voxel_generator"]
+    scenes = [synth.make_workload_scene("C1", i, pts_per_frame=3000) for i in range(3)]
+    samples, p4s = [], []
+    for s in scenes:
+        p4 = np.concatenate((s["input_points"], s["time_indice"]), 1).astype(np.float32)
+        p4s.append(p4)
+        s = dict(s)
+        s.update(oracle.voxelize(p4, vg["voxel_size"], vg["range"], vg["n_sweeps"]))
+        samples.append(s)
+    inp = synth.collate(samples)
+    allp = torch.tensor(np.concatenate(p4s)).cuda()
+    pb = torch.repeat_interleave(torch.arange(3, dtype=torch.int32), torch.tensor([p.shape[0] for p in p4s])).cuda()
+    out = Voxelization(vg).voxelize_batch(allp, pb, 3)
+    assert torch.equal(out["point_to_voxel_map"].cpu().long(), inp["point_to_voxel_map"][:, 0])
+    assert torch.equal(out["coordinates"].cpu().double(), inp["coordinates"][:, 1:])
+    assert torch.equal(out["pillar_batch"].cpu().double(), inp["coordinates"][:, 0])
+    assert out["num_voxels"].cpu().tolist() == inp["num_voxels"].tolist()
+
+
+def test_voxelize_full_size_properties():
+    """C2-sized input (5 x 150k points): size-independent invariants of first-touch numbering."""
+    from pcaccumulation_b200 import config, synth
+    from pcaccumulation_b200.voxel_generator import Voxelization
+
+    cfg = config.workload_config("C2")
+    vg = cfg["voxel_generator"]
+    s = synth.make_workload_scene("C2", 0)
+    pts4 = np.concatenate((s["input_points"], s["time_indice"]), 1).astype(np.float32)
+    out = Voxelization(vg).voxelize_batch(torch.tensor(pts4).cuda())
+    p2v = out["point_to_voxel_map"].cpu().numpy()
+    coords = out["coordinates"].cpu().numpy()
+    M = out["total_voxels"]
+    assert p2v.min() == 0 and p2v.max() == M - 1
+    # pillar ids appear in increasing order of first touch
+    first = np.full(M, pts4.shape[0], dtype=np.int64)
+    np.minimum.at(first, p2v, np.arange(pts4.shape[0]))
+    assert np.all(np.diff(first) > 0)
+    # coordinates are unique cells and every point lies in its pillar's cell
+    key = (coords[:, 1].astype(np.int64) * 288 + coords[:, 2]) * 5 + coords[:, 3]
+    assert np.unique(key).shape[0] == M and np.all(coords[:, 0] == 0)
+    cx = np.floor((pts4[:, 0] - np.float32(-36)) / np.float32(0.25)).astype(np.int32)
+    cy = np.floor((pts4[:, 1] - np.float32(-36)) / np.float32(0.25)).astype(np.int32)
+    assert np.array_equal(coords[p2v, 2], cx) and np.array_equal(coords[p2v, 1], cy)
+    assert np.array_equal(coords[p2v, 3], pts4[:, 3].astype(np.int32))
+    # idempotence: voxelising the same stream again gives the same answer
+    out2 = Voxelization(vg).voxelize_batch(torch.tensor(pts4).cuda())
+    assert torch.equal(out2["point_to_voxel_map"], out["point_to_voxel_map"])
+
+
+# -------------------------------------------------------------------------------------------------------------
+# convolution kernels vs torch CPU
+# -------------------------------------------------------------------------------------------------------------
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 40, 56), (1, 64, 64, 19, 23), (3, 128, 256, 9, 9), (1, 32, 64, 72, 72)])
+def test_conv3x3_f32_single_source(lib, shape):
+    from pcaccumulation_b200 import motionnet as mn
+    from pcaccumulation_b200._lib import I, P, call, stream
+
+    n, cin, cout, H, W = shape
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * 0.1
+    b = torch.randn(cout, generator=g)
+    sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    ref = F.relu((F.conv2d(x, w, b, padding=1)) * sc[None, :, None, None] + sh[None, :, None, None])
+    out = torch.empty(n, H, W, cout).cuda()
+    call("pcab_conv3x3_f32", P(_nhwc(x).cuda()), I(cin), P(None), I(0), P(None), I(0), I(1), P(mn._pack_conv3x3(w, [cin]).cuda()),
+         P(b.cuda()), P(sc.cuda()), P(sh.cuda()), I(1), P(out), I(n), I(H), I(W), I(cout), I(cout), I(0), stream())
+    assert_close_rel(out, _nhwc(ref), 2e-5, "conv3x3")
+
+
+def test_conv3x3_f32_concat_and_temporal(lib):
+    from pcaccumulation_b200 import motionnet as mn
+    from pcaccumulation_b200._lib import I, P, call, stream
+
+    g = torch.Generator().manual_seed(2)
+    a, b_ = torch.randn(2, 32, 20, 28, generator=g), torch.randn(2, 64, 20, 28, generator=g)
+    w = torch.randn(32, 96, 3, 3, generator=g) * 0.1
+    bias = torch.randn(32, generator=g)
+    ref = F.conv2d(torch.cat((a, b_), 1), w, bias, padding=1)
+    out = torch.empty(2, 20, 28, 32).cuda()
+    call("pcab_conv3x3_f32", P(_nhwc(a).cuda()), I(32), P(_nhwc(b_).cuda()), I(64), P(None), I(0), I(1),
+         P(mn._pack_conv3x3(w, [32, 64]).cuda()), P(bias.cuda()), P(None), P(None), I(0), P(out), I(2), I(20), I(28), I(32), I(32), I(0), stream())
+    assert_close_rel(out, _nhwc(ref), 2e-5, "concat conv")
+    # Conv3d 3x3x3 as three temporal sources: x [B=2, C=32, T=3, H, W]
+    x = torch.randn(2, 32, 3, 12, 16, generator=g)
+    w3 = torch.randn(32, 32, 3, 3, 3, generator=g) * 0.1
+    ref3 = F.relu(F.conv3d(x, w3, bias, padding=1))
+    xin = x.permute(0, 2, 3, 4, 1).reshape(6, 12, 16, 32).contiguous().cuda()
+    out3 = torch.empty(6, 12, 16, 32).cuda()
+    call("pcab_conv3x3_f32", P(xin), I(32), P(xin), I(32), P(xin), I(32), I(3), P(mn._pack_conv3d(w3).cuda()), P(bias.cuda()),
+         P(None), P(None), I(1), P(out3), I(6), I(12), I(16), I(32), I(32), I(0), stream())
+    assert_close_rel(out3, ref3.permute(0, 2, 3, 4, 1).reshape(6, 12, 16, 32), 2e-5, "conv3d")
+
+
+def test_convT_maxpool_temporalmax_head2(lib):
+    from pcaccumulation_b200 import motionnet as mn
+    from pcaccumulation_b200._lib import I, P, call, stream
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 64, 9, 11, generator=g)
+    w = torch.randn(64, 32, 2, 2, generator=g) * 0.1
+    b = torch.randn(32, generator=g)
+    ref = F.conv_transpose2d(x, w, b, stride=2)
+    out = torch.empty(2, 18, 22, 32).cuda()
+    call("pcab_convT2x2_f32", P(_nhwc(x).cuda()), P(mn._pack_convT(w).cuda()), P(b.cuda()), P(out), I(2), I(9), I(11), I(64), I(32), I(32), I(0), stream())
+    assert_close_rel(out, _nhwc(ref), 2e-5, "convT")
+    y = torch.randn(3, 32, 10, 14, generator=g)
+    outp = torch.empty(3, 5, 7, 32).cuda()
+    call("pcab_maxpool2x2", P(_nhwc(y).cuda()), P(outp), I(3), I(10), I(14), I(32), stream())
+    assert torch.equal(outp.cpu(), _nhwc(F.max_pool2d(y, 2, 2)))
+    z = torch.randn(2 * 5, 6, 7, 32, generator=g)
+    outm = torch.empty(2, 6, 7, 32).cuda()
+    call("pcab_temporal_max", P(z.cuda()), P(outm), I(2), I(5), I(6), I(7), I(32), stream())
+    assert torch.equal(outm.cpu(), z.view(2, 5, 6, 7, 32).max(1)[0])
+    h = torch.randn(2, 32, 13, 17, generator=g)
+    w2 = torch.randn(2, 32, 3, 3, generator=g) * 0.1
+    b2 = torch.randn(2, generator=g)
+    ref2 = F.conv2d(h, w2, b2, padding=1)
+    logits = torch.empty(2, 2, 13, 17).cuda()
+    am = torch.empty(2 * 13 * 17, dtype=torch.int32).cuda()
+    call("pcab_head2_conv", P(_nhwc(h).cuda()), I(32), P(w2.permute(2, 3, 1, 0).contiguous().cuda()), P(b2.cuda()), I(2), I(13), I(17), P(logits), P(am), stream())
+    assert_close_rel(logits, ref2, 2e-5, "head2")
+    assert torch.equal(am.cpu().view(2, 13, 17).long(), logits.cpu().max(1)[1])
+
+
+# -------------------------------------------------------------------------------------------------------------
+# full forward
+# -------------------------------------------------------------------------------------------------------------
+INT_KEYS = ("fb_est_per_points", "inst_labels_est", "inst_labels_adjusted", "fb_seg_gt")
+FLOAT_KEYS = ("occ_map", "fb_seg_est", "ego_motion_est", "ego_motion_gt", "transformed_points", "mos_est", "offset_est", "rec_est",
+              "sub_rec_est")
+
+
+def _check_forward(res, ref, rel=REL):
+    for k in INT_KEYS:
+        if k in ref:
+            assert torch.equal(res[k].cpu(), ref[k]), k
+    for k in FLOAT_KEYS:
+        if k in ref:
+            assert_close_rel(res[k], ref[k], rel, k)
+    # argmax of the motion logits is an integer output too
+    assert torch.equal(res["mos_est"].cpu().argmax(1), ref["mos_est"].argmax(1))
+    assert_close_rel(res["inst_pose_est"], ref["inst_pose_est"], 3 * rel, "inst_pose_est")  # end of a 60-layer chain
+    for a, b in zip(res["perm_matrix"], ref["perm_matrix"]):
+        assert_close_rel(a, b, rel, "perm_matrix")
+    assert abs(float(res["ego_l1_loss"]) - float(ref["ego_l1_loss"])) < 1e-4 * max(1.0, float(ref["ego_l1_loss"]))
+    assert abs(res["ego_trans_error"] - ref["ego_trans_error"]) < 1e-4 * max(1.0, ref["ego_trans_error"])
+    # acos near 1 is ill-conditioned: the rotation error is compared on the matrices above and loosely here
+    assert abs(res["ego_rot_error"] - ref["ego_rot_error"]) < 5e-3 * max(1.0, ref["ego_rot_error"])
+    assert abs(res["inst_l2_error"] - ref["inst_l2_error"]) < 1e-4 * max(1.0, ref["inst_l2_error"])
+    for it, terms in ref["tpointnet_loss_terms"].items():
+        for name in ("l1_loss", "l2_loss", "rot_loss", "trans_loss"):
+            a, b = float(res["tpointnet_loss_terms"][it][name]), float(terms[name])
+            assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (it, name, a, b)
+
+
+@pytest.mark.parametrize("mode", ["test", "val"])
+def test_forward_vs_oracle_synthetic(fixture_weights, mode):
+    from oracle import oracle
+    from pcaccumulation_b200 import config, synth
+
+    cfg = config.workload_config("C1", mode=mode)
+    sd = fixture_weights(cfg)
+    s = synth.make_workload_scene("C1", 5, pts_per_frame=12000)
+    p4 = np.concatenate((s["input_points"], s["time_indice"]), 1).astype(np.float32)
+    vg = cfg["voxel_generator"]
+    s.update(oracle.voxelize(p4, vg["voxel_size"], vg["range"], vg["n_sweeps"]))
+    inp = synth.collate([s])
+    torch.manual_seed(7)
+    ref = oracle.OracleMotionNet(cfg, sd).forward(inp)
+    model = make_model(cfg, sd)
+    torch.manual_seed(7)
+    res = model(cuda_dict(inp))
+    _check_forward(res, ref)
+    # determinism: same seed, same result
+    torch.manual_seed(7)
+    res2 = model(cuda_dict(inp))
+    assert torch.equal(res["rec_est"], res2["rec_est"]) and torch.equal(res["ego_motion_est"], res2["ego_motion_est"])
+
+
+@pytest.mark.parametrize("name", ["waymo_small", "nuscene_small"])
+def test_forward_vs_reference_golden(fixture_weights, name):
+    cfg, g, v, inp = load_golden_forward(name)
+    model = make_model(cfg, fixture_weights(cfg))
+    torch.manual_seed(42)
+    res = model(cuda_dict(inp))
+    for k in ("fb_est_per_points", "inst_labels_est", "inst_labels_adjusted"):
+        assert np.array_equal(res[k].cpu().numpy(), g["out_" + k]), k
+    for k in ("ego_motion_est", "ego_motion_gt", "transformed_points", "mos_est", "offset_est", "rec_est", "sub_rec_est"):
+        assert_close_rel(res[k], g["out_" + k], REL, k)
+    assert_close_rel(res["inst_pose_est"], g["out_inst_pose_est"], 3 * REL, "inst_pose_est")
+    assert_close_rel(model.stages["pillar_feats"][::8], g["stage_pillar_feats_sub8"], 1e-5, "pillar_feats")
+    assert_close_rel(model.stages["bev_feats"].permute(0, 3, 1, 2)[:, :, ::16, ::16], g["stage_bev_feats_sample"], REL, "bev_feats")
+    rows = torch.stack([p[0].sum(1) for p in res["perm_matrix"]])
+    assert_close_rel(rows, g["out_perm_rowsum"], REL, "perm row sums")
+
+
+def test_forward_batch_of_two_matches_oracle(fixture_weights):
+    from oracle import oracle
+    from pcaccumulation_b200 import config, synth
+
+    cfg = config.workload_config("C1")
+    sd = fixture_weights(cfg)
+    vg = cfg["voxel_generator"]
+    samples = []
+    for i in (11, 12):
+        s = synth.make_workload_scene("C1", i, pts_per_frame=9000)
+        p4 = np.concatenate((s["input_points"], s["time_indice"]), 1).astype(np.float32)
+        s.update(oracle.voxelize(p4, vg["voxel_size"], vg["range"], vg["n_sweeps"]))
+        samples.append(s)
+    inp = synth.collate(samples)
+    torch.manual_seed(3)
+    ref = oracle.OracleMotionNet(cfg, sd).forward(inp)
+    torch.manual_seed(3)
+    res = make_model(cfg, sd)(cuda_dict(inp))
+    _check_forward(res, ref)
+
+
+def test_runner_device_voxelise_equals_prevoxelised_input(fixture_weights):
+    from oracle import oracle
+    from pcaccumulation_b200 import config, synth
+    from pcaccumulation_b200.runner import SceneRunner, scene_to_points4
+
+    cfg = config.workload_config("C1")
+    sd = fixture_weights(cfg)
+    s = synth.make_workload_scene("C1", 21, pts_per_frame=9000)
+    p4 = scene_to_points4(s)
+    vg = cfg["voxel_generator"]
+    s2 = dict(s)
+    s2.update(oracle.voxelize(p4, vg["voxel_size"], vg["range"], vg["n_sweeps"]))
+    inp = cuda_dict(synth.collate([s2]))
+    runner = SceneRunner(cfg)
+    runner.model.load_state_dict(sd)
+    torch.manual_seed(1)
+    a = runner.model(inp)
+    torch.manual_seed(1)
+    labels = {k: inp[k] for k in ("fb_labels", "sd_labels", "inst_labels")}
+    b = runner.run_device(torch.tensor(p4).cuda(), [p4.shape[0]], labels=labels, ego_motion_gt=inp["ego_motion_gt"])
+    for k in ("rec_est", "mos_est", "ego_motion_est", "fb_est_per_points", "inst_labels_est"):
+        assert torch.equal(a[k], b[k]), k
+
+
+# -------------------------------------------------------------------------------------------------------------
+# clustering
+# -------------------------------------------------------------------------------------------------------------
+def test_cluster_matches_sklearn_pipeline():
+    from oracle import oracle
+    from pcaccumulation_b200 import config
+    from pcaccumulation_b200.motionnet import MotionNet
+
+    cfg = config.workload_config("C1")
+    rng = np.random.default_rng(4)
+    centers = rng.uniform(-30, 30, (60, 2))
+    pts = []
+    for c in centers:
+        n = int(rng.integers(3, 120))
+        pts.append(np.concatenate([c + rng.normal(0, 0.25, (n, 2)), rng.uniform(0, 2, (n, 1))], 1))
+    pts.append(np.concatenate([rng.uniform(-32, 32, (800, 2)), rng.uniform(0, 2, (800, 1))], 1))  # noise
+    pts = np.concatenate(pts).astype(np.float32)
+    pts = np.concatenate([pts, pts[:300] + np.float32(0.004)])  # near-duplicates that the 5 cm hash merges
+    perm = rng.permutation(pts.shape[0])
+    pts = pts[perm]
+    N = pts.shape[0]
+    tp = torch.tensor(pts)
+    off = torch.tensor(rng.normal(0, 0.05, (N, 2)).astype(np.float32))
+    mos = torch.zeros(N, 2)
+    dyn = torch.tensor(rng.random(N) < 0.9)
+    mos[dyn, 1] = 1.0
+    mos[~dyn, 0] = 1.0
+    ti = torch.zeros(N, 2, dtype=torch.float64)
+    orc = oracle.OracleMotionNet(cfg, {})
+    ref = orc.cluster(tp, mos.argmax(1), off, ti)
+    model = MotionNet(cfg)
+    got = model._cluster(tp.cuda(), mos.cuda(), off.cuda(), torch.tensor([N]), 1, N, torch.device("cuda"))
+    assert int(ref.max()) > 20
+    assert torch.equal(got.cpu(), ref)
+
+
+# -------------------------------------------------------------------------------------------------------------
+# Chamfer
+# -------------------------------------------------------------------------------------------------------------
+def test_chamfer_matches_reference_golden_bit_exact():
+    from pcaccumulation_b200.chamfer_distance import ChamferDistance, chamfer_with_indices
+
+    g = np.load(os.path.join(GOLDEN, "chamfer.npz"))
+    a, b = torch.tensor(g["xyz1"]).cuda(), torch.tensor(g["xyz2"]).cuda()
+    d1, d2, i1, i2 = chamfer_with_indices(a, b)
+    assert np.array_equal(i1.cpu().numpy(), g["idx1"]) and np.array_equal(i2.cpu().numpy(), g["idx2"])
+    assert np.array_equal(d1.cpu().numpy(), g["dist1"]) and np.array_equal(d2.cpu().numpy(), g["dist2"])
+    a.requires_grad_(True), b.requires_grad_(True)
+    o1, o2 = ChamferDistance()(a, b)
+    (o1 * torch.tensor(g["g1"]).cuda()).sum().backward(retain_graph=True)
+    (o2 * torch.tensor(g["g2"]).cuda()).sum().backward()
+    assert_close_rel(a.grad, g["grad1"], 1e-5, "grad xyz1")
+    assert_close_rel(b.grad, g["grad2"], 1e-5, "grad xyz2")
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (1, 3000), (2500, 1), (5000, 7000), (40000, 33000)])
+def test_chamfer_vs_oracle_sizes_and_ties(n, m):
+    from oracle import oracle
+    from pcaccumulation_b200.chamfer_distance import chamfer_with_indices
+
+    rng = np.random.default_rng(n + m)
+    a = rng.uniform(-30, 30, (1, n, 3)).astype(np.float32)
+    b = rng.uniform(-30, 30, (1, m, 3)).astype(np.float32)
+    if m > 10:
+        b[0, m // 2] = b[0, 2]  # duplicate target: lowest index must win
+    d1, d2, i1, i2 = oracle.chamfer(a, b)
+    g1, g2, j1, j2 = chamfer_with_indices(torch.tensor(a).cuda(), torch.tensor(b).cuda())
+    assert np.array_equal(j1.cpu().numpy(), i1) and np.array_equal(j2.cpu().numpy(), i2)
+    assert np.array_equal(g1.cpu().numpy(), d1) and np.array_equal(g2.cpu().numpy(), d2)
+
+
+def test_chamfer_nuscenes_sized_properties():
+    """C3-sized clouds (350k x 350k): identical sets -> zero distance and identity argmin; symmetry under swap."""
+    from pcaccumulation_b200.chamfer_distance import chamfer_with_indices
+
+    rng = np.random.default_rng(9)
+    a = torch.tensor(rng.uniform(-32, 32, (1, 350_000, 3)).astype(np.float32)).cuda()
+    d1, d2, i1, i2 = chamfer_with_indices(a, a)
+    assert float(d1.max()) == 0.0 and float(d2.max()) == 0.0
+    assert torch.equal(i1[0].long(), torch.arange(350_000, device="cuda"))
+    b = a[:, torch.randperm(350_000, generator=torch.Generator().manual_seed(0)).cuda()] + 0.01
+    e1, e2, _, _ = chamfer_with_indices(a, b)
+    f2, f1, _, _ = chamfer_with_indices(b, a)
+    assert torch.equal(e1, f1) and torch.equal(e2, f2)
+
+
+# -------------------------------------------------------------------------------------------------------------
+# ego-motion pieces with injected inputs
+# -------------------------------------------------------------------------------------------------------------
+def test_full_size_forward_properties(fixture_weights):
+    """C2-sized scene: invariants that do not need the (slow) oracle."""
+    from pcaccumulation_b200 import config, synth
+    from pcaccumulation_b200.runner import SceneRunner, scene_to_points4
+
+    cfg = config.workload_config("C2")
+    runner = SceneRunner(cfg)
+    runner.model.load_state_dict(fixture_weights(cfg))
+    s = synth.make_workload_scene("C2", 0)
+    p4 = torch.tensor(scene_to_points4(s)).cuda()
+    torch.manual_seed(0)
+    res = runner.run_device(p4, [p4.shape[0]])
+    N = p4.shape[0]
+    est = res["ego_motion_est"][0]
+    R = est[:, :3, :3]
+    eye = torch.eye(3, device="cuda")
+    assert torch.allclose(R @ R.transpose(1, 2), eye.expand_as(R), atol=1e-5) and torch.all(torch.det(R) > 0.999)
+    assert torch.equal(est[0], torch.eye(4, device="cuda"))
+    fb = res["fb_est_per_points"][:, 0]
+    inst = res["inst_labels_est"]
+    mos = res["mos_est"].argmax(1)
+    assert set(fb.unique().tolist()) <= {0, 1}
+    assert torch.all(mos[fb == 0] == 0) and torch.all(inst[mos == 0] == 0)  # only dynamic FG points get instances
+    labels = inst.unique().tolist()
+    assert labels == list(range(len(labels)))  # canonical 0..L
+    counts = torch.bincount(inst)[1:]
+    assert int(counts.min()) >= 1
+    # points of frame 0 are not moved by the ego transform; static points keep their ego-compensated position
+    t0 = p4[:, 3] == 0
+    assert torch.equal(res["transformed_points"][t0], p4[t0, :3])
+    keep = inst == 0
+    assert torch.equal(res["rec_est"][keep], res["transformed_points"][keep])
+    assert res["rec_est"].shape == (N, 3) and torch.isfinite(res["rec_est"]).all()
+    for p in res["perm_matrix"]:
+        assert float(p.sum(1).max()) <= 1.0 + 1e-4  # last Sinkhorn step normalises columns (incl. slack row)
