@@ -102,7 +102,7 @@ def run_reference(args, rank, world):
         return
     cfg = config.workload_config(args.workload)
     sd = fixture_weights(cfg)
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(min(32, os.cpu_count()))  # 32 threads is the fastest setting measured for this path on the 128-core box
     run = oracle_forward_fn(cfg, sd)
     scenes = make_scenes(args.workload, 0, min(N_SCENES, 2))
     steps = min(args.steps, 10)
@@ -252,7 +252,7 @@ def main():
     cpu_base = None
     epe = None
     if rank == 0 and not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count())
+        torch.set_num_threads(min(32, os.cpu_count()))  # 32 threads is the fastest setting measured for this path on the 128-core box
         run = oracle_forward_fn(cfg, sd)
         run(scenes[0])  # warm-up
         n_cpu = 2

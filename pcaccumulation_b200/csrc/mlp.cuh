@@ -1,5 +1,5 @@
 // Block-level dense layers for per-point MLPs: a CTA of 256 threads owns PTS = 64 rows whose
-// activations live in shared memory CHANNEL-MAJOR ([C][PTS]); weights stream through a shared-memory
+// activations live in shared memory CHANNEL-MAJOR ([C][LDP], LDP = PTS + 4); weights stream through a shared-memory
 // k-chunk.  Thread tile is 4 rows x (OUT/16) contiguous outputs: per k one 128-bit activation load
 // (4 rows) and OUT/64 128-bit weight loads feed 4*OUT/16 FMAs.
 #pragma once
@@ -8,6 +8,7 @@
 namespace mlp {
 
 constexpr int PTS = 64;
+constexpr int LDP = PTS + 4;  // row stride of the channel-major activation buffers (keeps float4 alignment, spreads banks)
 constexpr int KC = 32;  // weight rows staged per chunk
 
 // Y[OUT][PTS] = epilogue(W[IN][OUT]^T applied to X[IN][PTS] + b).  X, Y: shared memory, channel-major.
@@ -33,7 +34,7 @@ __device__ __forceinline__ void block_dense(const float* X, const float* __restr
     __syncthreads();
 #pragma unroll 4
     for (int k = 0; k < kc; ++k) {
-      float4 x = *reinterpret_cast<const float4*>(X + (k0 + k) * PTS + tr * 4);
+      float4 x = *reinterpret_cast<const float4*>(X + (k0 + k) * LDP + tr * 4);
       const float* wrow = s_w + k * OUT + tc * OPT;
 #pragma unroll
       for (int o2 = 0; o2 < OPT / 2; ++o2) {
@@ -61,7 +62,7 @@ __device__ __forceinline__ void block_dense(const float* X, const float* __restr
       if (scale) t = fmaf(t, sc, sh);
       v[p] = relu ? fmaxf(t, 0.f) : t;
     }
-    *reinterpret_cast<float4*>(Y + c * PTS + tr * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(Y + c * LDP + tr * 4) = make_float4(v[0], v[1], v[2], v[3]);
   }
   __syncthreads();
 }
@@ -73,8 +74,8 @@ __device__ __forceinline__ void block_dense_small(const float* X, const float* _
   for (int e = threadIdx.x; e < PTS * OUT; e += 256) {
     int p = e % PTS, o = e / PTS;
     float a = 0.f;
-    for (int k = 0; k < IN; ++k) a = fmaf(X[k * PTS + p], W[(size_t)k * OUT + o], a);
-    Y[o * PTS + p] = a + b[o];
+    for (int k = 0; k < IN; ++k) a = fmaf(X[k * LDP + p], W[(size_t)k * OUT + o], a);
+    Y[o * LDP + p] = a + b[o];
   }
   __syncthreads();
 }

@@ -12,6 +12,7 @@
 namespace {
 
 using mlp::PTS;
+using mlp::LDP;
 
 __global__ void k_select_write(const int* __restrict__ flag, const int* __restrict__ pos, int n, int* __restrict__ idx,
                                int* __restrict__ count) {
@@ -67,10 +68,10 @@ __global__ void __launch_bounds__(256) k_stpn_head(const float* __restrict__ mos
                                                    float* __restrict__ off_out) {
   extern __shared__ __align__(16) float sm[];
   float* E = sm;                  // [128][PTS]
-  float* F = E + 128 * PTS;       // [128][PTS]
-  float* G = F + 128 * PTS;       // [128][PTS]
-  float* s_w = G + 128 * PTS;     // [KC*128]
-  float* s_o = s_w + mlp::KC * 128;  // [4][PTS]
+  float* F = E + 128 * LDP;       // [128][PTS]
+  float* G = F + 128 * LDP;       // [128][PTS]
+  float* s_w = G + 128 * LDP;     // [KC*128]
+  float* s_o = s_w + mlp::KC * 128;  // [4][LDP]
   __shared__ int s_idx[PTS];
   const int base = blockIdx.x * PTS;
   if (threadIdx.x < PTS) s_idx[threadIdx.x] = (base + threadIdx.x < k) ? fg_idx[base + threadIdx.x] : -1;
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(256) k_stpn_head(const float* __restrict__ mos
   for (int e = threadIdx.x; e < 3 * PTS; e += 256) {
     int c = e / PTS, p = e % PTS;
     int i = s_idx[p];
-    G[c * PTS + p] = i >= 0 ? tp[3 * i + c] / x_abs : 0.f;
+    G[c * LDP + p] = i >= 0 ? tp[3 * i + c] / x_abs : 0.f;
   }
   __syncthreads();
   mlp::block_dense<3, 32>(G, pk + S_PE0W, pk + S_PE0B, nullptr, nullptr, true, F, s_w);
@@ -98,23 +99,23 @@ __global__ void __launch_bounds__(256) k_stpn_head(const float* __restrict__ mos
       v.z = fmaf(d.z, bl.w11, fmaf(c.z, bl.w10, fmaf(b.z, bl.w01, a.z * bl.w00)));
       v.w = fmaf(d.w, bl.w11, fmaf(c.w, bl.w10, fmaf(b.w, bl.w01, a.w * bl.w00)));
     }
-    E[(64 + 4 * q + 0) * PTS + p] = v.x;
-    E[(64 + 4 * q + 1) * PTS + p] = v.y;
-    E[(64 + 4 * q + 2) * PTS + p] = v.z;
-    E[(64 + 4 * q + 3) * PTS + p] = v.w;
+    E[(64 + 4 * q + 0) * LDP + p] = v.x;
+    E[(64 + 4 * q + 1) * LDP + p] = v.y;
+    E[(64 + 4 * q + 2) * LDP + p] = v.z;
+    E[(64 + 4 * q + 3) * LDP + p] = v.w;
   }
   __syncthreads();
   mlp::block_dense<128, 128>(E, pk + S_FPW, pk + S_FPB, nullptr, nullptr, true, F, s_w);
   mlp::block_dense<128, 128>(F, pk + S_M0W, pk + S_M0B, pk + S_M0S, pk + S_M0T, true, G, s_w);
   mlp::block_dense_small<128, 2>(G, pk + S_M3W, pk + S_M3B, s_o);
   mlp::block_dense<128, 128>(F, pk + S_O0W, pk + S_O0B, pk + S_O0S, pk + S_O0T, true, E, s_w);
-  mlp::block_dense_small<128, 2>(E, pk + S_O3W, pk + S_O3B, s_o + 2 * PTS);
+  mlp::block_dense_small<128, 2>(E, pk + S_O3W, pk + S_O3B, s_o + 2 * LDP);
   for (int e = threadIdx.x; e < PTS * 2; e += 256) {
     int p = e % PTS, o = e / PTS;
     int i = s_idx[p];
     if (i < 0) continue;
-    mos_out[2 * i + o] = s_o[o * PTS + p];
-    float v = s_o[(2 + o) * PTS + p];
+    mos_out[2 * i + o] = s_o[o * LDP + p];
+    float v = s_o[(2 + o) * LDP + p];
     if (isnan(v) || isinf(v)) v = 0.f;  // safe_guard_offset (models/stpn.py:61-65)
     off_out[2 * i + o] = fminf(fmaxf(v, -20.f), 20.f);
   }
@@ -144,10 +145,23 @@ __device__ void embed_and_max(float* A, float* Bf, float* s_w, const float* __re
   mlp::block_dense<IN, H1>(A, W0, b0, nullptr, nullptr, true, Bf, s_w);
   mlp::block_dense<H1, H2>(Bf, W1, b1, nullptr, nullptr, true, A, s_w);
   mlp::block_dense<H2, 128>(A, W2, b2, nullptr, nullptr, false, Bf, s_w);
-  for (int e = threadIdx.x; e < PTS * 128; e += 256) {
-    int p = e % PTS, c = e / PTS;
-    int s = s_seg[p];
-    if (s >= 0) mlp::atomic_max_float(dst + (size_t)s * 128 + c, Bf[c * PTS + p]);
+  // points arrive sorted by segment, so a CTA sees a few runs: reduce each run in shared memory and issue ONE
+  // atomic per (run, channel).  Two threads per channel, each scanning half of the rows.
+  {
+    const int c = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const float* row = Bf + c * LDP;
+    int cur_seg = -1;
+    float cur = -INFINITY;
+    for (int p = half * (PTS / 2); p < (half + 1) * (PTS / 2); ++p) {
+      int s = s_seg[p];
+      if (s != cur_seg) {
+        if (cur_seg >= 0) mlp::atomic_max_float(dst + (size_t)cur_seg * 128 + c, cur);
+        cur_seg = s;
+        cur = -INFINITY;
+      }
+      if (s >= 0) cur = fmaxf(cur, row[p]);
+    }
+    if (cur_seg >= 0) mlp::atomic_max_float(dst + (size_t)cur_seg * 128 + c, cur);
   }
   __syncthreads();
 }
@@ -161,8 +175,8 @@ __global__ void __launch_bounds__(256) k_tpn_static_embed(const float* __restric
                                                           float* __restrict__ geo_emb) {
   extern __shared__ __align__(16) float sm[];
   float* A = sm;
-  float* Bf = A + 128 * PTS;
-  float* s_w = Bf + 128 * PTS;
+  float* Bf = A + 128 * LDP;
+  float* s_w = Bf + 128 * LDP;
   __shared__ int s_seg[PTS], s_src[PTS];
   int base = blockIdx.x * PTS;
   if (threadIdx.x < PTS) {
@@ -173,13 +187,13 @@ __global__ void __launch_bounds__(256) k_tpn_static_embed(const float* __restric
   __syncthreads();
   for (int e = threadIdx.x; e < PTS * 64; e += 256) {
     int p = e / 64, c = e % 64;
-    A[c * PTS + p] = s_src[p] >= 0 ? mos_feat[(size_t)s_src[p] * 64 + c] : 0.f;
+    A[c * LDP + p] = s_src[p] >= 0 ? mos_feat[(size_t)s_src[p] * 64 + c] : 0.f;
   }
   __syncthreads();
   embed_and_max<64, 64, 128>(A, Bf, s_w, pk_motion, s_seg, mos_emb);
   for (int e = threadIdx.x; e < PTS * 32; e += 256) {
     int p = e / 32, c = e % 32;
-    A[c * PTS + p] = s_src[p] >= 0 ? geo_feat[(size_t)s_src[p] * 32 + c] : 0.f;
+    A[c * LDP + p] = s_src[p] >= 0 ? geo_feat[(size_t)s_src[p] * 32 + c] : 0.f;
   }
   __syncthreads();
   embed_and_max<32, 32, 64>(A, Bf, s_w, pk_geo, s_seg, geo_emb);
@@ -203,8 +217,8 @@ __global__ void __launch_bounds__(256) k_tpn_pos_embed(const float* __restrict__
                                                        float* __restrict__ frame_emb) {
   extern __shared__ __align__(16) float sm[];
   float* A = sm;
-  float* Bf = A + 128 * PTS;
-  float* s_w = Bf + 128 * PTS;
+  float* Bf = A + 128 * LDP;
+  float* s_w = Bf + 128 * LDP;
   __shared__ int s_seg[PTS];
   int base = blockIdx.x * PTS;
   if (threadIdx.x < PTS) {
@@ -215,13 +229,13 @@ __global__ void __launch_bounds__(256) k_tpn_pos_embed(const float* __restrict__
       s_seg[p] = k * T + t;
       const double* s = sums + (size_t)k * T * 4;  // anchor frame (t = 0) of the instance
       double cnt = s[3] > 0 ? s[3] : 1.0;
-      A[0 * PTS + p] = pts[3 * j] - (float)(s[0] / cnt);
-      A[1 * PTS + p] = pts[3 * j + 1] - (float)(s[1] / cnt);
-      A[2 * PTS + p] = pts[3 * j + 2] - (float)(s[2] / cnt);
-      A[3 * PTS + p] = (float)((double)t / (double)T);
+      A[0 * LDP + p] = pts[3 * j] - (float)(s[0] / cnt);
+      A[1 * LDP + p] = pts[3 * j + 1] - (float)(s[1] / cnt);
+      A[2 * LDP + p] = pts[3 * j + 2] - (float)(s[2] / cnt);
+      A[3 * LDP + p] = (float)((double)t / (double)T);
     } else {
       s_seg[p] = -1;
-      A[p] = A[PTS + p] = A[2 * PTS + p] = A[3 * PTS + p] = 0.f;
+      A[p] = A[LDP + p] = A[2 * LDP + p] = A[3 * LDP + p] = 0.f;
     }
   }
   __syncthreads();
@@ -393,7 +407,7 @@ extern "C" int pcab_stpn_head(const float* mos_feats_nhwc, int H, int W, const f
                               const int* point_batch, const int* fg_idx, int n_fg, const float* weight_pack,
                               float x_abs, float y_abs, float* mos_out, float* offset_out, cudaStream_t stream) {
   if (n_fg <= 0) return PCAB_OK;
-  size_t smem = (size_t)(3 * 128 * PTS + mlp::KC * 128 + 4 * PTS) * sizeof(float);
+  size_t smem = (size_t)(3 * 128 * LDP + mlp::KC * 128 + 4 * LDP) * sizeof(float);
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(k_stpn_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -409,7 +423,7 @@ extern "C" int pcab_stpn_head(const float* mos_feats_nhwc, int H, int W, const f
 extern "C" int pcab_tpn_static_embed(const float* mos_feat, const float* geo_feat, const int* src_idx, const int* inst,
                                      int n, int K, const float* pack_motion, const float* pack_geo, float* mos_emb,
                                      float* geo_emb, cudaStream_t stream) {
-  size_t smem = (size_t)(2 * 128 * PTS + mlp::KC * 128) * sizeof(float);
+  size_t smem = (size_t)(2 * 128 * LDP + mlp::KC * 128) * sizeof(float);
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(k_tpn_static_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -452,7 +466,7 @@ extern "C" int pcab_tpn_iteration(const float* points, const int* inst, const in
   f += kt * 8;
   double* sums = (double*)((char*)workspace + al256p(kt * (128 + 512 + 256 + 128 + 8) * 4));
   PCAB_CUDA(cudaMemsetAsync(sums, 0, kt * 4 * 8, stream));
-  size_t smem = (size_t)(2 * 128 * PTS + mlp::KC * 128) * sizeof(float);
+  size_t smem = (size_t)(2 * 128 * LDP + mlp::KC * 128) * sizeof(float);
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(k_tpn_pos_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -225,6 +225,9 @@ class MotionNet(nn.Module):
         self.use_tensor_cores = True
         self.stages = {}  # stage-boundary tensors of the last forward (for stage-wise parity tests)
         self.keep_stages = False
+        # stage-wise parity protocol: tensors placed here replace the computed value for the stages
+        # DOWNSTREAM of it; keys: 'ego_motion_est' [B,T,4,4], 'mos_est' [N,2], 'offset_est' [N,2], 'inst_labels_est' [N]
+        self.inject = {}
         self.conv_events = None  # when a list: (start_event, end_event, flops, path) per conv launch (bench roofline)
 
     # ------------------------------------------------------------------------------------------
@@ -462,6 +465,8 @@ class MotionNet(nn.Module):
 
         # 5. warp + motion segmentation
         pose_est = results["ego_motion_est"].float().contiguous()
+        if "ego_motion_est" in self.inject:
+            pose_est = self.inject["ego_motion_est"].to(dev).float().contiguous()
         warped = torch.empty(B * T, Ny, Nx, 32, device=dev)
         call("pcab_warp_bev", P(bev_feats), P(pose_est), I(B), I(T), I(Ny), I(Nx), I(32), F(self.resolution[0]),
              F(self.resolution[1]), F(self.pc_range[0]), F(self.pc_range[1]), P(warped), stream())
@@ -491,6 +496,10 @@ class MotionNet(nn.Module):
         if self.keep_stages:
             st.update(warped=warped, mos_feats=mos_feats)
         results["mos_est"], results["offset_est"] = full_mos, full_off
+        if "mos_est" in self.inject:
+            full_mos = self.inject["mos_est"].to(dev).float().contiguous()
+        if "offset_est" in self.inject:
+            full_off = self.inject["offset_est"].to(dev).float().contiguous()
         rec_est = tp.clone()
         results["rec_est"] = rec_est
 
@@ -501,6 +510,8 @@ class MotionNet(nn.Module):
         else:
             inst_labels = self._cluster(tp, full_mos, full_off, input_dict["num_points"], B, N, dev)
             results["inst_labels_est"] = inst_labels
+            if "inst_labels_est" in self.inject:
+                inst_labels = self.inject["inst_labels_est"].to(dev).long().contiguous()
             rec_idx, n_rec = self._select(N, dev, flags=(inst_labels != 0).to(torch.int32))
         if n_rec > MIN_POINTS:
             if mos_feats is None:  # quirk Q4 (motionnet.py:222-245): upstream dies with NameError here
@@ -638,41 +649,38 @@ class MotionNet(nn.Module):
             g = ego_gt[b][None].repeat(K, 1, 1, 1).view(-1, 4, 4)
             e = ego_est[b][None].repeat(K, 1, 1, 1).view(-1, 4, 4)
             upd.append((m.reshape(-1, 4, 4) @ g @ torch.linalg.inv(e)).view(K, -1, 4, 4))
-        run = 0
-        tb = time_indice[:, 0]
-        for b in range(len(upd)):
-            sel = tb == b
-            if bool(sel.any()):
-                inst_labels[sel] += run
-                run += upd[b].size(0)
+        # alignnet.py:201-206: instance ids become global over the batch (scenes without points do not advance the offset)
+        tb = time_indice[:, 0].long()
+        ks = torch.tensor([u.size(0) for u in upd], device=dev)
+        has = torch.bincount(tb, minlength=len(upd))[:len(upd)] > 0
+        ks_eff = ks * has
+        inst_labels = inst_labels + (torch.cumsum(ks_eff, 0) - ks_eff)[tb]
         motion = torch.cat(upd)
         K = motion.size(0)
         t_idx = time_indice[:, 1].long()
         frame_indice = inst_labels * T + t_idx
         frame_count = torch.zeros(K * T, device=dev).scatter_add_(0, frame_indice, torch.ones(n_points, device=dev))
-        inst_count = frame_count.view(K, T).sum(1)
-        anchor_count = frame_count[::T]
-        pad = []
-        for k in torch.where((anchor_count == 0) & (inst_count > 0))[0].tolist():  # alignnet.py:137-151
-            c = frame_count[k * T:(k + 1) * T]
-            f = k * T + int(torch.where(c > 0)[0][0])
-            pad.append(torch.where(frame_indice == f)[0])
+        fc = frame_count.view(K, T)
+        inst_count = fc.sum(1)
+        # alignnet.py:137-151: instances without anchor-frame points get the points of their first non-empty frame
+        # duplicated as t = 0 (vectorised; the order of the padded rows is irrelevant to every consumer)
+        need = (fc[:, 0] == 0) & (inst_count > 0)
+        first_frame = (fc > 0).float().argmax(1)
+        pad = torch.nonzero(need[inst_labels] & (t_idx == first_frame[inst_labels]))[:, 0]
         keep = inst_count > 0
         motion = motion[keep]
-        mapping = -torch.ones(K, dtype=torch.long, device=dev)
-        mapping[keep] = torch.arange(int(keep.sum()), device=dev)
+        mapping = torch.cumsum(keep.long(), 0) - 1
         inst_labels = mapping[inst_labels]
         inst_motion_gt = motion.clone()
         K = motion.size(0)
-        if pad:
-            pad = torch.cat(pad)
-            p_time = torch.cat((t_idx, torch.zeros_like(pad)))
-            p_idx = torch.cat((torch.arange(n_points, device=dev), pad))
-        else:
-            p_time, p_idx = t_idx, torch.arange(n_points, device=dev)
+        p_time = torch.cat((t_idx, torch.zeros_like(pad)))
+        p_idx = torch.cat((torch.arange(n_points, device=dev), pad))
+        p_inst = inst_labels[p_idx]
+        # sort the (padded) rows by (instance, frame): segment max-pools become run reductions inside a CTA
+        order = torch.sort(p_inst * T + p_time, stable=True)[1]
+        p_idx, p_time, p_inst = p_idx[order], p_time[order], p_inst[order]
         n_pad = p_idx.numel()
         p_idx32 = p_idx.to(torch.int32).contiguous()
-        p_inst = inst_labels[p_idx]
         p_inst32 = p_inst.to(torch.int32).contiguous()
         p_time32 = p_time.to(torch.int32).contiguous()
         p_seg32 = (p_inst32 * T + p_time32).contiguous()

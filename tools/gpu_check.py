@@ -34,6 +34,8 @@ torch.manual_seed(42)
 t = time.time()
 ref = orc.forward(inp)
 print("oracle s", time.time() - t)
+for kk, vv in ref.get("tpointnet_loss_terms", {}).items():
+    print(kk, {n: float(x) for n, x in vv.items() if n != "inst_est_motion"})
 inp_g = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in inp.items()}
 torch.manual_seed(42)
 t = time.time()
