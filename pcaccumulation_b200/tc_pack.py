@@ -1,0 +1,12 @@
+"""Weight pack of the tcgen05 convolution path: [2 (hi, lo)][Cout][K] with K = the row order of the FP32 pack
+(per source: tap-major, channel-minor).  hi = the 19 bits a kind::tf32 MMA reads (sign, exponent, 10 mantissa bits),
+lo = w - hi (exact in FP32); see csrc/conv_tc.cu."""
+import torch
+
+
+def pack_conv_tc(layer):
+    k = layer.pack.numel() // layer.cout
+    w = layer.pack.view(k, layer.cout).t().contiguous()  # [Cout][K]
+    hi = (w.view(torch.int32) & -8192).view(torch.float32)  # 0xffffe000
+    lo = w - hi
+    return torch.cat((hi, lo), 0).contiguous()

@@ -1,0 +1,70 @@
+"""Developer script: tcgen05 conv vs FP32 CUDA-core conv on the layer shapes of the model (accuracy + time)."""
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from pcaccumulation_b200 import _lib, motionnet as mn, tc_pack  # noqa: E402
+from pcaccumulation_b200._lib import I, P, call, stream  # noqa: E402
+
+mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+_lib.lib().pcab_conv3x3_tc_set_base_offset_mode(I(mode))
+torch.manual_seed(0)
+dev = "cuda"
+# (n_img, [src channels], Cout, H, W, temporal_T)
+shapes = [(5, [32], 32, 288, 288, 1), (5, [32], 64, 288, 288, 1), (5, [64], 64, 144, 144, 1), (5, [32, 32], 32, 288, 288, 1),
+          (5, [64, 64], 64, 144, 144, 1), (5, [128], 128, 72, 72, 1), (5, [128, 128], 128, 72, 72, 1), (5, [64], 128, 72, 72, 1),
+          (5, [32], 32, 288, 288, 5), (1, [64], 64, 288, 288, 1), (2, [32], 32, 100, 76, 1), (1, [256], 256, 72, 72, 1)]
+for n, cs, cout, H, W, T in shapes:
+    cin = sum(cs)
+    xs = [torch.randn(n, H, W, c, device=dev) for c in cs]
+    if T > 1:
+        w = torch.randn(cout, cs[0], 3, 3, 3, device=dev) * 0.1
+
+        class Lyr:
+            pass
+        conv = type("C", (), {"weight": w, "bias": torch.randn(cout, device=dev)})()
+        layer = mn._ConvLayer(conv, temporal=True)
+        srcs = [xs[0]] * 3
+        c3 = [cs[0]] * 3
+    else:
+        w = torch.randn(cout, cin, 3, 3, device=dev) * 0.1
+        conv = type("C", (), {"weight": w, "bias": torch.randn(cout, device=dev)})()
+        layer = mn._ConvLayer(conv, splits=cs)
+        srcs = xs + [None] * (3 - len(xs))
+        c3 = cs + [0] * (3 - len(cs))
+    ok = _lib.lib().pcab_conv3x3_tc_supported(I(3 if T > 1 else len(cs)), I(c3[0]), I(c3[1]), I(c3[2]), I(cout), I(H), I(W))
+    ref = torch.empty(n, H, W, cout, device=dev)
+    out = torch.full((n, H, W, cout), float("nan"), device=dev)
+    sc, sh = torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev)
+    args = lambda pack, o: (P(srcs[0]), I(c3[0]), P(srcs[1]), I(c3[1]), P(srcs[2]), I(c3[2]), I(T), P(pack), P(layer.bias), P(sc), P(sh),
+                            I(1), P(o), I(n), I(H), I(W), I(cout), I(cout), I(0), stream())
+    call("pcab_conv3x3_f32", *args(layer.pack, ref))
+    torch.cuda.synchronize()
+    if not ok:
+        print(f"shape n={n} cs={cs} cout={cout} {H}x{W} T={T}: TC unsupported")
+        continue
+    tcw = tc_pack.pack_conv_tc(layer)
+    try:
+        call("pcab_conv3x3_tc", *args(tcw, out))
+        torch.cuda.synchronize()
+    except Exception as e:
+        print("TC FAILED", n, cs, cout, H, W, T, e)
+        sys.exit(1)
+    err = (out - ref).abs().max().item()
+    nan = torch.isnan(out).sum().item()
+    flops = 2.0 * 9 * cin * cout * H * W * n * (1 if T == 1 else (3 * T - 2) / T)
+    ts = {}
+    for name, fn, pack, o in (("f32", "pcab_conv3x3_f32", layer.pack, ref), ("tc", "pcab_conv3x3_tc", tcw, out)):
+        for _ in range(2):
+            call(fn, *args(pack, o))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            call(fn, *args(pack, o))
+        e1.record()
+        torch.cuda.synchronize()
+        ts[name] = e0.elapsed_time(e1) / 10
+    print(f"n={n} cs={cs} cout={cout} {H}x{W} T={T}: maxerr {err:.3e} (ref max {ref.abs().max().item():.1f}) nan {nan} | "
+          f"f32 {ts['f32']:.3f} ms {flops / ts['f32'] / 1e9:.1f} TF/s | tc {ts['tc']:.3f} ms {flops / ts['tc'] / 1e9:.1f} TF/s")
