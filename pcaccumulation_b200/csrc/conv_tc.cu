@@ -11,7 +11,7 @@
 // 128 bytes per pixel = one swizzle row.  Output pixels are indexed in the FLATTENED padded grid m = r*(Wt+2)+x,
 // so the A operand of tap (ky,kx) is the same plane viewed from row  m + ky*(Wt+2) + kx : nine shifted views of
 // one staged plane instead of nine loads (the two extra columns per row compute garbage that is never stored).
-// 3xTF32:  a = a_hi + a_lo, w = w_hi + w_lo with *_hi = the 19 bits the tensor core reads;
+// 3xTF32:  a = a_hi + a_lo, w = w_hi + w_lo with *_hi = the value rounded to the nearest tf32 (19 bits);
 //          acc += a_lo*w_hi + a_hi*w_lo + a_hi*w_hi   (a_lo*w_lo ~ 2^-22 is dropped).
 // w_hi / w_lo are pre-split on the host; a_lo is produced in shared memory by the epilogue warps right after the
 // plane lands.  Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = a_lo split and
@@ -150,7 +150,7 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
   }
 
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < a.mt * a.cout_t) tmem_cols <<= 1;
+  while ((int)tmem_cols < 2 * a.mt * a.cout_t) tmem_cols <<= 1;  // main + correction accumulators
 
   if (threadIdx.x == 0) {
     mbar_init(bar_a_full, 1);
@@ -219,15 +219,19 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
           for (int mt = 0; mt < a.mt; ++mt) {
             const uint32_t row_off = (uint32_t)(mt * 128 + shift_rows) * 128u;
             const uint32_t ah = smem_u32(plane_hi) + row_off, al = smem_u32(plane_lo) + row_off;
+            // two accumulators per tile: the big a_hi*w_hi products and the ~2^-11 smaller correction products.  The
+            // tensor core truncates when it adds into the FP32 accumulator, so keeping the small terms out of the
+            // large accumulator cuts its number of (biased) roundings from 3K/8 to K/8.
             const uint32_t tmem_d = tmem_base + (uint32_t)(mt * a.cout_t);
+            const uint32_t tmem_c = tmem_base + (uint32_t)((a.mt + mt) * a.cout_t);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint32_t first = (ci == 0 && tap == 0 && kk == 0) ? 0u : 1u;
               const uint64_t dah = umma_desc(ah + kk * 32, a.base_offset_mode), dal = umma_desc(al + kk * 32, a.base_offset_mode);
               const uint64_t dbh = umma_desc(bh + kk * 32, 0), dbl = umma_desc(bl + kk * 32, 0);
-              umma_tf32(tmem_d, dal, dbh, idesc, first);  // small terms first
-              umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-              umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+              umma_tf32(tmem_c, dal, dbh, idesc, first);
+              umma_tf32(tmem_c, dah, dbl, idesc, 1u);
+              umma_tf32(tmem_d, dah, dbh, idesc, first);
             }
           }
           umma_commit(bar_b_empty0 + 8 * bs);  // frees this weight stage once the MMAs above retire
@@ -245,16 +249,16 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
     const int n_f4 = (a.R + 2) * a.Wp * 8;  // float4 per plane (the rows the TMA box wrote)
     for (int ci = 0; ci < nchunks; ++ci) {
       mbar_wait(bar_a_full, ci & 1);
-      const float4* hi = reinterpret_cast<const float4*>(plane_hi);
+      float4* hi = reinterpret_cast<float4*>(plane_hi);
       float4* lo = reinterpret_cast<float4*>(plane_lo);
+      // hi := a rounded to NEAREST tf32 (so the split error is zero-mean; truncation would bias every term the same
+      // way and the error would grow ~K instead of ~sqrt(K)); lo := a - hi (exact in FP32)
+      auto rnd = [](float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); };
       for (int i = et; i < n_f4; i += 128) {
         float4 v = hi[i];
-        float4 r;
-        r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-        r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-        r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-        r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-        lo[i] = r;
+        float4 h = make_float4(rnd(v.x), rnd(v.y), rnd(v.z), rnd(v.w));
+        hi[i] = h;
+        lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
       mbar_arrive(bar_lo_done);
@@ -269,8 +273,9 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
       const bool valid = r < a.R && xc < a.Wt && gy < a.H && gx < a.W;
       float* orow = a.out + (((size_t)n * a.H + gy) * a.W + gx) * a.out_cstride + a.out_coff + co0;
       for (int c32 = 0; c32 < a.cout_t / 32; ++c32) {
-        uint32_t v[32];
+        uint32_t v[32], vc[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * a.cout_t + c32 * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((a.mt + mt) * a.cout_t + c32 * 32), vc);
         if (valid) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -278,7 +283,7 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               int co = co0 + c32 * 32 + 4 * q + u;
-              float f = __uint_as_float(v[4 * q + u]) + a.bias[co];
+              float f = (__uint_as_float(v[4 * q + u]) + __uint_as_float(vc[4 * q + u])) + a.bias[co];
               if (a.bn_scale) f = fmaf(f, a.bn_scale[co], a.bn_shift[co]);
               o[u] = a.relu ? fmaxf(f, 0.f) : f;
             }
@@ -319,9 +324,9 @@ struct TileCfg {
 
 bool choose_cfg(int H, int W, int Cout, TileCfg* c) {
   if (Cout % 32) return false;
-  c->cout_t = Cout <= 128 ? Cout : 128;
+  c->cout_t = Cout <= 64 ? Cout : 64;  // 2 accumulators x 4 M-tiles x 64 columns = the 512 TMEM columns
   if (Cout % c->cout_t) return false;
-  c->mt = c->cout_t <= 64 ? 4 : 3;
+  c->mt = 4;
   // widest column tile with Wt + 2 <= 98 that divides W when possible
   int Wt = W <= 96 ? W : 96;
   for (int cand = 96; cand >= 48; --cand)
@@ -356,7 +361,7 @@ extern "C" int pcab_conv3x3_tc_supported(int n_sources, int c0, int c1, int c2, 
   int cs[3] = {c0, c1, c2};
   for (int s = 0; s < n_sources; ++s)
     if (cs[s] <= 0 || cs[s] % 32) return 0;
-  if (H < 64 || W < 64) return 0;  // small maps keep the FP32 CUDA-core path (too few tiles for 148 SMs)
+  if (H < 32 || W < 32) return 0;  // the smallest maps keep the FP32 CUDA-core path (too few tiles for 148 SMs)
   TileCfg c;
   return choose_cfg(H, W, Cout, &c) ? 1 : 0;
 }

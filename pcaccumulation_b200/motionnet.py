@@ -226,7 +226,8 @@ class MotionNet(nn.Module):
         self.stages = {}  # stage-boundary tensors of the last forward (for stage-wise parity tests)
         self.keep_stages = False
         # stage-wise parity protocol: tensors placed here replace the computed value for the stages
-        # DOWNSTREAM of it; keys: 'ego_motion_est' [B,T,4,4], 'mos_est' [N,2], 'offset_est' [N,2], 'inst_labels_est' [N]
+        # DOWNSTREAM of it; keys: 'fb_est_map' [B,T,1,Ny,Nx], 'ego_motion_est' [B,T,4,4], 'mos_est' [N,2],
+        # 'offset_est' [N,2], 'inst_labels_est' [N]
         self.inject = {}
         self.conv_events = None  # when a list: (start_event, end_event, flops, path) per conv launch (bench roofline)
 
@@ -449,6 +450,8 @@ class MotionNet(nn.Module):
         fb_est = torch.empty(B * T * HW, dtype=torch.int32, device=dev)
         call("pcab_head2_conv", P(h), I(32), P(W["sem3"][0]), P(W["sem3"][1]), I(B * T), I(Ny), I(Nx), P(fb_seg),
              P(fb_est), stream())
+        if "fb_est_map" in self.inject:  # [B,T,1,Ny,Nx] or flat: the argmax map the ego head and the gathers consume
+            fb_est = self.inject["fb_est_map"].to(dev).reshape(-1).to(torch.int32).contiguous()
         fb_pp = torch.empty(N, 1, dtype=torch.int64, device=dev)
         call("pcab_fb_per_point", P(fb_est), P(pillar_cell), P(p2v), I(N), P(fb_pp), stream())
         results["fb_seg_est"] = fb_seg
@@ -765,29 +768,22 @@ class MotionNet(nn.Module):
 
 def _mat2quat_scipy(R):
     """scipy.spatial.transform.Rotation.from_matrix(R).as_quat() (xyzw), as used at models/tpointnet.py:66-67:
-    non-orthogonal inputs are projected with an SVD first, then the largest-component branch is taken."""
+    the input is projected onto SO(3) with an SVD (scipy does so for inputs that are not orthogonal to 1e-12, which
+    is every float32 matrix; for exactly orthogonal ones the projection is the identity to 1e-16), then scipy's
+    largest-component branch is taken.  Branch-free (no boolean-mask indexing) so it costs a handful of launches."""
     M = R.double()
-    gram = M @ M.transpose(1, 2)
-    bad = ~torch.isclose(gram, torch.eye(3, dtype=M.dtype, device=M.device)[None].expand_as(gram), atol=1e-12, rtol=1e-5).all(-1).all(-1)
-    if bool(bad.any()):
-        U, _, Vt = torch.linalg.svd(M[bad])
-        M = M.clone()
-        M[bad] = U @ Vt
-    diag = torch.diagonal(M, dim1=1, dim2=2)
-    dec = torch.cat((diag, diag.sum(1, keepdim=True)), 1)
+    U, _, Vt = torch.linalg.svd(M)
+    M = U @ Vt
+    m = lambda i, j: M[:, i, j]
+    d0, d1, d2 = m(0, 0), m(1, 1), m(2, 2)
+    tr = d0 + d1 + d2
+    dec = torch.stack((d0, d1, d2, tr), 1)
     choice = dec.argmax(1)
-    q = torch.empty(M.shape[0], 4, dtype=M.dtype, device=M.device)
-    for i in range(3):
-        j, k = (i + 1) % 3, (i + 2) % 3
-        s = choice == i
-        q[s, i] = 1 - dec[s, 3] + 2 * M[s, i, i]
-        q[s, j] = M[s, j, i] + M[s, i, j]
-        q[s, k] = M[s, k, i] + M[s, i, k]
-        q[s, 3] = M[s, k, j] - M[s, j, k]
-    s = choice == 3
-    q[s, 0] = M[s, 2, 1] - M[s, 1, 2]
-    q[s, 1] = M[s, 0, 2] - M[s, 2, 0]
-    q[s, 2] = M[s, 1, 0] - M[s, 0, 1]
-    q[s, 3] = 1 + dec[s, 3]
+    q0 = torch.stack((1 - tr + 2 * d0, m(1, 0) + m(0, 1), m(2, 0) + m(0, 2), m(2, 1) - m(1, 2)), 1)
+    q1 = torch.stack((m(0, 1) + m(1, 0), 1 - tr + 2 * d1, m(2, 1) + m(1, 2), m(0, 2) - m(2, 0)), 1)
+    q2 = torch.stack((m(0, 2) + m(2, 0), m(1, 2) + m(2, 1), 1 - tr + 2 * d2, m(1, 0) - m(0, 1)), 1)
+    q3 = torch.stack((m(2, 1) - m(1, 2), m(0, 2) - m(2, 0), m(1, 0) - m(0, 1), 1 + tr), 1)
+    allq = torch.stack((q0, q1, q2, q3), 1)  # [n, case, 4]
+    q = allq.gather(1, choice.view(-1, 1, 1).expand(-1, 1, 4))[:, 0]
     q = q / torch.norm(q, dim=1, keepdim=True)
     return q.float()
