@@ -149,6 +149,7 @@ def main():
         return run_reference(args, rank, world)
     args.warmup = max(args.warmup, 3)
 
+    torch.set_num_threads(1)  # the GPU arm's host logic is single-threaded (OpenMP fan-out only slows torch.randperm)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     import torch.distributed as dist

@@ -229,6 +229,7 @@ class MotionNet(nn.Module):
         # DOWNSTREAM of it; keys: 'fb_est_map' [B,T,1,Ny,Nx], 'ego_motion_est' [B,T,4,4], 'mos_est' [N,2],
         # 'offset_est' [N,2], 'inst_labels_est' [N]
         self.inject = {}
+        self.stage_marks = None  # when a list: (name, cuda event) at stage boundaries (profiling aid)
         self.conv_events = None  # when a list: (start_event, end_event, flops, path) per conv launch (bench roofline)
 
     # ------------------------------------------------------------------------------------------
@@ -369,6 +370,12 @@ class MotionNet(nn.Module):
     def _count(self, t):
         return int(t.item())
 
+    def _mark(self, name):
+        if self.stage_marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.stage_marks.append((name, e))
+
     def _select(self, n, dev, flags=None, values=None, value=0):
         idx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -384,6 +391,7 @@ class MotionNet(nn.Module):
         """Same contract as ``models/motionnet.py:137-262`` (inference; gradients are round-2 work)."""
         W = self._weights()
         st = self.stages = {}
+        self._deferred = []  # (keys, device tensor): python floats of the API are fetched with ONE sync at the end
         cfg = self.cfg
         pts = input_dict["input_points"].float().contiguous()
         dev = pts.device
@@ -402,6 +410,7 @@ class MotionNet(nn.Module):
         vsz = host_floats(self.resolution)
         x_abs, y_abs = abs(float(self.pc_range[0])), abs(float(self.pc_range[1]))
 
+        self._mark("start")
         # schema -> compact int32 device arrays
         p2v = input_dict["point_to_voxel_map"].reshape(-1).to(torch.int32).contiguous()
         pbatch = time_indice[:, 0].to(torch.int32).contiguous()
@@ -432,6 +441,7 @@ class MotionNet(nn.Module):
              P(mean_map), stream())
         results = {"fb_seg_gt": fb_map, "occ_map": occ_map}
 
+        self._mark("index+stats")
         # 1. pillar encoder -> BEV canvas
         canvas = torch.zeros(B * T, Ny, Nx, 32, device=dev)
         pillar_feats = torch.empty(M, 32, device=dev)
@@ -441,9 +451,11 @@ class MotionNet(nn.Module):
              Z(ws.numel()), stream())
         del ws
 
+        self._mark("pillar_encoder")
         # 2. UNet backbone
         bev_feats = self._unet(W, "unet.", canvas, B * T, Ny, Nx, cfg["unet"]["depth"], True)
 
+        self._mark("unet")
         # 3. FG/BG head
         h = self._conv(W["sem0"], [bev_feats], B * T, Ny, Nx, True)
         fb_seg = torch.empty(B, T, 2, Ny, Nx, device=dev)
@@ -457,15 +469,19 @@ class MotionNet(nn.Module):
         results["fb_seg_est"] = fb_seg
         results["fb_est_per_points"] = fb_pp
 
-        # 4. ego-motion
+        self._mark("fb_head")
+        # 4. ego-motion: the background-pillar counts start their trip to the host before the head convolutions are
+        # queued, so the host draws the keypoint permutations while the GPU is busy with them
+        prep = self._ego_prepare(cell2pillar, fb_est, M, B, T, Ny, Nx)
         h = self._conv(W["ego0"], [bev_feats], B * T, Ny, Nx, True)
         geo = self._conv(W["ego3"], [h], B * T, Ny, Nx, False)
         del h
-        self._ego_motion(W, geo, cell2pillar, fb_est, pillar_mean, pillar_frame, M, ego_gt, B, T, Ny, Nx, results)
+        self._ego_motion(W, geo, cell2pillar, prep, pillar_mean, pillar_frame, M, ego_gt, B, T, Ny, Nx, results)
         if self.keep_stages:
             st.update(pillar_mean=pillar_mean, pillar_feats=pillar_feats, bev_feats=bev_feats, geo=geo, fb_est=fb_est)
         del geo
 
+        self._mark("ego")
         # 5. warp + motion segmentation
         pose_est = results["ego_motion_est"].float().contiguous()
         if "ego_motion_est" in self.inject:
@@ -506,6 +522,7 @@ class MotionNet(nn.Module):
         rec_est = tp.clone()
         results["rec_est"] = rec_est
 
+        self._mark("warp+stpn")
         # 6. instances + TubeNet
         if self.mode in ("train", "val"):
             inst_labels = input_dict["inst_labels"][:, 0].long().contiguous()
@@ -513,6 +530,7 @@ class MotionNet(nn.Module):
         else:
             inst_labels = self._cluster(tp, full_mos, full_off, input_dict["num_points"], B, N, dev)
             results["inst_labels_est"] = inst_labels
+            self._mark("cluster")
             if "inst_labels_est" in self.inject:
                 inst_labels = self.inject["inst_labels_est"].to(dev).long().contiguous()
             rec_idx, n_rec = self._select(N, dev, flags=(inst_labels != 0).to(torch.int32))
@@ -534,15 +552,21 @@ class MotionNet(nn.Module):
                 "mos_labels": input_dict["sd_labels"][ridx, 0].long(), "ego_motion_est": results["ego_motion_est"],
                 "ego_motion_gt": results["ego_motion_gt"]}, results, T)
             call("pcab_scatter_rows3", P(results["sub_rec_est"]), P(rec_idx), I(n_rec), P(rec_est), stream())
+        self._mark("tubenet")
+        if self._deferred:
+            vals = torch.cat([t.reshape(-1).float() for _, t in self._deferred]).cpu().tolist()
+            i = 0
+            for keys, _ in self._deferred:
+                for k in keys:
+                    results[k] = vals[i]
+                    i += 1
         return results
 
     # ------------------------------------------------------------------------------------------
-    def _ego_motion(self, W, geo, cell2pillar, fb_est, pillar_mean, pillar_frame, M, ego_gt, B, T, Ny, Nx, results):
-        """models/egomotion.py:387-469.  The host only draws the keypoint permutations (H3 protocol:
-        ``torch.randperm`` on the CPU generator, in the reference's order) from ONE readback of the
-        per-frame background-pillar counts; everything else is batched over all pairs on the device."""
-        dev = geo.device
-        cfg = self.cfg
+    def _ego_prepare(self, cell2pillar, fb_est, M, B, T, Ny, Nx):
+        """Compact the occupied background cells per frame (cell order, like the boolean masks of
+        models/egomotion.py:418-430) and start the asynchronous readback of the per-frame counts."""
+        dev = cell2pillar.device
         nF = B * T
         ncell = nF * Ny * Nx
         bg_cells = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
@@ -550,7 +574,24 @@ class MotionNet(nn.Module):
         ws = scratch(size("pcab_bg_compact_workspace", L.L(ncell)), dev)
         call("pcab_bg_compact", P(cell2pillar), P(fb_est), I(nF), I(Ny), I(Nx), P(bg_cells), P(frame_off), P(ws),
              Z(ws.numel()), stream())
-        off = frame_off.cpu().tolist()  # the one D2H sync of the ego head
+        if getattr(self, "_pin_off", None) is None or self._pin_off.numel() != nF + 1:
+            self._pin_off = torch.empty(nF + 1, dtype=torch.int32).pin_memory()
+        host = self._pin_off
+        host.copy_(frame_off, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return bg_cells, frame_off, host, ev
+
+    def _ego_motion(self, W, geo, cell2pillar, prep, pillar_mean, pillar_frame, M, ego_gt, B, T, Ny, Nx, results):
+        """models/egomotion.py:387-469.  The host only draws the keypoint permutations (H3 protocol:
+        ``torch.randperm`` on the CPU generator, in the reference's order) from ONE readback of the
+        per-frame background-pillar counts; everything else is batched over all pairs on the device."""
+        dev = geo.device
+        cfg = self.cfg
+        nF = B * T
+        bg_cells, frame_off, host_off, ev = prep
+        ev.synchronize()  # the one host wait of the ego head
+        off = host_off.tolist()
         counts = [off[f + 1] - off[f] for f in range(nF)]
         mode = cfg["pose_estimation"]["seq_pose"]
         freq = cfg["data"]["freq"]
@@ -599,9 +640,8 @@ class MotionNet(nn.Module):
              I(cfg["pose_estimation"]["sinkhorn_iter"]), P(ego_gt), P(chain_pair_d), I(B), I(T),
              I(1 if mode == "chain" else 0), P(perm), P(pose_pairs), P(est), P(gt), P(scalars), P(ws), Z(ws.numel()),
              stream())
-        sc = scalars.cpu()
         results["ego_l1_loss"], results["ego_l2_loss"] = scalars[0], scalars[1]
-        results["ego_rot_error"], results["ego_trans_error"] = float(sc[2]), float(sc[3])
+        self._deferred.append((("ego_rot_error", "ego_trans_error"), scalars[2:4]))  # floats are read at the end of forward
         keep = [p for p, (b, anchor, ref, d) in enumerate(pairs) if mode == "chain" or anchor == 0]
         results["perm_matrix"] = [perm[p] for p in keep]
         results["ego_motion_est"], results["ego_motion_gt"] = est, gt
@@ -655,9 +695,12 @@ class MotionNet(nn.Module):
         # alignnet.py:201-206: instance ids become global over the batch (scenes without points do not advance the offset)
         tb = time_indice[:, 0].long()
         ks = torch.tensor([u.size(0) for u in upd], device=dev)
-        has = torch.bincount(tb, minlength=len(upd))[:len(upd)] > 0
+        nb = int(ego_est.shape[0])
+        has = torch.bincount(tb, minlength=nb)[:len(upd)] > 0
         ks_eff = ks * has
-        inst_labels = inst_labels + (torch.cumsum(ks_eff, 0) - ks_eff)[tb]
+        offs = torch.zeros(max(nb, len(upd)), dtype=torch.long, device=dev)
+        offs[:len(upd)] = torch.cumsum(ks_eff, 0) - ks_eff  # scenes beyond len(upd) keep offset 0, as upstream's loop does
+        inst_labels = inst_labels + offs[tb]
         motion = torch.cat(upd)
         K = motion.size(0)
         t_idx = time_indice[:, 1].long()
@@ -696,22 +739,37 @@ class MotionNet(nn.Module):
         results["tpointnet_loss_terms"] = {}
         final = None
         ws = scratch(size("pcab_tpn_iteration_workspace", I(K), I(T)), dev)
+        motion0 = motion
+        poses = []
+
+        def gt_motion_at(it):
+            """GT instance motion seen by iteration `it` (alignnet.py:250-254 applied for the earlier iterations)."""
+            m = motion0.reshape(-1, 4, 4).clone()
+            for c in poses[:it]:
+                c = c.reshape(-1, 4, 4)
+                m[:, :3, :3] = torch.matmul(m[:, :3, :3], c[:, :3, :3].transpose(1, 2))
+                m[:, :3, 3] = m[:, :3, 3] - torch.matmul(m[:, :3, :3], c[:, :3, 3].unsqueeze(-1)).squeeze(-1)
+            return m.view(K, T, 4, 4)
+
         for it in range(self.cfg["tpointnet"]["n_iterations"]):
             pose = torch.empty(K, T, 4, 4, device=dev)
             pose_c = torch.empty(K * T, 4, 4, device=dev)
             rep = torch.empty(K * T, 7, device=dev)
             call("pcab_tpn_iteration", P(p_pts), P(p_inst32), P(p_time32), I(n_pad), I(K), I(T), P(mos_emb), P(geo_emb),
                  P(W["tpn_pos"]), P(W["tpn_reg"]), P(pose), P(pose_c), P(rep), P(ws), Z(ws.numel()), stream())
-            results["tpointnet_loss_terms"][f"{it}_th"] = self._tpn_losses(p_pts, p_inst, p_time, p_seg32, p_mos, motion,
-                                                                          pose, pose_c, rep, K, T)
+            poses.append(pose)
+
+            def compute(it=it, pts=p_pts, pose=pose, pose_c=pose_c, rep=rep):
+                return self._tpn_losses(pts, p_inst, p_time, p_seg32, p_mos, gt_motion_at(it), pose, pose_c, rep, K, T)
+
+            terms = _LazyLossTerms(pose, compute)
+            if self.mode != "test":
+                terms.materialize()  # the training / validation losses consume them
+            results["tpointnet_loss_terms"][f"{it}_th"] = terms
             new_pts = torch.empty_like(p_pts)
             call("pcab_apply_seg_pose", P(p_pts), P(p_seg32), P(pose), I(n_pad), P(new_pts), stream())
             p_pts = new_pts
-            motion = motion.reshape(-1, 4, 4).clone()
             c = pose.reshape(-1, 4, 4)
-            motion[:, :3, :3] = torch.matmul(motion[:, :3, :3], c[:, :3, :3].transpose(1, 2))
-            motion[:, :3, 3] = motion[:, :3, 3] - torch.matmul(motion[:, :3, :3], c[:, :3, 3].unsqueeze(-1)).squeeze(-1)
-            motion = motion.view(K, T, 4, 4)
             final = c if final is None else torch.matmul(c, final)
         final = final.view(K, T, 4, 4).contiguous()
         seg32 = (inst_labels * T + t_idx).to(torch.int32).contiguous()
@@ -722,8 +780,8 @@ class MotionNet(nn.Module):
         l2 = torch.norm(rec_est - rec_gt, p=2, dim=1)
         w = t_idx > 0
         wm = (mos_labels == 1) & w
-        errs = torch.stack(((l2 * w).sum() / (w.sum() + 1e-20), (l2 * wm).sum() / (wm.sum() + 1e-20))).cpu()
-        results["inst_l2_error"], results["dynamic_inst_l2_error"] = float(errs[0]), float(errs[1])
+        errs = torch.stack(((l2 * w).sum() / (w.sum() + 1e-20), (l2 * wm).sum() / (wm.sum() + 1e-20)))
+        self._deferred.append((("inst_l2_error", "dynamic_inst_l2_error"), errs))
         results["inst_labels_adjusted"] = inst_labels
         results["inst_pose_est"] = final
         results["sub_rec_est"] = rec_est
@@ -736,8 +794,9 @@ class MotionNet(nn.Module):
         frame_count = torch.zeros(K * T, device=dev).scatter_add_(0, seg, ones)
         fw = (frame_count > self.cfg["tpointnet"]["min_points"]).float()
         inst_mos = torch.zeros(K * T, dtype=mos_labels.dtype, device=dev).scatter_reduce_(0, seg, mos_labels, "amax", include_self=False)
-        mw = torch.ones_like(inst_mos, dtype=torch.float32)
-        mw[inst_mos == 0] = 0.2
+        # quirk: upstream builds the weights with ones_like(<int64 labels>) and assigns 0.2 into that INTEGER tensor
+        # (models/tpointnet.py:232-233), which truncates to 0 -- frames without a dynamic point get weight 0, not 0.2
+        mw = (inst_mos != 0).float()
         tw = ((torch.arange(self.n_sweeps, device=dev) + 1).repeat(K) / self.n_sweeps).float()
         fw = fw * mw * tw
         sums = torch.zeros(K * T, 3, device=dev, dtype=torch.float64).index_add_(0, seg, pts.double())
@@ -764,6 +823,40 @@ class MotionNet(nn.Module):
             "trans_loss": (torch.norm(gt[:, :3, 3] - rep[:, 4:], p=2, dim=1) * fw).sum() / wsum,
             "inst_est_motion": pose,
         }
+
+
+class _LazyLossTerms(dict):
+    """Per-iteration TubeNet outputs (models/tpointnet.py:297-303).  ``inst_est_motion`` is always present; the four
+    loss scalars (``l1_loss, l2_loss, rot_loss, trans_loss``) are only consumed by the training loss, so in test mode
+    they are computed on first access instead of on the hot path."""
+
+    _LOSS_KEYS = ("l1_loss", "l2_loss", "rot_loss", "trans_loss")
+
+    def __init__(self, pose, compute):
+        super().__init__(inst_est_motion=pose)
+        self._compute = compute
+
+    def materialize(self):
+        if self._compute is not None:
+            fn, self._compute = self._compute, None
+            self.update(fn())
+        return self
+
+    def __missing__(self, key):
+        if key in self._LOSS_KEYS and self._compute is not None:
+            return self.materialize()[key]
+        raise KeyError(key)
+
+    def keys(self):
+        self.materialize()
+        return dict.keys(self)
+
+    def items(self):
+        self.materialize()
+        return dict.items(self)
+
+    def __contains__(self, key):
+        return key in self._LOSS_KEYS or dict.__contains__(self, key)
 
 
 def _mat2quat_scipy(R):
