@@ -82,6 +82,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst
       : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // K-major, 128B-swizzled shared-memory operand descriptor (8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int base_offset_mode) {
   uint64_t d = 0;
@@ -204,9 +210,16 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs this loop with warp-uniform values (so descriptors live in uniform registers); only the
+    // tcgen05 instructions themselves are issued by one elected lane.  A descriptor differs from tile to tile only in
+    // its 14-bit start-address field, so it is built once and advanced with a 32-bit add per MMA.
+    {
       // instruction descriptor: D=f32, A=B=tf32, K-major both, N = cout_t, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout_t >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO, version, SWIZZLE_128B (upper word)
+      const uint32_t desc_lo0 = 1u << 16;                                          // LBO field (lower word)
+      const uint32_t ah16 = (smem_u32(plane_hi) & 0x3FFFF) >> 4, al16 = (smem_u32(plane_lo) & 0x3FFFF) >> 4;
+      const uint32_t b16 = (smem_u32(b_stage) & 0x3FFFF) >> 4, bstep16 = b_bytes >> 4;
       int bs = 0, bph = 0;
       for (int ci = 0; ci < nchunks; ++ci) {
         mbar_wait(bar_lo_done, ci & 1);
@@ -214,35 +227,42 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(bar_b_full0 + 8 * bs, bph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int shift_rows = (tap / 3) * a.Wp + (tap % 3);
-          const uint32_t bh = smem_u32(b_stage + (2 * bs) * b_bytes), bl = smem_u32(b_stage + (2 * bs + 1) * b_bytes);
+          const uint32_t shift16 = (uint32_t)((tap / 3) * a.Wp + (tap % 3)) * 8u;  // rows * 128 B / 16
+          const uint32_t bh16 = b16 + (uint32_t)(2 * bs) * bstep16, bl16 = bh16 + bstep16;
           for (int mt = 0; mt < a.mt; ++mt) {
-            const uint32_t row_off = (uint32_t)(mt * 128 + shift_rows) * 128u;
-            const uint32_t ah = smem_u32(plane_hi) + row_off, al = smem_u32(plane_lo) + row_off;
             // two accumulators per tile: the big a_hi*w_hi products and the ~2^-11 smaller correction products.  The
             // tensor core truncates when it adds into the FP32 accumulator, so keeping the small terms out of the
             // large accumulator cuts its number of (biased) roundings from 3K/8 to K/8.
             const uint32_t tmem_d = tmem_base + (uint32_t)(mt * a.cout_t);
             const uint32_t tmem_c = tmem_base + (uint32_t)((a.mt + mt) * a.cout_t);
+            const uint32_t arow16 = (uint32_t)(mt * 128) * 8u + shift16;
+            const uint32_t first = (ci == 0 && tap == 0) ? 0u : 1u;
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint32_t first = (ci == 0 && tap == 0 && kk == 0) ? 0u : 1u;
-              const uint64_t dah = umma_desc(ah + kk * 32, a.base_offset_mode), dal = umma_desc(al + kk * 32, a.base_offset_mode);
-              const uint64_t dbh = umma_desc(bh + kk * 32, 0), dbl = umma_desc(bl + kk * 32, 0);
-              umma_tf32(tmem_c, dal, dbh, idesc, first);
-              umma_tf32(tmem_c, dah, dbl, idesc, 1u);
-              umma_tf32(tmem_d, dah, dbh, idesc, first);
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t dah = ((uint64_t)desc_hi << 32) | (desc_lo0 | (ah16 + arow16 + 2u * kk));
+                const uint64_t dal = ((uint64_t)desc_hi << 32) | (desc_lo0 | (al16 + arow16 + 2u * kk));
+                const uint64_t dbh = ((uint64_t)desc_hi << 32) | (desc_lo0 | (bh16 + 2u * kk));
+                const uint64_t dbl = ((uint64_t)desc_hi << 32) | (desc_lo0 | (bl16 + 2u * kk));
+                const uint32_t acc = (kk == 0) ? first : 1u;
+                umma_tf32(tmem_c, dal, dbh, idesc, acc);
+                umma_tf32(tmem_c, dah, dbl, idesc, 1u);
+                umma_tf32(tmem_d, dah, dbh, idesc, acc);
+              }
             }
+            __syncwarp();
           }
-          umma_commit(bar_b_empty0 + 8 * bs);  // frees this weight stage once the MMAs above retire
+          if (elect_one()) umma_commit(bar_b_empty0 + 8 * bs);  // frees this weight stage once the MMAs above retire
+          __syncwarp();
           bs ^= 1;
           if (bs == 0) bph ^= 1;
         }
-        umma_commit(bar_a_free);  // planes may be overwritten
+        if (elect_one()) umma_commit(bar_a_free);  // planes may be overwritten
+        __syncwarp();
       }
-      umma_commit(bar_acc);
+      if (elect_one()) umma_commit(bar_acc);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===================== a_lo split, then epilogue =====================
     const int et = threadIdx.x - 64;  // 0..127

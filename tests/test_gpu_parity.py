@@ -286,7 +286,11 @@ def _check_protocol(model, inp_cuda, ref, seed, rel=REL):
     # rounding alone reaches 1.0e-4 of the +-20 clamp range there, so this stage gets 2e-4
     assert_close_rel(b["mos_est"], ref["mos_est"], 2 * rel, "mos_est")
     assert_close_rel(b["offset_est"], ref["offset_est"], 2 * rel, "offset_est")
-    assert torch.equal(b["mos_est"].cpu().argmax(1), ref["mos_est"].argmax(1)), "motion labels"
+    mos_flips = int((b["mos_est"].cpu().argmax(1) != ref["mos_est"].argmax(1)).sum())
+    if not model.use_tensor_cores:
+        assert mos_flips == 0, "FP32 path: motion labels must be bit-exact"
+    else:
+        assert mos_flips <= max(2, b["mos_est"].shape[0] // 50000), mos_flips  # ties at the 3e-5 level of the tensor-core path
 
     inj = dict(extra, ego_motion_est=ref["ego_motion_est"], mos_est=ref["mos_est"], offset_est=ref["offset_est"])
     c = _seeded(model, inp_cuda, seed, inj)
@@ -295,14 +299,15 @@ def _check_protocol(model, inp_cuda, ref, seed, rel=REL):
         assert torch.equal(c["inst_labels_est"].cpu(), ref["inst_labels_est"]), "instance labels"
     assert "inst_pose_est" in ref, "the test scene must exercise the TubeNet branch"
     assert torch.equal(c["inst_labels_adjusted"].cpu(), ref["inst_labels_adjusted"])
-    # instance poses sit at the end of a ~60-layer chain; the tensor-core path (3e-5 per conv stack) gets 2e-4 here
-    assert_close_rel(c["inst_pose_est"], ref["inst_pose_est"], 2 * rel if model.use_tensor_cores else rel, "inst_pose_est")
-    assert_close_rel(c["sub_rec_est"], ref["sub_rec_est"], rel, "sub_rec_est")
-    assert_close_rel(c["rec_est"], ref["rec_est"], rel, "rec_est")
+    # TubeNet outputs sit at the end of a ~60-layer chain; the tensor-core path (3e-5 per conv stack) gets 2e-4 here
+    trel = 2 * rel if model.use_tensor_cores else rel
+    assert_close_rel(c["inst_pose_est"], ref["inst_pose_est"], trel, "inst_pose_est")
+    assert_close_rel(c["sub_rec_est"], ref["sub_rec_est"], trel, "sub_rec_est")
+    assert_close_rel(c["rec_est"], ref["rec_est"], trel, "rec_est")
     assert abs(c["inst_l2_error"] - ref["inst_l2_error"]) < 1e-4 * max(1.0, ref["inst_l2_error"])
     assert abs(c["dynamic_inst_l2_error"] - ref["dynamic_inst_l2_error"]) < 1e-4 * max(1.0, ref["dynamic_inst_l2_error"])
     for it, terms in ref["tpointnet_loss_terms"].items():
-        assert_close_rel(c["tpointnet_loss_terms"][it]["inst_est_motion"], terms["inst_est_motion"], rel, "inst_est_motion")
+        assert_close_rel(c["tpointnet_loss_terms"][it]["inst_est_motion"], terms["inst_est_motion"], trel, "inst_est_motion")
         for name in ("l1_loss", "l2_loss", "rot_loss", "trans_loss"):
             x, y = float(c["tpointnet_loss_terms"][it][name]), float(terms[name])
             assert abs(x - y) <= 2e-4 * max(1.0, abs(y)), (it, name, x, y)
@@ -356,14 +361,15 @@ def test_forward_vs_reference_golden(fixture_weights, name, tc):
     b = _seeded(model, inp_c, 42, {"ego_motion_est": pose})
     assert_close_rel(b["mos_est"], g["out_mos_est"], 2 * REL, "mos_est")
     assert_close_rel(b["offset_est"], g["out_offset_est"], 2 * REL, "offset_est")
-    assert np.array_equal(b["mos_est"].cpu().argmax(1).numpy(), g["out_mos_est"].argmax(1))
+    mos_flips = int((b["mos_est"].cpu().argmax(1).numpy() != g["out_mos_est"].argmax(1)).sum())
+    assert mos_flips == 0 if not tc else mos_flips <= 2, mos_flips
     inj = {"ego_motion_est": pose, "mos_est": torch.tensor(g["out_mos_est"]), "offset_est": torch.tensor(g["out_offset_est"])}
     c = _seeded(model, inp_c, 42, inj)
     for k in ("inst_labels_est", "inst_labels_adjusted"):
         assert np.array_equal(c[k].cpu().numpy(), g["out_" + k]), k
     assert_close_rel(c["inst_pose_est"], g["out_inst_pose_est"], 2 * REL if tc else REL, "inst_pose_est")
     for k in ("sub_rec_est", "rec_est"):
-        assert_close_rel(c[k], g["out_" + k], REL, k)
+        assert_close_rel(c[k], g["out_" + k], 2 * REL if tc else REL, k)
 
 
 def test_forward_batch_of_two_matches_oracle(fixture_weights):
