@@ -93,6 +93,21 @@ def test_forward_bit_identical_to_reference_when_present(fixture_weights):
         assert torch.equal(ref[k], out[k]), k
     for a, b in zip(ref["perm_matrix"], out["perm_matrix"]):
         assert torch.equal(a, b)
+    # batch of two scenes (per-scene loops, pillar offsets, the single-element motion list of test mode)
+    samples = []
+    for i in (11, 12):
+        sc = synth.make_workload_scene("C1", i, pts_per_frame=6000)
+        p4 = np.concatenate((sc["input_points"], sc["time_indice"]), 1).astype(np.float32)
+        sc.update(ns["Voxelization"](cfg["voxel_generator"])(p4))
+        samples.append(sc)
+    inp, inp2 = ns["collate_fn"](samples), synth.collate(samples)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        ref = model(inp)
+    torch.manual_seed(3)
+    out = oracle.OracleMotionNet(cfg, sd).forward(inp2)
+    for k in ("fb_est_per_points", "ego_motion_est", "mos_est", "rec_est", "inst_labels_est"):
+        assert torch.equal(ref[k], out[k]), k
 
 
 def test_segment_reductions_match_torch_scatter_semantics():
