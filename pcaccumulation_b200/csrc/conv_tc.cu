@@ -11,7 +11,7 @@
 // 128 bytes per pixel = one swizzle row.  Output pixels are indexed in the FLATTENED padded grid m = r*(Wt+2)+x,
 // so the A operand of tap (ky,kx) is the same plane viewed from row  m + ky*(Wt+2) + kx : nine shifted views of
 // one staged plane instead of nine loads (the two extra columns per row compute garbage that is never stored).
-// 3xTF32:  a = a_hi + a_lo, w = w_hi + w_lo with *_hi = the value rounded to the nearest tf32 (19 bits);
+// 3xTF32:  a = a_hi + a_lo, w = w_hi + w_lo; a_hi = the 19 bits the tensor core reads of a, w_hi = w rounded to tf32;
 //          acc += a_lo*w_hi + a_hi*w_lo + a_hi*w_hi   (a_lo*w_lo ~ 2^-22 is dropped).
 // w_hi / w_lo are pre-split on the host; a_lo is produced in shared memory by the epilogue warps right after the
 // plane lands.  Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = a_lo split and
@@ -122,10 +122,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// wait for the outstanding tcgen05.ld's; the "+r" operands tie the loaded registers to the wait so that no use of
+// them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32], uint32_t (&w)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]) : : "memory");
+  asm volatile("" : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]), "+r"(w[16]), "+r"(w[17]), "+r"(w[18]), "+r"(w[19]), "+r"(w[20]), "+r"(w[21]), "+r"(w[22]), "+r"(w[23]), "+r"(w[24]), "+r"(w[25]), "+r"(w[26]), "+r"(w[27]), "+r"(w[28]), "+r"(w[29]), "+r"(w[30]), "+r"(w[31]) : : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
              const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -269,16 +274,22 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
     const int n_f4 = (a.R + 2) * a.Wp * 8;  // float4 per plane (the rows the TMA box wrote)
     for (int ci = 0; ci < nchunks; ++ci) {
       mbar_wait(bar_a_full, ci & 1);
-      float4* hi = reinterpret_cast<float4*>(plane_hi);
+      const float4* hi = reinterpret_cast<const float4*>(plane_hi);
       float4* lo = reinterpret_cast<float4*>(plane_lo);
-      // hi := a rounded to NEAREST tf32 (so the split error is zero-mean; truncation would bias every term the same
-      // way and the error would grow ~K instead of ~sqrt(K)); lo := a - hi (exact in FP32)
-      auto rnd = [](float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); };
-      for (int i = et; i < n_f4; i += 128) {
+      // a_hi is what the tensor core reads of the raw FP32 value (it ignores the low 13 mantissa bits), so the hi plane
+      // needs no rewrite; a_lo = a - trunc_tf32(a) is exact in FP32.  Four independent 128-bit loads in flight per thread.
+      auto low = [](float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); };
+      int i = et;
+      for (; i + 384 < n_f4; i += 512) {
+        float4 v0 = hi[i], v1 = hi[i + 128], v2 = hi[i + 256], v3 = hi[i + 384];
+        lo[i] = make_float4(low(v0.x), low(v0.y), low(v0.z), low(v0.w));
+        lo[i + 128] = make_float4(low(v1.x), low(v1.y), low(v1.z), low(v1.w));
+        lo[i + 256] = make_float4(low(v2.x), low(v2.y), low(v2.z), low(v2.w));
+        lo[i + 384] = make_float4(low(v3.x), low(v3.y), low(v3.z), low(v3.w));
+      }
+      for (; i < n_f4; i += 128) {
         float4 v = hi[i];
-        float4 h = make_float4(rnd(v.x), rnd(v.y), rnd(v.z), rnd(v.w));
-        hi[i] = h;
-        lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        lo[i] = make_float4(low(v.x), low(v.y), low(v.z), low(v.w));
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
       mbar_arrive(bar_lo_done);
@@ -296,6 +307,7 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
         uint32_t v[32], vc[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * a.cout_t + c32 * 32), v);
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((a.mt + mt) * a.cout_t + c32 * 32), vc);
+        tmem_ld_wait(v, vc);
         if (valid) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -342,18 +354,31 @@ struct TileCfg {
   size_t smem;
 };
 
+int g_tile_mode = 1;  // 0: 4 M-tiles, 1 CTA/SM; 1: 2 M-tiles sized for 2 co-resident CTAs/SM (phases of one hide the other's)
+
 bool choose_cfg(int H, int W, int Cout, TileCfg* c) {
   if (Cout % 32) return false;
   c->cout_t = Cout <= 64 ? Cout : 64;  // 2 accumulators x 4 M-tiles x 64 columns = the 512 TMEM columns
   if (Cout % c->cout_t) return false;
-  c->mt = 4;
-  // widest column tile with Wt + 2 <= 98 that divides W when possible
-  int Wt = W <= 96 ? W : 96;
-  for (int cand = 96; cand >= 48; --cand)
-    if (W % cand == 0) {
-      Wt = cand;
-      break;
-    }
+  int Wt;
+  if (g_tile_mode == 0) {
+    c->mt = 4;
+    // widest column tile with Wt + 2 <= 98 that divides W when possible
+    Wt = W <= 96 ? W : 96;
+    for (int cand = 96; cand >= 48; --cand)
+      if (W % cand == 0) {
+        Wt = cand;
+        break;
+      }
+  } else {
+    c->mt = 2;
+    Wt = W <= 24 ? W : 24;
+    for (int cand = 24; cand >= 12; --cand)
+      if (W % cand == 0) {
+        Wt = cand;
+        break;
+      }
+  }
   c->Wt = Wt;
   c->Wp = Wt + 2;
   c->R = (c->mt * 128) / c->Wp;
@@ -364,7 +389,8 @@ bool choose_cfg(int H, int W, int Cout, TileCfg* c) {
   if (box > rows) rows = box;
   c->plane_rows = (rows + 7) & ~7;
   c->smem = (size_t)2 * c->plane_rows * 128 + (size_t)4 * c->cout_t * 128 + 128 + 1024;
-  return c->smem <= (size_t)kMaxSmem && c->Wp <= 256 && c->R + 2 <= 256;
+  size_t cap = g_tile_mode == 0 ? (size_t)kMaxSmem : (size_t)113 * 1024;
+  return c->smem <= cap && c->Wp <= 256 && c->R + 2 <= 256;
 }
 
 int g_base_offset_mode = 0;
@@ -372,7 +398,8 @@ int g_base_offset_mode = 0;
 }  // namespace
 
 extern "C" int pcab_conv3x3_tc_set_base_offset_mode(int mode) {
-  g_base_offset_mode = mode;
+  g_base_offset_mode = mode & 1;
+  g_tile_mode = ((mode >> 1) & 1) ^ 1;  // bit 1 set selects the large 1-CTA/SM tile shape (tuning knob)
   return 0;
 }
 
