@@ -12,7 +12,7 @@
 // so the A operand of tap (ky,kx) is the same plane viewed from row  m + ky*(Wt+2) + kx : nine shifted views of
 // one staged plane instead of nine loads (the two extra columns per row compute garbage that is never stored).
 // 3xTF32:  a = a_hi + a_lo, w = w_hi + w_lo; a_hi = the 19 bits the tensor core reads of a, w_hi = w rounded to tf32;
-//          acc += a_lo*w_hi + a_hi*w_lo + a_hi*w_hi   (a_lo*w_lo ~ 2^-22 is dropped).
+//          acc += a_hi*[w_hi|w_lo] (one N=2*Cout MMA) + a_lo*w_hi   (a_lo*w_lo ~ 2^-22 is dropped).
 // w_hi / w_lo are pre-split on the host; a_lo is produced in shared memory by the epilogue warps right after the
 // plane lands.  Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = a_lo split and
 // epilogue (tcgen05.ld -> bias/BN/ReLU -> NHWC global stores).
@@ -38,6 +38,7 @@ struct TcArgs {
   int relu;
   int out_cstride, out_coff;
   int base_offset_mode;
+  int nst;  // weight pipeline stages (2..4)
   const float* bias;
   const float* bn_scale;
   const float* bn_shift;
@@ -141,10 +142,10 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
   uint8_t* plane_hi = base;
   uint8_t* plane_lo = base + plane_bytes;
   uint8_t* b_stage = base + 2 * plane_bytes;  // stage s: hi at s*2*b_bytes, lo at +b_bytes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stage + 4 * b_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stage + 2 * a.nst * b_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const uint32_t bar_a_full = smem_u32(bars + 0), bar_lo_done = smem_u32(bars + 1), bar_a_free = smem_u32(bars + 2);
-  const uint32_t bar_b_full0 = smem_u32(bars + 3), bar_b_empty0 = smem_u32(bars + 5), bar_acc = smem_u32(bars + 7);
+  const uint32_t bar_acc = smem_u32(bars + 3), bar_b_full0 = smem_u32(bars + 4), bar_b_empty0 = smem_u32(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
@@ -167,8 +168,7 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
     mbar_init(bar_a_full, 1);
     mbar_init(bar_lo_done, 128);
     mbar_init(bar_a_free, 1);
-    mbar_init(bar_b_full0, 1), mbar_init(bar_b_full0 + 8, 1);
-    mbar_init(bar_b_empty0, 1), mbar_init(bar_b_empty0 + 8, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(bar_b_full0 + 8 * i, 1), mbar_init(bar_b_empty0 + 8 * i, 1);
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -204,8 +204,7 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
               const int k0 = kbase_src + tap * Cs + c0;
               tma_load_2d(&map_b, smem_u32(b_stage + (2 * bs) * b_bytes), bar_b_full0 + 8 * bs, k0, co0);
               tma_load_2d(&map_b, smem_u32(b_stage + (2 * bs + 1) * b_bytes), bar_b_full0 + 8 * bs, k0, a.Cout + co0);
-              bs ^= 1;
-              if (bs == 0) bph ^= 1;
+              if (++bs == a.nst) bs = 0, bph ^= 1;
             }
           }
         }
@@ -219,8 +218,11 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
     // tcgen05 instructions themselves are issued by one elected lane.  A descriptor differs from tile to tile only in
     // its 14-bit start-address field, so it is built once and advanced with a 32-bit add per MMA.
     {
-      // instruction descriptor: D=f32, A=B=tf32, K-major both, N = cout_t, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout_t >> 3) << 17) | ((128u >> 4) << 24);
+      // instruction descriptors: D=f32, A=B=tf32, K-major both, M = 128; N = 2*cout_t for the fused main MMA
+      // (weights staged as [w_hi rows | w_lo rows] = one 2*cout_t-row operand), N = cout_t for the a_lo correction
+      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
+      const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * a.cout_t) >> 3) << 17);
+      const uint32_t idesc1 = idesc_base | ((uint32_t)(a.cout_t >> 3) << 17);
       const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO, version, SWIZZLE_128B (upper word)
       const uint32_t desc_lo0 = 1u << 16;                                          // LBO field (lower word)
       const uint32_t ah16 = (smem_u32(plane_hi) & 0x3FFFF) >> 4, al16 = (smem_u32(plane_lo) & 0x3FFFF) >> 4;
@@ -233,13 +235,15 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
           mbar_wait(bar_b_full0 + 8 * bs, bph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t shift16 = (uint32_t)((tap / 3) * a.Wp + (tap % 3)) * 8u;  // rows * 128 B / 16
-          const uint32_t bh16 = b16 + (uint32_t)(2 * bs) * bstep16, bl16 = bh16 + bstep16;
+          const uint32_t bh16 = b16 + (uint32_t)(2 * bs) * bstep16;
           for (int mt = 0; mt < a.mt; ++mt) {
-            // two accumulators per tile: the big a_hi*w_hi products and the ~2^-11 smaller correction products.  The
-            // tensor core truncates when it adds into the FP32 accumulator, so keeping the small terms out of the
-            // large accumulator cuts its number of (biased) roundings from 3K/8 to K/8.
-            const uint32_t tmem_d = tmem_base + (uint32_t)(mt * a.cout_t);
-            const uint32_t tmem_c = tmem_base + (uint32_t)((a.mt + mt) * a.cout_t);
+            // TMEM columns of tile mt: [0, c) = sum a_hi*w_hi (main), [c, 2c) = sum of the ~2^-11 smaller corrections
+            // a_hi*w_lo + a_lo*w_hi.  One N=2c MMA  a_hi x [w_hi | w_lo]  fills both halves reading a_hi ONCE (the kernel is
+            // bound by shared-memory operand bandwidth), one N=c MMA  a_lo x w_hi  adds into the correction half.  The
+            // tensor core truncates when it adds into an accumulator, so keeping the small terms out of the main half also
+            // cuts its number of (biased) roundings from 3K/8 to K/8.
+            const uint32_t tmem_d = tmem_base + (uint32_t)(mt * 2 * a.cout_t);
+            const uint32_t tmem_c = tmem_d + (uint32_t)a.cout_t;
             const uint32_t arow16 = (uint32_t)(mt * 128) * 8u + shift16;
             const uint32_t first = (ci == 0 && tap == 0) ? 0u : 1u;
             if (elect_one()) {
@@ -248,19 +252,15 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
                 const uint64_t dah = ((uint64_t)desc_hi << 32) | (desc_lo0 | (ah16 + arow16 + 2u * kk));
                 const uint64_t dal = ((uint64_t)desc_hi << 32) | (desc_lo0 | (al16 + arow16 + 2u * kk));
                 const uint64_t dbh = ((uint64_t)desc_hi << 32) | (desc_lo0 | (bh16 + 2u * kk));
-                const uint64_t dbl = ((uint64_t)desc_hi << 32) | (desc_lo0 | (bl16 + 2u * kk));
-                const uint32_t acc = (kk == 0) ? first : 1u;
-                umma_tf32(tmem_c, dal, dbh, idesc, acc);
-                umma_tf32(tmem_c, dah, dbl, idesc, 1u);
-                umma_tf32(tmem_d, dah, dbh, idesc, acc);
+                umma_tf32(tmem_d, dah, dbh, idesc2, (kk == 0) ? first : 1u);
+                umma_tf32(tmem_c, dal, dbh, idesc1, 1u);
               }
             }
             __syncwarp();
           }
           if (elect_one()) umma_commit(bar_b_empty0 + 8 * bs);  // frees this weight stage once the MMAs above retire
           __syncwarp();
-          bs ^= 1;
-          if (bs == 0) bph ^= 1;
+          if (++bs == a.nst) bs = 0, bph ^= 1;
         }
         if (elect_one()) umma_commit(bar_a_free);  // planes may be overwritten
         __syncwarp();
@@ -305,8 +305,8 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
       float* orow = a.out + (((size_t)n * a.H + gy) * a.W + gx) * a.out_cstride + a.out_coff + co0;
       for (int c32 = 0; c32 < a.cout_t / 32; ++c32) {
         uint32_t v[32], vc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * a.cout_t + c32 * 32), v);
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((a.mt + mt) * a.cout_t + c32 * 32), vc);
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * 2 * a.cout_t + c32 * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * 2 * a.cout_t + a.cout_t + c32 * 32), vc);
         tmem_ld_wait(v, vc);
         if (valid) {
 #pragma unroll
@@ -350,10 +350,11 @@ EncodeTiledFn get_encode() {
 }
 
 struct TileCfg {
-  int cout_t, mt, Wt, Wp, R, plane_rows;
+  int cout_t, mt, Wt, Wp, R, plane_rows, nst;
   size_t smem;
 };
 
+int g_max_stages = 4;
 int g_tile_mode = 1;  // 0: 4 M-tiles, 1 CTA/SM; 1: 2 M-tiles sized for 2 co-resident CTAs/SM (phases of one hide the other's)
 
 bool choose_cfg(int H, int W, int Cout, TileCfg* c) {
@@ -388,18 +389,24 @@ bool choose_cfg(int H, int W, int Cout, TileCfg* c) {
   int box = (c->R + 2) * c->Wp;
   if (box > rows) rows = box;
   c->plane_rows = (rows + 7) & ~7;
-  c->smem = (size_t)2 * c->plane_rows * 128 + (size_t)4 * c->cout_t * 128 + 128 + 1024;
   size_t cap = g_tile_mode == 0 ? (size_t)kMaxSmem : (size_t)113 * 1024;
-  return c->smem <= cap && c->Wp <= 256 && c->R + 2 <= 256;
+  for (c->nst = g_max_stages; c->nst >= 2; --c->nst) {  // deepest weight pipeline that fits
+    c->smem = (size_t)2 * c->plane_rows * 128 + (size_t)2 * c->nst * c->cout_t * 128 + 128 + 1024;
+    if (c->smem <= cap) break;
+  }
+  return c->nst >= 2 && c->smem <= cap && c->Wp <= 256 && c->R + 2 <= 256;
 }
 
 int g_base_offset_mode = 0;
+int g_min_hw = 16;
 
 }  // namespace
 
 extern "C" int pcab_conv3x3_tc_set_base_offset_mode(int mode) {
   g_base_offset_mode = mode & 1;
   g_tile_mode = ((mode >> 1) & 1) ^ 1;  // bit 1 set selects the large 1-CTA/SM tile shape (tuning knob)
+  g_min_hw = (mode & 4) ? 32 : 16;        // bit 2 set: leave maps below 32x32 to the FP32 path
+  g_max_stages = (mode & 8) ? 2 : 4;      // bit 3 set: 2-stage weight pipeline
   return 0;
 }
 
@@ -408,7 +415,7 @@ extern "C" int pcab_conv3x3_tc_supported(int n_sources, int c0, int c1, int c2, 
   int cs[3] = {c0, c1, c2};
   for (int s = 0; s < n_sources; ++s)
     if (cs[s] <= 0 || cs[s] % 32) return 0;
-  if (H < 32 || W < 32) return 0;  // the smallest maps keep the FP32 CUDA-core path (too few tiles for 148 SMs)
+  if (H < g_min_hw || W < g_min_hw) return 0;  // the smallest maps keep the FP32 CUDA-core path (too few tiles for 148 SMs)
   TileCfg c;
   return choose_cfg(H, W, Cout, &c) ? 1 : 0;
 }
@@ -473,6 +480,7 @@ extern "C" int pcab_conv3x3_tc(const float* src0, int c0, const float* src1, int
   a.cout_t = cfg.cout_t, a.mt = cfg.mt, a.R = cfg.R, a.Wt = cfg.Wt, a.Wp = cfg.Wp, a.plane_rows = cfg.plane_rows;
   a.tiles_x = cdiv(W, cfg.Wt), a.tiles_y = cdiv(H, cfg.R);
   a.relu = relu, a.out_cstride = out_cstride, a.out_coff = out_coff, a.base_offset_mode = g_base_offset_mode;
+  a.nst = cfg.nst;
   a.bias = bias, a.bn_scale = bn_scale, a.bn_shift = bn_shift, a.out = out;
   static bool configured = false;
   if (!configured) {

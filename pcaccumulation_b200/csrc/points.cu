@@ -199,14 +199,32 @@ __global__ void __launch_bounds__(256) k_tpn_static_embed(const float* __restric
   embed_and_max<32, 32, 64>(A, Bf, s_w, pk_geo, s_seg, geo_emb);
 }
 
-// per (instance, frame) sums of the points (double) and counts
+// per (instance, frame) sums of the points (double) and counts.  Rows arrive sorted by segment, so each warp reduces
+// its 32 consecutive rows with a segmented shuffle scan and issues one atomic per run instead of one per row.
 __global__ void k_tpn_frame_sums(const float* __restrict__ pts, const int* __restrict__ inst,
                                  const int* __restrict__ tidx, int T, int n, double* __restrict__ sums /* [KT][4] */) {
   int stride = gridDim.x * blockDim.x;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-    double* s = sums + ((size_t)inst[j] * T + tidx[j]) * 4;
-    atomicAdd(s, (double)pts[3 * j]), atomicAdd(s + 1, (double)pts[3 * j + 1]), atomicAdd(s + 2, (double)pts[3 * j + 2]);
-    atomicAdd(s + 3, 1.0);
+  int lane = threadIdx.x & 31;
+  for (int j0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; j0 < n; j0 += stride) {
+    int j = j0 + lane;
+    bool ok = j < n;
+    int seg = ok ? inst[j] * T + tidx[j] : -1;
+    double x = ok ? (double)pts[3 * j] : 0.0, y = ok ? (double)pts[3 * j + 1] : 0.0, z = ok ? (double)pts[3 * j + 2] : 0.0;
+    double c = ok ? 1.0 : 0.0;
+    // inclusive segmented suffix sums: lane i accumulates lanes i.. of its run; the run head then holds the run total
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int s2 = __shfl_down_sync(0xffffffffu, seg, o);
+      double x2 = __shfl_down_sync(0xffffffffu, x, o), y2 = __shfl_down_sync(0xffffffffu, y, o);
+      double z2 = __shfl_down_sync(0xffffffffu, z, o), c2 = __shfl_down_sync(0xffffffffu, c, o);
+      if (lane + o < 32 && s2 == seg) x += x2, y += y2, z += z2, c += c2;
+    }
+    int prev = __shfl_up_sync(0xffffffffu, seg, 1);
+    bool head = ok && (lane == 0 || prev != seg);
+    if (head) {
+      double* s = sums + (size_t)seg * 4;
+      atomicAdd(s, x), atomicAdd(s + 1, y), atomicAdd(s + 2, z), atomicAdd(s + 3, c);
+    }
   }
 }
 

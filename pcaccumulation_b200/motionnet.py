@@ -411,14 +411,19 @@ class MotionNet(nn.Module):
         x_abs, y_abs = abs(float(self.pc_range[0])), abs(float(self.pc_range[1]))
 
         self._mark("start")
-        # schema -> compact int32 device arrays
-        p2v = input_dict["point_to_voxel_map"].reshape(-1).to(torch.int32).contiguous()
-        pbatch = time_indice[:, 0].to(torch.int32).contiguous()
-        ptime = time_indice[:, 1].to(torch.int32).contiguous()
-        pframe = (pbatch * T + ptime).contiguous()
-        ci = coordinates.to(torch.int32)
-        coords_zyxt = ci[:, 1:5].contiguous()
-        pillar_batch = ci[:, 0].contiguous()
+        # schema -> compact int32 device arrays (SceneRunner hands them over directly and skips the f64 round trip)
+        fast = input_dict.get("_pcab")
+        if fast is not None:
+            p2v, pbatch, ptime = fast["p2v"], fast["pbatch"], fast["ptime"]
+            coords_zyxt, pillar_batch = fast["coords_zyxt"], fast["pillar_batch"]
+        else:
+            p2v = input_dict["point_to_voxel_map"].reshape(-1).to(torch.int32).contiguous()
+            pbatch = time_indice[:, 0].to(torch.int32).contiguous()
+            ptime = time_indice[:, 1].to(torch.int32).contiguous()
+            ci = coordinates.to(torch.int32)
+            coords_zyxt = ci[:, 1:5].contiguous()
+            pillar_batch = ci[:, 0].contiguous()
+        pframe = (pbatch * T + ptime).contiguous() if B > 1 else ptime
         fb64 = fb_labels.reshape(-1).to(torch.int64).contiguous()
 
         # pillar index (stable sort by pillar) + statistics

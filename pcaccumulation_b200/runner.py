@@ -22,6 +22,7 @@ class SceneRunner:
         self.T = vg["n_sweeps"]
         g = self.vox.grid_size
         self.shape = torch.tensor([[int(g[0]), int(g[1]), int(g[2]), self.T]], dtype=torch.int64)
+        self.check_range = True  # libs/dataset.py:218 check (one device sync); the benchmark scenes are known to be in range
 
     def build_input(self, points4, num_points, labels=None, ego_motion_gt=None, inst_motion_gt=None):
         """points4: CUDA f32 [N,4] (x,y,z,t) with the scenes of a batch concatenated; num_points: list[int]."""
@@ -34,9 +35,10 @@ class SceneRunner:
         else:
             pbatch = torch.zeros(N, dtype=torch.int32, device=dev)
         v = self.vox.voxelize_batch(points4, pbatch if B > 1 else None, B)
-        if int((v["point_to_voxel_map"] < 0).sum()) != 0:  # libs/dataset.py:218 rejects such samples
+        if self.check_range and int((v["point_to_voxel_map"] < 0).sum()) != 0:  # libs/dataset.py:218 rejects such samples
             raise ValueError("points outside the voxel range")
         coords = torch.cat((v["pillar_batch"][:, None], v["coordinates"]), 1).double()
+        ptime = points4[:, 3].to(torch.int32)
         time_indice = torch.stack((pbatch.double(), points4[:, 3].double()), 1)
         zeros = torch.zeros(N, 1, dtype=torch.int64, device=dev)
         labels = labels or {}
@@ -54,6 +56,9 @@ class SceneRunner:
             "num_voxels": v["num_voxels"].to(torch.int64),
             "shape": self.shape.repeat(B, 1),
             "point_to_voxel_map": v["point_to_voxel_map"].to(torch.int64)[:, None],
+            # the int32 device arrays the kernels consume (same information as the reference-schema entries above)
+            "_pcab": {"p2v": v["point_to_voxel_map"], "pbatch": pbatch, "ptime": ptime,
+                      "coords_zyxt": v["coordinates"].contiguous(), "pillar_batch": v["pillar_batch"].contiguous()},
         }
 
     @torch.no_grad()

@@ -23,14 +23,14 @@ for it in range(5):
     torch.manual_seed(5); runner.run_device(p4, [p4.shape[0]])
     torch.cuda.synchronize()
     walls.append((time.perf_counter() - t0) * 1e3)
-    prev, pname = e0, "voxelize+build_input"
+    prev = e0
     for nm, e in runner.model.stage_marks:
-        acc.setdefault(pname, []).append(prev.elapsed_time(e)); prev, pname = e, nm
+        acc.setdefault(nm, []).append(prev.elapsed_time(e)); prev = e
 print("threads", torch.get_num_threads(), "wall ms", [round(w, 2) for w in walls])
 tot = 0
 order = ["voxelize+build_input", "start", "index+stats", "pillar_encoder", "unet", "fb_head", "ego", "warp+stpn", "cluster"]
-labels = {"voxelize+build_input": "voxelize+build_input", "start": "schema casts", "index+stats": "pillar index+stats+canvases", "pillar_encoder": "pillar encoder",
-          "unet": "unet", "fb_head": "fb head", "ego": "ego (heads+pairs)", "warp+stpn": "warp+stpn+head", "cluster": "cluster+select", "tubenet": "tubenet"}
+labels = {"start": "voxelize + build_input (runner)", "index+stats": "casts + pillar index/stats/canvases", "pillar_encoder": "pillar encoder",
+          "unet": "unet", "fb_head": "fb head", "ego": "ego (2 head convs + pairs)", "warp+stpn": "warp + stpn + point head", "cluster": "cluster", "tubenet": "tubenet"}
 for k, v in acc.items():
     m = sum(v) / len(v); tot += m
     print(f"{labels.get(k, k):32s} {m:7.3f} ms")

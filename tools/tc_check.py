@@ -15,7 +15,8 @@ dev = "cuda"
 # (n_img, [src channels], Cout, H, W, temporal_T)
 shapes = [(5, [32], 32, 288, 288, 1), (5, [32], 64, 288, 288, 1), (5, [64], 64, 144, 144, 1), (5, [32, 32], 32, 288, 288, 1),
           (5, [64, 64], 64, 144, 144, 1), (5, [128], 128, 72, 72, 1), (5, [128, 128], 128, 72, 72, 1), (5, [64], 128, 72, 72, 1),
-          (5, [32], 32, 288, 288, 5), (1, [64], 64, 288, 288, 1), (2, [32], 32, 100, 76, 1), (1, [256], 256, 72, 72, 1)]
+          (5, [32], 32, 288, 288, 5), (1, [64], 64, 288, 288, 1), (2, [32], 32, 100, 76, 1), (1, [256], 256, 72, 72, 1),
+          (5, [256], 512, 18, 18, 1), (5, [512], 512, 18, 18, 1), (1, [128], 256, 18, 18, 1), (1, [256], 256, 18, 18, 1), (5, [256, 256], 256, 36, 36, 1)]
 for n, cs, cout, H, W, T in shapes:
     cin = sum(cs)
     xs = [torch.randn(n, H, W, c, device=dev) for c in cs]
