@@ -541,3 +541,61 @@ def test_full_size_forward_properties(fixture_weights):
     assert res["rec_est"].shape == (N, 3) and torch.isfinite(res["rec_est"]).all()
     for p in res["perm_matrix"]:
         assert float(p.sum(1).max()) <= 1.0 + 1e-4  # last Sinkhorn step normalises columns (incl. slack row)
+
+
+@pytest.mark.parametrize("seq_pose", ["chain", "full"])
+def test_sequence_strategies_chain_and_full(fixture_weights, seq_pose):
+    """models/egomotion.py:195-306: the non-default sequence strategies (pair lists, chaining, RNG order)."""
+    from oracle import oracle
+    from pcaccumulation_b200 import config, synth
+
+    cfg = config.workload_config("C1")
+    cfg["pose_estimation"]["seq_pose"] = seq_pose
+    sd = fixture_weights(cfg)
+    s = synth.make_workload_scene("C1", 8, pts_per_frame=10000)
+    p4 = np.concatenate((s["input_points"], s["time_indice"]), 1).astype(np.float32)
+    vg = cfg["voxel_generator"]
+    s.update(oracle.voxelize(p4, vg["voxel_size"], vg["range"], vg["n_sweeps"]))
+    inp = synth.collate([s])
+    torch.manual_seed(11)
+    ref = oracle.OracleMotionNet(cfg, sd).forward(inp)
+    model = make_model(cfg, sd, False)
+    a = _seeded(model, cuda_dict(inp), 11)
+    assert torch.equal(a["fb_est_per_points"].cpu(), ref["fb_est_per_points"])
+    assert_close_rel(a["ego_motion_est"], ref["ego_motion_est"], REL, "ego_motion_est")
+    assert_close_rel(a["ego_motion_gt"], ref["ego_motion_gt"], REL, "ego_motion_gt")
+    assert len(a["perm_matrix"]) == len(ref["perm_matrix"]) == 4
+    for x, y in zip(a["perm_matrix"], ref["perm_matrix"]):
+        assert_close_rel(x, y, REL, "perm_matrix")
+    assert abs(float(a["ego_l1_loss"]) - float(ref["ego_l1_loss"])) < 1e-4 * max(1.0, float(ref["ego_l1_loss"]))
+
+
+@pytest.mark.parametrize("name", ["C3", "C5"])
+def test_other_baseline_configs_run_at_full_size(fixture_weights, name):
+    """BASELINE.json configs[2] (nuScenes-shaped 10 x 35k, z-range [-5,3]) and configs[4] (5 x 400k points, 512 x 512 grid)."""
+    from pcaccumulation_b200 import config, synth
+    from pcaccumulation_b200.runner import SceneRunner, scene_to_points4
+
+    cfg = config.workload_config(name)
+    runner = SceneRunner(cfg)
+    runner.model.load_state_dict(fixture_weights(cfg))
+    s = synth.make_workload_scene(name, 0)
+    p4 = torch.tensor(scene_to_points4(s)).cuda()
+    torch.manual_seed(0)
+    res = runner.run_device(p4, [p4.shape[0]])
+    T = cfg["voxel_generator"]["n_sweeps"]
+    g = 512 if name == "C5" else 288
+    assert res["fb_seg_est"].shape == (1, T, 2, g, g) and res["ego_motion_est"].shape == (1, T, 4, 4)
+    assert torch.isfinite(res["rec_est"]).all() and res["rec_est"].shape == (p4.shape[0], 3)
+    R = res["ego_motion_est"][0, :, :3, :3]
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3, device="cuda").expand_as(R), atol=1e-5)
+    inst = res["inst_labels_est"]
+    labels = inst.unique().tolist()
+    assert labels == list(range(len(labels))) and len(labels) > 1
+    # the FP32 and tensor-core conv paths agree on this size too
+    runner.model.use_tensor_cores = False
+    torch.manual_seed(0)
+    res2 = runner.run_device(p4, [p4.shape[0]])
+    assert_close_rel(res2["fb_seg_est"], res["fb_seg_est"].cpu(), 2e-4, "fb_seg_est tc vs fp32")
+    flips = int((res2["fb_est_per_points"] != res["fb_est_per_points"]).sum())
+    assert flips <= 40, flips
