@@ -36,17 +36,32 @@ __device__ __forceinline__ void block_dense(const float* X, const float* __restr
     for (int k = 0; k < kc; ++k) {
       float4 x = *reinterpret_cast<const float4*>(X + (k0 + k) * LDP + tr * 4);
       const float* wrow = s_w + k * OUT + tc * OPT;
+      if constexpr (OPT % 4 == 0) {
 #pragma unroll
-      for (int o2 = 0; o2 < OPT / 2; ++o2) {
-        float2 w = *reinterpret_cast<const float2*>(wrow + 2 * o2);
-        acc[2 * o2][0] = fmaf(x.x, w.x, acc[2 * o2][0]);
-        acc[2 * o2][1] = fmaf(x.y, w.x, acc[2 * o2][1]);
-        acc[2 * o2][2] = fmaf(x.z, w.x, acc[2 * o2][2]);
-        acc[2 * o2][3] = fmaf(x.w, w.x, acc[2 * o2][3]);
-        acc[2 * o2 + 1][0] = fmaf(x.x, w.y, acc[2 * o2 + 1][0]);
-        acc[2 * o2 + 1][1] = fmaf(x.y, w.y, acc[2 * o2 + 1][1]);
-        acc[2 * o2 + 1][2] = fmaf(x.z, w.y, acc[2 * o2 + 1][2]);
-        acc[2 * o2 + 1][3] = fmaf(x.w, w.y, acc[2 * o2 + 1][3]);
+        for (int o4 = 0; o4 < OPT / 4; ++o4) {
+          float4 w = *reinterpret_cast<const float4*>(wrow + 4 * o4);
+          const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[4 * o4 + u][0] = fmaf(x.x, wv[u], acc[4 * o4 + u][0]);
+            acc[4 * o4 + u][1] = fmaf(x.y, wv[u], acc[4 * o4 + u][1]);
+            acc[4 * o4 + u][2] = fmaf(x.z, wv[u], acc[4 * o4 + u][2]);
+            acc[4 * o4 + u][3] = fmaf(x.w, wv[u], acc[4 * o4 + u][3]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int o2 = 0; o2 < OPT / 2; ++o2) {
+          float2 w = *reinterpret_cast<const float2*>(wrow + 2 * o2);
+          acc[2 * o2][0] = fmaf(x.x, w.x, acc[2 * o2][0]);
+          acc[2 * o2][1] = fmaf(x.y, w.x, acc[2 * o2][1]);
+          acc[2 * o2][2] = fmaf(x.z, w.x, acc[2 * o2][2]);
+          acc[2 * o2][3] = fmaf(x.w, w.x, acc[2 * o2][3]);
+          acc[2 * o2 + 1][0] = fmaf(x.x, w.y, acc[2 * o2 + 1][0]);
+          acc[2 * o2 + 1][1] = fmaf(x.y, w.y, acc[2 * o2 + 1][1]);
+          acc[2 * o2 + 1][2] = fmaf(x.z, w.y, acc[2 * o2 + 1][2]);
+          acc[2 * o2 + 1][3] = fmaf(x.w, w.y, acc[2 * o2 + 1][3]);
+        }
       }
     }
   }

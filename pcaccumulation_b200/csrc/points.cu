@@ -67,10 +67,10 @@ __global__ void __launch_bounds__(256) k_stpn_head(const float* __restrict__ mos
                                                    float x_abs, float y_abs, float* __restrict__ mos_out,
                                                    float* __restrict__ off_out) {
   extern __shared__ __align__(16) float sm[];
-  float* E = sm;                  // [128][PTS]
-  float* F = E + 128 * LDP;       // [128][PTS]
-  float* G = F + 128 * LDP;       // [128][PTS]
-  float* s_w = G + 128 * LDP;     // [KC*128]
+  float* E = sm;                  // [128][LDP]
+  float* F = E + 128 * LDP;       // [128][LDP]
+  float* G = E;                   // the hidden layer of the motion head reuses E (dead after final_proj)
+  float* s_w = F + 128 * LDP;     // [KC*128]
   float* s_o = s_w + mlp::KC * 128;  // [4][LDP]
   __shared__ int s_idx[PTS];
   const int base = blockIdx.x * PTS;
@@ -425,7 +425,7 @@ extern "C" int pcab_stpn_head(const float* mos_feats_nhwc, int H, int W, const f
                               const int* point_batch, const int* fg_idx, int n_fg, const float* weight_pack,
                               float x_abs, float y_abs, float* mos_out, float* offset_out, cudaStream_t stream) {
   if (n_fg <= 0) return PCAB_OK;
-  size_t smem = (size_t)(3 * 128 * LDP + mlp::KC * 128 + 4 * LDP) * sizeof(float);
+  size_t smem = (size_t)(2 * 128 * LDP + mlp::KC * 128 + 4 * LDP) * sizeof(float);
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(k_stpn_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

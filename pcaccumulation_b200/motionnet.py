@@ -397,14 +397,15 @@ class MotionNet(nn.Module):
         dev = pts.device
         if dev.type != "cuda":
             raise L.PcabError("pcaccumulation_b200.MotionNet runs on CUDA (sm_100a) only; move input_dict to the GPU")
-        time_indice = input_dict["time_indice"]
+        time_indice = input_dict.get("time_indice")  # absent on the SceneRunner fast path (int32 arrays in "_pcab")
         fb_labels = input_dict["fb_labels"]
         ego_gt = input_dict["ego_motion_gt"].float().contiguous()
-        coordinates = input_dict["coordinates"]
+        coordinates = input_dict.get("coordinates")
         num_voxels = input_dict["num_voxels"]
         shape = input_dict["shape"][0]
         Nx, Ny, nt = int(shape[0]), int(shape[1]), int(shape[3])
-        N, M, B, T = pts.shape[0], coordinates.shape[0], num_voxels.shape[0], nt
+        M = input_dict["_pcab"]["coords_zyxt"].shape[0] if coordinates is None else coordinates.shape[0]
+        N, B, T = pts.shape[0], num_voxels.shape[0], nt
         HW = Ny * Nx
         rng = host_floats(self.pc_range)
         vsz = host_floats(self.resolution)
@@ -552,7 +553,8 @@ class MotionNet(nn.Module):
                 st.update(backbone_feats=bb, motion_feats=mf)
             ridx = rec_idx.long()
             self._alignnet(W, {
-                "inst_labels": inst_labels[ridx], "time_indice": time_indice[ridx], "transformed_points": tp[ridx],
+                "inst_labels": inst_labels[ridx], "batch_idx": pbatch[ridx].long(), "time_idx": ptime[ridx].long(),
+                "transformed_points": tp[ridx],
                 "backbone_feats": bb, "motion_feats": mf, "inst_motion_gt": input_dict["inst_motion_gt"],
                 "mos_labels": input_dict["sd_labels"][ridx, 0].long(), "ego_motion_est": results["ego_motion_est"],
                 "ego_motion_gt": results["ego_motion_gt"]}, results, T)
@@ -682,7 +684,6 @@ class MotionNet(nn.Module):
         dev = inp["transformed_points"].device
         mos_labels = inp["mos_labels"]
         inst_labels = inp["inst_labels"].clone()
-        time_indice = inp["time_indice"]
         tp = inp["transformed_points"].contiguous()
         n_points = inst_labels.size(0)
         ego_est, ego_gt = inp["ego_motion_est"], inp["ego_motion_gt"]
@@ -698,7 +699,7 @@ class MotionNet(nn.Module):
             e = ego_est[b][None].repeat(K, 1, 1, 1).view(-1, 4, 4)
             upd.append((m.reshape(-1, 4, 4) @ g @ torch.linalg.inv(e)).view(K, -1, 4, 4))
         # alignnet.py:201-206: instance ids become global over the batch (scenes without points do not advance the offset)
-        tb = time_indice[:, 0].long()
+        tb = inp["batch_idx"]
         ks = torch.tensor([u.size(0) for u in upd], device=dev)
         nb = int(ego_est.shape[0])
         has = torch.bincount(tb, minlength=nb)[:len(upd)] > 0
@@ -708,7 +709,7 @@ class MotionNet(nn.Module):
         inst_labels = inst_labels + offs[tb]
         motion = torch.cat(upd)
         K = motion.size(0)
-        t_idx = time_indice[:, 1].long()
+        t_idx = inp["time_idx"]
         frame_indice = inst_labels * T + t_idx
         frame_count = torch.zeros(K * T, device=dev).scatter_add_(0, frame_indice, torch.ones(n_points, device=dev))
         fc = frame_count.view(K, T)

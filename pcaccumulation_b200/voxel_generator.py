@@ -39,9 +39,9 @@ class Voxelization:
         call("pcab_voxelize", P(points4), P(point_batch), I(n), I(batch_size), host_floats(self.point_cloud_range),
              host_floats(self.voxel_size), I(self.n_sweeps), P(coords), P(pillar_batch), P(p2v), P(num_voxels), P(total),
              P(ws), Z(ws.numel()), stream())
-        m = int(total.item())
+        m, n_rejected = torch.stack((total[0], (p2v < 0).sum().to(torch.int32))).tolist()  # one readback for both
         return {"coordinates": coords[:m], "pillar_batch": pillar_batch[:m], "point_to_voxel_map": p2v,
-                "num_voxels": num_voxels, "total_voxels": m}
+                "num_voxels": num_voxels, "total_voxels": m, "n_rejected": n_rejected}
 
     def __call__(self, points):
         is_np = isinstance(points, np.ndarray)
