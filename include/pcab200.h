@@ -128,6 +128,14 @@ int pcab_cluster_scene(const float* transformed_points, const float* offset, con
                        int* n_instances_out, void* workspace, size_t workspace_bytes, pcab_stream_t stream);
 
 /* ---- TubeNet: models/tpointnet.py:211-305, toolbox/register_utils.py:72-93 -------------------------------- */
+/* models/alignnet.py:115-163,201-225: relabel non-empty instances, pad instances without anchor-frame rows, order rows */
+int pcab_tpn_relabel(const long long* inst, const long long* tidx, int n, int K0, int T, int* frame_count /* [K0*T] */,
+                     int* mapping /* [K0] */, int* pad_frame /* [K0] */, int* totals /* {K, P} */, pcab_stream_t stream);
+size_t pcab_tpn_rows_workspace(int n_rows);
+int pcab_tpn_rows(const long long* inst, const long long* tidx, int n, int n_pad_rows, int T, const int* mapping,
+                  const int* pad_frame, const float* pts_rec, int* seg_rows /* [n] */, long long* inst_new /* [n] */,
+                  int* row_src, int* row_inst, int* row_time, int* row_seg, float* row_pts /* [n+P,...] */,
+                  void* workspace, size_t workspace_bytes, pcab_stream_t stream);
 int pcab_tpn_static_embed(const float* mos_feat /* [n_src,64] */, const float* geo_feat /* [n_src,32] */,
                           const int* src_idx /* [n] row of each (padded) point */, const int* inst, int n, int K,
                           const float* pack_motion, const float* pack_geo, float* mos_emb /* [K,128] */,

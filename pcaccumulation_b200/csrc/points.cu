@@ -367,6 +367,89 @@ __global__ void k_scatter_rows3(const float* __restrict__ src, const int* __rest
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// TubeNet bookkeeping (models/alignnet.py:115-163 `padding`, :201-225): drop empty instances and relabel, find the
+// instances without anchor-frame (t = 0) points and duplicate the rows of their first non-empty frame as t = 0, order
+// all rows by (instance, frame).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_tpn_hist(const long long* __restrict__ inst, const long long* __restrict__ tidx, int n, int T,
+                           int* __restrict__ frame_count) {
+  int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+    atomicAdd(frame_count + (int)inst[j] * T + (int)tidx[j], 1);
+}
+
+// single block: mapping (old id -> new id or -1), first non-empty frame, pad source frame (or -1), totals {K, P}
+__global__ void __launch_bounds__(1024) k_tpn_relabel(const int* __restrict__ frame_count, int K0, int T,
+                                                      int* __restrict__ mapping, int* __restrict__ pad_frame,
+                                                      int* __restrict__ totals) {
+  __shared__ int s_scan[1024];
+  __shared__ int s_base, s_pad;
+  if (threadIdx.x == 0) s_base = 0, s_pad = 0;
+  __syncthreads();
+  for (int k0 = 0; k0 < K0; k0 += 1024) {
+    int k = k0 + threadIdx.x;
+    int cnt = 0, first = -1;
+    if (k < K0)
+      for (int t = 0; t < T; ++t) {
+        int c = frame_count[k * T + t];
+        cnt += c;
+        if (first < 0 && c > 0) first = t;
+      }
+    int keep = cnt > 0;
+    s_scan[threadIdx.x] = keep;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // inclusive Hillis-Steele scan
+      int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_scan[threadIdx.x] += v;
+      __syncthreads();
+    }
+    if (k < K0) {
+      mapping[k] = keep ? s_base + s_scan[threadIdx.x] - 1 : -1;
+      bool need = keep && first > 0;  // no anchor-frame points
+      pad_frame[k] = need ? first : -1;
+      if (need) atomicAdd(&s_pad, frame_count[k * T + first]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += s_scan[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[0] = s_base, totals[1] = s_pad;
+}
+
+__global__ void k_tpn_keys(const long long* __restrict__ inst, const long long* __restrict__ tidx, int n, int T,
+                           const int* __restrict__ mapping, const int* __restrict__ pad_frame, int* __restrict__ keys,
+                           int* __restrict__ vals, int* __restrict__ seg_rows, long long* __restrict__ inst_new,
+                           int* __restrict__ pad_cursor) {
+  int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    int k = (int)inst[j], t = (int)tidx[j];
+    int m = mapping[k];
+    keys[j] = m * T + t;
+    vals[j] = j;
+    seg_rows[j] = m * T + t;
+    inst_new[j] = m;
+    if (pad_frame[k] == t) {  // duplicate as an anchor-frame row
+      int q = n + atomicAdd(pad_cursor, 1);
+      keys[q] = m * T;
+      vals[q] = j;
+    }
+  }
+}
+
+__global__ void k_tpn_rows(const int* __restrict__ keys_sorted, const int* __restrict__ vals_sorted, int n_pad, int T,
+                           const float* __restrict__ pts_rec, int* __restrict__ row_src, int* __restrict__ row_inst,
+                           int* __restrict__ row_time, int* __restrict__ row_seg, float* __restrict__ row_pts) {
+  int stride = gridDim.x * blockDim.x;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pad; q += stride) {
+    int key = keys_sorted[q], src = vals_sorted[q];
+    row_src[q] = src, row_inst[q] = key / T, row_time[q] = key % T, row_seg[q] = key;
+    row_pts[3 * q] = pts_rec[3 * src], row_pts[3 * q + 1] = pts_rec[3 * src + 1], row_pts[3 * q + 2] = pts_rec[3 * src + 2];
+  }
+}
+
 __global__ void k_fill(float* a, long long n, float v) {
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) a[i] = v;
@@ -434,6 +517,53 @@ extern "C" int pcab_stpn_head(const float* mos_feats_nhwc, int H, int W, const f
   k_stpn_head<<<cdiv(n_fg, PTS), 256, smem, stream>>>(mos_feats_nhwc, H, W, transformed_points, point_batch, fg_idx,
                                                       n_fg, weight_pack, x_abs, y_abs, mos_out, offset_out);
   PCAB_CHECK_LAUNCH("pcab_stpn_head");
+  return PCAB_OK;
+}
+
+
+// step 1: histogram + relabel.  frame_count [K0*T] (zero-filled here), mapping [K0], pad_frame [K0], totals {K, P} (device)
+extern "C" int pcab_tpn_relabel(const long long* inst, const long long* tidx, int n, int K0, int T, int* frame_count,
+                                int* mapping, int* pad_frame, int* totals, cudaStream_t stream) {
+  PCAB_CUDA(cudaMemsetAsync(frame_count, 0, (size_t)K0 * T * 4, stream));
+  k_tpn_hist<<<grid_for(n, 256), 256, 0, stream>>>(inst, tidx, n, T, frame_count);
+  k_tpn_relabel<<<1, 1024, 0, stream>>>(frame_count, K0, T, mapping, pad_frame, totals);
+  PCAB_CHECK_LAUNCH("pcab_tpn_relabel");
+  return PCAB_OK;
+}
+
+extern "C" size_t pcab_tpn_rows_workspace(int n_rows) {
+  size_t sort_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, n_rows);
+  return al256p(sort_bytes) + 4 * al256p((size_t)n_rows * 4) + 512;
+}
+
+// step 2 (after the host read K and P): the n + P rows ordered by (instance, frame) with their source row, instance,
+// frame, segment id and point; also the relabelled instance / segment id of the n original rows
+extern "C" int pcab_tpn_rows(const long long* inst, const long long* tidx, int n, int n_pad_rows, int T, const int* mapping,
+                             const int* pad_frame, const float* pts_rec, int* seg_rows, long long* inst_new, int* row_src,
+                             int* row_inst, int* row_time, int* row_seg, float* row_pts, void* workspace,
+                             size_t workspace_bytes, cudaStream_t stream) {
+  int total = n + n_pad_rows;
+  PCAB_REQUIRE(workspace_bytes >= pcab_tpn_rows_workspace(total), "workspace too small");
+  char* w = (char*)workspace;
+  int* keys = (int*)w;
+  w += al256p((size_t)total * 4);
+  int* vals = (int*)w;
+  w += al256p((size_t)total * 4);
+  int* keys_s = (int*)w;
+  w += al256p((size_t)total * 4);
+  int* vals_s = (int*)w;
+  w += al256p((size_t)total * 4);
+  int* cursor = (int*)w;
+  w += 256;
+  size_t sort_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys, keys_s, vals, vals_s, total);
+  PCAB_CUDA(cudaMemsetAsync(cursor, 0, 4, stream));
+  k_tpn_keys<<<grid_for(n, 256), 256, 0, stream>>>(inst, tidx, n, T, mapping, pad_frame, keys, vals, seg_rows, inst_new, cursor);
+  PCAB_CUDA(cub::DeviceRadixSort::SortPairs(w, sort_bytes, keys, keys_s, vals, vals_s, total, 0, 32, stream));
+  k_tpn_rows<<<grid_for(total, 256), 256, 0, stream>>>(keys_s, vals_s, total, T, pts_rec, row_src, row_inst, row_time, row_seg,
+                                                       row_pts);
+  PCAB_CHECK_LAUNCH("pcab_tpn_rows");
   return PCAB_OK;
 }
 

@@ -534,11 +534,12 @@ class MotionNet(nn.Module):
             inst_labels = input_dict["inst_labels"][:, 0].long().contiguous()
             rec_idx, n_rec = self._select(N, dev, values=fb64, value=1)
         else:
-            inst_labels = self._cluster(tp, full_mos, full_off, input_dict["num_points"], B, N, dev)
+            inst_labels, n_inst_max = self._cluster(tp, full_mos, full_off, input_dict["num_points"], B, N, dev)
             results["inst_labels_est"] = inst_labels
             self._mark("cluster")
             if "inst_labels_est" in self.inject:
                 inst_labels = self.inject["inst_labels_est"].to(dev).long().contiguous()
+                n_inst_max = int(inst_labels.max())
             rec_idx, n_rec = self._select(N, dev, flags=(inst_labels != 0).to(torch.int32))
         if n_rec > MIN_POINTS:
             if mos_feats is None:  # quirk Q4 (motionnet.py:222-245): upstream dies with NameError here
@@ -554,6 +555,7 @@ class MotionNet(nn.Module):
             ridx = rec_idx.long()
             self._alignnet(W, {
                 "inst_labels": inst_labels[ridx], "batch_idx": pbatch[ridx].long(), "time_idx": ptime[ridx].long(),
+                "n_inst_max": n_inst_max if self.mode == "test" else 0,
                 "transformed_points": tp[ridx],
                 "backbone_feats": bb, "motion_feats": mf, "inst_motion_gt": input_dict["inst_motion_gt"],
                 "mos_labels": input_dict["sd_labels"][ridx, 0].long(), "ego_motion_est": results["ego_motion_est"],
@@ -661,6 +663,7 @@ class MotionNet(nn.Module):
         cc = self.cfg["cluster"]
         inst = torch.zeros(N, dtype=torch.int64, device=dev)
         npts = [int(v) for v in num_points.reshape(-1).tolist()]
+        ninst_all = torch.zeros(max(B, 1), dtype=torch.int32, device=dev)
         n0 = 0
         for b in range(B):
             n = npts[b]
@@ -671,73 +674,75 @@ class MotionNet(nn.Module):
             sel, s = self._select(n, dev, flags=flags)
             if s > cc["min_p_cluster"]:
                 ws = scratch(size("pcab_cluster_workspace", I(s)), dev)
-                ninst = torch.zeros(1, dtype=torch.int32, device=dev)
                 call("pcab_cluster_scene", P(tp), P(off), P(sel), I(n0), I(s), F(0.05), D(cc["eps_dbscan"]),
-                     I(cc["min_samples_dbscan"]), I(cc["min_p_cluster"]), P(inst), P(ninst), P(ws), Z(ws.numel()), stream())
+                     I(cc["min_samples_dbscan"]), I(cc["min_p_cluster"]), P(inst), P(ninst_all[b:b + 1]), P(ws), Z(ws.numel()),
+                     stream())
             n0 += n
-        return inst
+        return inst, max(ninst_all.tolist())
 
     # ------------------------------------------------------------------------------------------
     def _alignnet(self, W, inp, results, T):
-        """models/alignnet.py:166-285.  Index bookkeeping (a handful of tiny tensors) uses torch ops on the
-        device like the reference; embeddings / regression / reconstruction are pcab kernels."""
+        """models/alignnet.py:166-285.  Relabelling / padding / row ordering run in two pcab calls
+        (``pcab_tpn_relabel``, ``pcab_tpn_rows``) with one small readback between them; embeddings, regression and
+        reconstruction are pcab kernels; only [K,T,4,4]-sized pose algebra stays in torch."""
         dev = inp["transformed_points"].device
         mos_labels = inp["mos_labels"]
-        inst_labels = inp["inst_labels"].clone()
+        inst_labels = inp["inst_labels"]
+        tb, t_idx = inp["batch_idx"], inp["time_idx"]
         tp = inp["transformed_points"].contiguous()
         n_points = inst_labels.size(0)
         ego_est, ego_gt = inp["ego_motion_est"], inp["ego_motion_gt"]
-        if self.mode == "test":
-            n_inst = int(inst_labels.max()) + 1
-            inst_motion_gt = [torch.eye(4, device=dev)[None, None].repeat(n_inst, T, 1, 1)]
+        test = self.mode == "test"
+        if test:
+            # upstream builds ONE identity motion list entry for the whole batch (alignnet.py:190-192), so every instance's
+            # "GT" is the ego-pose error of scene 0 per frame and instance ids are not offset per scene
+            K0 = inp["n_inst_max"] + 1
+            G = (ego_gt[0] @ torch.linalg.inv(ego_est[0])).contiguous()  # [T,4,4]
+            motion_all = None
         else:
             inst_motion_gt = [m.to(dev).float() for m in inp["inst_motion_gt"]]
-        upd = []
-        for b, m in enumerate(inst_motion_gt):  # alignnet.py:9-38
-            K = m.size(0)
-            g = ego_gt[b][None].repeat(K, 1, 1, 1).view(-1, 4, 4)
-            e = ego_est[b][None].repeat(K, 1, 1, 1).view(-1, 4, 4)
-            upd.append((m.reshape(-1, 4, 4) @ g @ torch.linalg.inv(e)).view(K, -1, 4, 4))
-        # alignnet.py:201-206: instance ids become global over the batch (scenes without points do not advance the offset)
-        tb = inp["batch_idx"]
-        ks = torch.tensor([u.size(0) for u in upd], device=dev)
-        nb = int(ego_est.shape[0])
-        has = torch.bincount(tb, minlength=nb)[:len(upd)] > 0
-        ks_eff = ks * has
-        offs = torch.zeros(max(nb, len(upd)), dtype=torch.long, device=dev)
-        offs[:len(upd)] = torch.cumsum(ks_eff, 0) - ks_eff  # scenes beyond len(upd) keep offset 0, as upstream's loop does
-        inst_labels = inst_labels + offs[tb]
-        motion = torch.cat(upd)
-        K = motion.size(0)
-        t_idx = inp["time_idx"]
-        frame_indice = inst_labels * T + t_idx
-        frame_count = torch.zeros(K * T, device=dev).scatter_add_(0, frame_indice, torch.ones(n_points, device=dev))
-        fc = frame_count.view(K, T)
-        inst_count = fc.sum(1)
-        # alignnet.py:137-151: instances without anchor-frame points get the points of their first non-empty frame
-        # duplicated as t = 0 (vectorised; the order of the padded rows is irrelevant to every consumer)
-        need = (fc[:, 0] == 0) & (inst_count > 0)
-        first_frame = (fc > 0).float().argmax(1)
-        pad = torch.nonzero(need[inst_labels] & (t_idx == first_frame[inst_labels]))[:, 0]
-        keep = inst_count > 0
-        motion = motion[keep]
-        mapping = torch.cumsum(keep.long(), 0) - 1
-        inst_labels = mapping[inst_labels]
-        inst_motion_gt = motion.clone()
-        K = motion.size(0)
-        p_time = torch.cat((t_idx, torch.zeros_like(pad)))
-        p_idx = torch.cat((torch.arange(n_points, device=dev), pad))
-        p_inst = inst_labels[p_idx]
-        # sort the (padded) rows by (instance, frame): segment max-pools become run reductions inside a CTA
-        order = torch.sort(p_inst * T + p_time, stable=True)[1]
-        p_idx, p_time, p_inst = p_idx[order], p_time[order], p_inst[order]
-        n_pad = p_idx.numel()
-        p_idx32 = p_idx.to(torch.int32).contiguous()
-        p_inst32 = p_inst.to(torch.int32).contiguous()
-        p_time32 = p_time.to(torch.int32).contiguous()
-        p_seg32 = (p_inst32 * T + p_time32).contiguous()
-        p_mos = mos_labels[p_idx]
-        p_pts = tp[p_idx].contiguous()
+            upd = []
+            for b, m in enumerate(inst_motion_gt):  # alignnet.py:9-38
+                Kb = m.size(0)
+                g = ego_gt[b][None].repeat(Kb, 1, 1, 1).view(-1, 4, 4)
+                e = ego_est[b][None].repeat(Kb, 1, 1, 1).view(-1, 4, 4)
+                upd.append((m.reshape(-1, 4, 4) @ g @ torch.linalg.inv(e)).view(Kb, -1, 4, 4))
+            # alignnet.py:201-206: instance ids become global over the batch (scenes without points do not advance the offset)
+            ks = torch.tensor([u.size(0) for u in upd], device=dev)
+            nb = int(ego_est.shape[0])
+            has = torch.bincount(tb, minlength=nb)[:len(upd)] > 0
+            ks_eff = ks * has
+            offs = torch.zeros(max(nb, len(upd)), dtype=torch.long, device=dev)
+            offs[:len(upd)] = torch.cumsum(ks_eff, 0) - ks_eff
+            inst_labels = inst_labels + offs[tb]
+            motion_all = torch.cat(upd)
+            K0 = motion_all.size(0)
+        inst_labels = inst_labels.contiguous()
+        t_idx = t_idx.contiguous()
+        frame_count = torch.empty(K0 * T, dtype=torch.int32, device=dev)
+        mapping = torch.empty(K0, dtype=torch.int32, device=dev)
+        pad_frame = torch.empty(K0, dtype=torch.int32, device=dev)
+        totals = torch.empty(2, dtype=torch.int32, device=dev)
+        call("pcab_tpn_relabel", P(inst_labels), P(t_idx), I(n_points), I(K0), I(T), P(frame_count), P(mapping), P(pad_frame),
+             P(totals), stream())
+        K, n_extra = totals.tolist()  # the one readback of the TubeNet bookkeeping
+        n_pad = n_points + n_extra
+        seg32 = torch.empty(n_points, dtype=torch.int32, device=dev)
+        inst_new = torch.empty(n_points, dtype=torch.int64, device=dev)
+        p_idx32 = torch.empty(n_pad, dtype=torch.int32, device=dev)
+        p_inst32 = torch.empty(n_pad, dtype=torch.int32, device=dev)
+        p_time32 = torch.empty(n_pad, dtype=torch.int32, device=dev)
+        p_seg32 = torch.empty(n_pad, dtype=torch.int32, device=dev)
+        p_pts = torch.empty(n_pad, 3, device=dev)
+        ws = scratch(size("pcab_tpn_rows_workspace", I(n_pad)), dev)
+        call("pcab_tpn_rows", P(inst_labels), P(t_idx), I(n_points), I(n_extra), I(T), P(mapping), P(pad_frame), P(tp),
+             P(seg32), P(inst_new), P(p_idx32), P(p_inst32), P(p_time32), P(p_seg32), P(p_pts), P(ws), Z(ws.numel()), stream())
+        inst_labels = inst_new
+        if test:
+            motion0_fn = lambda: G[None].expand(K, T, 4, 4).contiguous()
+        else:
+            motion_kept = motion_all[mapping >= 0]
+            motion0_fn = lambda: motion_kept
         mos_emb = torch.empty(K, 128, device=dev)
         geo_emb = torch.empty(K, 128, device=dev)
         call("pcab_tpn_static_embed", P(inp["motion_feats"]), P(inp["backbone_feats"]), P(p_idx32), P(p_inst32), I(n_pad),
@@ -745,12 +750,11 @@ class MotionNet(nn.Module):
         results["tpointnet_loss_terms"] = {}
         final = None
         ws = scratch(size("pcab_tpn_iteration_workspace", I(K), I(T)), dev)
-        motion0 = motion
         poses = []
 
         def gt_motion_at(it):
             """GT instance motion seen by iteration `it` (alignnet.py:250-254 applied for the earlier iterations)."""
-            m = motion0.reshape(-1, 4, 4).clone()
+            m = motion0_fn().reshape(-1, 4, 4).clone()
             for c in poses[:it]:
                 c = c.reshape(-1, 4, 4)
                 m[:, :3, :3] = torch.matmul(m[:, :3, :3], c[:, :3, :3].transpose(1, 2))
@@ -766,10 +770,12 @@ class MotionNet(nn.Module):
             poses.append(pose)
 
             def compute(it=it, pts=p_pts, pose=pose, pose_c=pose_c, rep=rep):
-                return self._tpn_losses(pts, p_inst, p_time, p_seg32, p_mos, gt_motion_at(it), pose, pose_c, rep, K, T)
+                rows = p_idx32.long()
+                return self._tpn_losses(pts, p_inst32.long(), p_time32.long(), p_seg32, mos_labels[rows], gt_motion_at(it),
+                                        pose, pose_c, rep, K, T)
 
             terms = _LazyLossTerms(pose, compute)
-            if self.mode != "test":
+            if not test:
                 terms.materialize()  # the training / validation losses consume them
             results["tpointnet_loss_terms"][f"{it}_th"] = terms
             new_pts = torch.empty_like(p_pts)
@@ -778,11 +784,14 @@ class MotionNet(nn.Module):
             c = pose.reshape(-1, 4, 4)
             final = c if final is None else torch.matmul(c, final)
         final = final.view(K, T, 4, 4).contiguous()
-        seg32 = (inst_labels * T + t_idx).to(torch.int32).contiguous()
         rec_est = torch.empty(n_points, 3, device=dev)
         rec_gt = torch.empty(n_points, 3, device=dev)
         call("pcab_apply_seg_pose", P(tp), P(seg32), P(final), I(n_points), P(rec_est), stream())
-        call("pcab_apply_seg_pose", P(tp), P(seg32), P(inst_motion_gt.contiguous()), I(n_points), P(rec_gt), stream())
+        if test:
+            t32 = t_idx.to(torch.int32)
+            call("pcab_apply_seg_pose", P(tp), P(t32), P(G), I(n_points), P(rec_gt), stream())
+        else:
+            call("pcab_apply_seg_pose", P(tp), P(seg32), P(motion_kept.contiguous()), I(n_points), P(rec_gt), stream())
         l2 = torch.norm(rec_est - rec_gt, p=2, dim=1)
         w = t_idx > 0
         wm = (mos_labels == 1) & w
