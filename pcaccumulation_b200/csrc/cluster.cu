@@ -252,9 +252,11 @@ extern "C" size_t pcab_cluster_workspace(int s) {
   cub::DeviceScan::ExclusiveSum(nullptr, scan, (int*)nullptr, (int*)nullptr, s);
   size_t tmp = sort64 > sort32 ? sort64 : sort32;
   if (scan > tmp) tmp = scan;
-  // q 3s f | c 3s i | key 2x s u64 | val 2x s | head,rank s | pxy 2s f | inverse s | ckey 2x s | cval 2x s |
-  // key_of, core, parent, is_root, root_rank, label, size, keep, keep_rank (9 s) | counts
-  return alc((size_t)s * 12) * 2 + alc((size_t)s * 8) * 2 + alc((size_t)s * 4) * 20 + alc(tmp) + alc(sizeof(Counts)) + 1024;
+  // must mirror the take() sequence of pcab_cluster_scene: q, c (12 B/row) | key, key_s (8) | val, val_s, head, rank (4) |
+  // pxy (8) | spare, inverse, ckey, ckey_s, cval, cval_s, key_of, core, parent, is_root, root_rank, label, size, keep,
+  // keep_rank (15 x 4) | counts | sort/scan temp
+  return 2 * alc((size_t)s * 12) + 2 * alc((size_t)s * 8) + 4 * alc((size_t)s * 4) + alc((size_t)s * 8) +
+         15 * alc((size_t)s * 4) + alc(sizeof(Counts)) + alc(tmp) + 1024;
 }
 
 // flags[i] = argmax(mos[n0+i]) == 1 for i in [0, n)
@@ -308,6 +310,9 @@ extern "C" int pcab_cluster_scene(const float* transformed_points, const float* 
   cub::DeviceRadixSort::SortPairs(nullptr, sort32, ckey, ckey_s, cval, cval_s, s);
   cub::DeviceScan::ExclusiveSum(nullptr, scan, head, rank, s);
   void* tmp = w;
+  size_t tmp_need = sort64 > sort32 ? sort64 : sort32;
+  if (scan > tmp_need) tmp_need = scan;
+  PCAB_REQUIRE((size_t)(w - (char*)workspace) + tmp_need <= workspace_bytes, "workspace carve exceeds the buffer");
 
   const int B = 256;
   int g = grid_for(s, B);
