@@ -351,9 +351,21 @@ def test_forward_vs_reference_golden(fixture_weights, name, tc):
     flips = int((a["fb_est_per_points"].cpu().numpy() != g["out_fb_est_per_points"]).sum())
     if not tc:
         assert flips == 0
-    elif flips:
-        pytest.skip(f"tensor-core path flipped {flips} FG/BG labels on this golden (ties at 3e-5): staged checks run in "
-                    "test_forward_vs_oracle_synthetic with the label map injected")
+    else:
+        assert flips <= 12, flips
+    extra = {}
+    if flips:
+        # tensor-core path: a pillar whose two logits tie at the 3e-5 level flipped; continue the staged checks from the
+        # reference's own label map (rebuilt from its per-point labels: all points of a pillar share the pillar's label)
+        T, grid = cfg["voxel_generator"]["n_sweeps"], int(g["vox_shape"][0])
+        pillar_fb = np.zeros(v["coordinates"].shape[0], dtype=np.int64)
+        pillar_fb[v["point_to_voxel_map"][:, 0]] = g["out_fb_est_per_points"][:, 0]
+        fb_map = torch.zeros(1, T, 1, grid, grid, dtype=torch.int64)
+        co = v["coordinates"]
+        fb_map[0, co[:, 3], 0, co[:, 1], co[:, 2]] = torch.from_numpy(pillar_fb)
+        extra = {"fb_est_map": fb_map}
+        a = _seeded(model, inp_c, 42, extra)
+        assert np.array_equal(a["fb_est_per_points"].cpu().numpy(), g["out_fb_est_per_points"])
     for k in ("ego_motion_est", "ego_motion_gt", "transformed_points"):
         assert_close_rel(a[k], g["out_" + k], REL, k)
     assert_close_rel(model.stages["pillar_feats"][::8], g["stage_pillar_feats_sub8"], 1e-5, "pillar_feats")
@@ -361,12 +373,12 @@ def test_forward_vs_reference_golden(fixture_weights, name, tc):
     rows = torch.stack([p[0].sum(1) for p in a["perm_matrix"]])
     assert_close_rel(rows, g["out_perm_rowsum"], 3 * REL if tc else REL, "perm row sums")
     pose = torch.tensor(g["out_ego_motion_est"])
-    b = _seeded(model, inp_c, 42, {"ego_motion_est": pose})
+    b = _seeded(model, inp_c, 42, dict(extra, ego_motion_est=pose))
     assert_close_rel(b["mos_est"], g["out_mos_est"], 2 * REL, "mos_est")
     assert_close_rel(b["offset_est"], g["out_offset_est"], 2 * REL, "offset_est")
     mos_flips = int((b["mos_est"].cpu().argmax(1).numpy() != g["out_mos_est"].argmax(1)).sum())
     assert mos_flips == 0 if not tc else mos_flips <= 2, mos_flips
-    inj = {"ego_motion_est": pose, "mos_est": torch.tensor(g["out_mos_est"]), "offset_est": torch.tensor(g["out_offset_est"])}
+    inj = dict(extra, ego_motion_est=pose, mos_est=torch.tensor(g["out_mos_est"]), offset_est=torch.tensor(g["out_offset_est"]))
     c = _seeded(model, inp_c, 42, inj)
     for k in ("inst_labels_est", "inst_labels_adjusted"):
         assert np.array_equal(c[k].cpu().numpy(), g["out_" + k]), k
