@@ -75,6 +75,8 @@ int pcab_temporal_max(const float* in, float* out, int B, int T, int H, int W, i
 /* tcgen05 tensor-core path (3xTF32 split, FP32 accumulate in TMEM); same semantics as pcab_conv3x3_f32 */
 int pcab_conv3x3_tc_supported(int n_sources, int c0, int c1, int c2, int Cout, int H, int W);
 int pcab_conv3x3_tc_set_base_offset_mode(int mode); /* debug: UMMA descriptor base-offset policy for shifted views */
+int pcab_conv3x3_tc_plan(int n_images, int H, int W, int Cout, int* out10 /* host: c, mt, strip, mtx, R, Wt, tiles_x, tiles_y, cout tiles, work items */);
+int pcab_conv3x3_tc_set_stats(long long* device_counters); /* debug: 148*16 int64 wait-cycle counters (NULL = off) */
 size_t pcab_conv3x3_tc_pack_floats(int cin_total, int Cout);
 int pcab_conv3x3_tc(const float* src0, int c0, const float* src1, int c1, const float* src2, int c2, int temporal_T,
                     const float* weight_tc_packed, const float* bias, const float* bn_scale, const float* bn_shift,

@@ -333,6 +333,483 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
   }
 }
 
+
+// =====================================================================================================================
+// v2: persistent, fully pipelined kernel (one CTA per SM, 16 warps).
+//   * each CTA walks a static list of (output tile, cout tile) work items;
+//   * hi planes are double buffered (TMA of chunk g+1 overlaps the MMAs of chunk g), so are the a_lo planes written by
+//     the splitter warps, the weight tap stages run through a 3-deep ring fed by their own producer warp;
+//   * the TMEM accumulators are per 32-channel CHUNK and double buffered: after the 36 K-steps of a chunk the drain
+//     warps pull the partial sums into FP32 registers (round-to-nearest adds) while the tensor core already works on the
+//     next chunk.  The tensor core drops the addend bits below the accumulator's ulp on every accumulation, so long
+//     in-TMEM chains (K up to 4608 here) were the dominant error of v1; with chunk-wise draining the chain is 36 steps
+//     whatever the layer.
+//   * tiles: "strip" = 8 pixels wide x 16*mt rows, the 8-row core-matrix groups of the UMMA descriptor are image rows
+//     (stride-byte-offset = plane pitch), every M row is a real output pixel; "flat" = flattened padded grid as in v1
+//     (used for narrow maps).
+// Warp roles (the warp scheduler favours high warp ids, so the latency-critical roles sit at the top):
+//   0-7 drain + epilogue | 8-11 a_lo split | 12 plane TMA | 13 weight TMA | 14,15 MMA issue (one M tile each; 14 owns TMEM)
+// Warp roles: 0 plane TMA | 1 weight TMA | 2,3 MMA issue (one M tile each; 2 also owns TMEM) | 4-11 drain + epilogue | 12-15 a_lo split
+// =====================================================================================================================
+namespace v2 {
+
+constexpr int kThreads2 = 512;
+constexpr int kPlaneRows = 344;                 // rows of 128 B per plane buffer
+constexpr uint32_t kPlaneBytes = kPlaneRows * 128;  // 44032 = 43 KiB (keeps every buffer 1024-aligned)
+constexpr int kWStages = 3;
+
+struct Args {
+  int nsrc;
+  int src_c[3];
+  int T;
+  int N, H, W, Cout;
+  int c;       // output channels per work item (MMA N = 2c main, c correction)
+  int mt;      // M tiles of 128 rows per work item (1 or 2)
+  int strip;   // 1: strip tiles (8 px wide groups), 0: flattened padded grid
+  int mtx;     // strip mode: M tiles side by side (1 or 2); tile mi sits at column block mi % mtx, row block mi / mtx
+  int R, Wt, Wp;
+  int tiles_x, tiles_y, n_ctile, total_items;
+  int relu;
+  int out_cstride, out_coff;
+  int store32;  // output rows are 32 B aligned: 256-bit stores
+  const float* bias;
+  const float* bn_scale;
+  const float* bn_shift;
+  float* out;
+  long long* stats;  // debug: per-CTA wait-cycle counters (null = off)
+  int dbg;           // debug: bit 0 = splitter does no work, bit 1 = no epilogue stores, bit 2 = producer loads the weights of the first item only
+};
+
+// barrier wait that adds the waited cycles to a register counter when the debug counters are on
+__device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, bool on, long long& acc) {
+  if (on) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// a - (the 19 bits the tensor core reads of a), rounded to the nearest tf32 (the hardware would truncate it)
+__device__ __forceinline__ float split_lo(float x) {
+  float d = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(d));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16], uint32_t (&w)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+  asm volatile(""
+               : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]),
+                 "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15])
+               :
+               : "memory");
+}
+
+struct Item {
+  int n, x0, y0, co0, tframe;
+};
+__device__ __forceinline__ Item decode_item(const Args& a, int it) {
+  Item r;
+  const int ct = it % a.n_ctile, sp = it / a.n_ctile;
+  const int tx = sp % a.tiles_x, ty = (sp / a.tiles_x) % a.tiles_y;
+  r.n = sp / (a.tiles_x * a.tiles_y);
+  r.x0 = tx * a.Wt, r.y0 = ty * a.R, r.co0 = ct * a.c;
+  r.tframe = a.T > 1 ? r.n % a.T : 0;
+  return r;
+}
+__device__ __forceinline__ bool src_valid(const Args& a, int s, int tframe) {
+  return a.T <= 1 || (tframe + s - 1 >= 0 && tframe + s - 1 < a.T);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads2, 1)
+k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+              const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b, Args a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t hi0 = sbase, lo0 = sbase + 2 * kPlaneBytes, w0 = sbase + 4 * kPlaneBytes;
+  constexpr uint32_t kWBytes = 2u * C * 128u;  // one tap stage: [w_hi rows | w_lo rows]
+  const uint32_t bars = w0 + kWStages * kWBytes;
+  // barrier slots (8 B each)
+  const uint32_t bar_hi_full = bars, bar_plane_free = bars + 16, bar_lo_full = bars + 32, bar_w_full = bars + 48,
+                 bar_w_free = bars + 72, bar_acc_full = bars + 96, bar_acc_empty = bars + 112, tmem_slot = bars + 128;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
+  const uint32_t tmem_cols_needed = 4u * a.mt * C;  // 2 stages x mt tiles x [main c | corr c]
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_hi_full + 8 * i, 1);
+      mbar_init(bar_plane_free + 8 * i, a.mt);  // one tcgen05.commit per issuing warp
+      mbar_init(bar_lo_full + 8 * i, 128);
+      mbar_init(bar_acc_full + 8 * i, a.mt);
+      mbar_init(bar_acc_empty + 8 * i, 256);
+    }
+    for (int i = 0; i < kWStages; ++i) mbar_init(bar_w_full + 8 * i, 1), mbar_init(bar_w_free + 8 * i, a.mt);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 14) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 12 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a0)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  const uint32_t box_bytes = (uint32_t)(a.R + 2) * a.Wp * 128u;
+
+  if (warp == 12) {
+    // ===================== plane producer =====================
+    if (lane == 0) {
+      int g = 0;
+      for (int it = blockIdx.x; it < a.total_items; it += gridDim.x) {
+        const Item t = decode_item(a, it);
+        for (int s = 0; s < a.nsrc; ++s) {
+          if (!src_valid(a, s, t.tframe)) continue;
+          const CUtensorMap* am = a.T > 1 ? &map_a0 : (s == 0 ? &map_a0 : (s == 1 ? &map_a1 : &map_a2));
+          const int img = a.T > 1 ? t.n + s - 1 : t.n;
+          for (int c0 = 0; c0 < a.src_c[s]; c0 += 32, ++g) {
+            const int st = g & 1;
+            if (a.dbg & 8) continue;
+            if (g >= 2) mbar_wait(bar_plane_free + 8 * st, ((g >> 1) - 1) & 1);
+            mbar_expect_tx(bar_hi_full + 8 * st, box_bytes);
+            tma_load_4d(am, hi0 + st * kPlaneBytes, bar_hi_full + 8 * st, c0, t.x0 - 1, t.y0 - 1, img);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 13) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      int wg = 0;
+      for (int it = blockIdx.x; it < a.total_items; it += gridDim.x) {
+        const Item t = decode_item(a, it);
+        int kbase_src = 0;
+        for (int s = 0; s < a.nsrc; ++s) {
+          const int Cs = a.src_c[s];
+          if (src_valid(a, s, t.tframe)) {
+            for (int c0 = 0; c0 < Cs; c0 += 32) {
+              for (int tap = 0; tap < 9; ++tap, ++wg) {
+                const int ws = wg % kWStages;
+                if (a.dbg & 4) continue;
+                if (wg >= kWStages) mbar_wait(bar_w_free + 8 * ws, ((wg / kWStages) - 1) & 1);
+                mbar_expect_tx(bar_w_full + 8 * ws, kWBytes);
+                const int k0 = kbase_src + tap * Cs + c0;
+                tma_load_2d(&map_b, w0 + ws * kWBytes, bar_w_full + 8 * ws, k0, t.co0);
+                tma_load_2d(&map_b, w0 + ws * kWBytes + C * 128u, bar_w_full + 8 * ws, k0, a.Cout + t.co0);
+              }
+            }
+          }
+          kbase_src += 9 * Cs;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 14) {
+    // ===================== MMA issuers =====================
+    // Two issuing warps: warp 14 owns M tile 0, warp 15 owns M tile 1 (disjoint accumulators, so no ordering between
+    // them is needed).  The tensor-core queue is shallow: every cycle an issuer spends on barrier waits, fences and
+    // descriptor arithmetic is a cycle its MMAs are not queued, and a second issuer fills those gaps.  One elected
+    // lane per warp runs the whole chunk (9 taps, fully unrolled: tap offsets, weight stage and parity are literals).
+    const int mi = warp - 14;
+    if (mi < a.mt) {
+      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
+      const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * C) >> 3) << 17);
+      const uint32_t idesc1 = idesc_base | ((uint32_t)(C >> 3) << 17);
+      const uint32_t sbo_a = a.strip ? (uint32_t)a.Wp * 8u : 64u;  // stride between 8-row groups, in 16 B units
+      const uint64_t desc_hi_a = (uint64_t)(sbo_a | (1u << 14) | (2u << 29)) << 32;
+      const uint64_t desc_hi_b = (uint64_t)(64u | (1u << 14) | (2u << 29)) << 32;
+      const uint32_t lbo = 1u << 16;
+      // this warp's M tile in the plane (16 B units): strip tiles are 8 px x 16 rows blocks, flat tiles 128 consecutive rows
+      const uint32_t tile_off16 = a.strip ? ((uint32_t)(mi % a.mtx) * 8u + (uint32_t)(mi / a.mtx) * 16u * (uint32_t)a.Wp) * 8u : (uint32_t)mi * 1024u;
+      const uint32_t wp8 = (uint32_t)a.Wp * 8u;
+      const uint32_t ah_base = lbo | ((((hi0)&0x3FFFF) >> 4) + tile_off16), al_base = lbo | ((((lo0)&0x3FFFF) >> 4) + tile_off16);
+      const uint32_t b_base = lbo | ((w0 & 0x3FFFF) >> 4);
+      const bool st_on = a.stats != nullptr && mi == 0;
+      long long c_lo = 0, c_acc = 0, c_issue = 0;
+      int g = 0;
+      const long long tm0 = a.stats ? clock64() : 0;
+      for (int it = blockIdx.x; it < a.total_items; it += gridDim.x) {
+        const Item t = decode_item(a, it);
+        int nchunks = 0;
+        for (int s = 0; s < a.nsrc; ++s)
+          if (src_valid(a, s, t.tframe)) nchunks += a.src_c[s] / 32;
+        for (int ci = 0; ci < nchunks; ++ci, ++g) {
+          const int st = g & 1;
+          timed_wait(bar_lo_full + 8 * st, (g >> 1) & 1, st_on, c_lo);
+          if (g >= 2) timed_wait(bar_acc_empty + 8 * st, ((g >> 1) - 1) & 1, st_on, c_acc);
+          if (elect_one()) {
+            const long long ti0 = st_on ? clock64() : 0;
+            const uint32_t ah = ah_base + (uint32_t)st * (kPlaneBytes >> 4), al = al_base + (uint32_t)st * (kPlaneBytes >> 4);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(st * a.mt * 2 * C + mi * 2 * C);
+            const uint32_t wpar = (uint32_t)g;  // weight stage `tap % 3` is in its (3g + tap/3)-th use
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              constexpr int kStagesLit = 3;
+              static_assert(kWStages == kStagesLit, "the unrolled tap loop assumes a 3-deep weight ring");
+              const int ws = tap % 3;
+              if (!(a.dbg & 4)) mbar_wait(bar_w_full + 8 * ws, (wpar + (uint32_t)(tap / 3)) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t shift16 = (uint32_t)(tap / 3) * wp8 + (uint32_t)(tap % 3) * 8u;
+              const uint32_t b16 = b_base + (uint32_t)ws * (kWBytes >> 4);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t dah = desc_hi_a | (ah + shift16 + 2u * kk);
+                const uint64_t dal = desc_hi_a | (al + shift16 + 2u * kk);
+                const uint64_t db = desc_hi_b | (b16 + 2u * kk);
+                umma_tf32(tmem_d, dah, db, idesc2, (tap == 0 && kk == 0) ? 0u : 1u);  // [a_hi*w_hi | a_hi*w_lo]
+                umma_tf32(tmem_d + (uint32_t)C, dal, db, idesc1, 1u);                // += a_lo*w_hi into the second half
+              }
+              umma_commit(bar_w_free + 8 * ws);
+            }
+            umma_commit(bar_plane_free + 8 * st);
+            umma_commit(bar_acc_full + 8 * st);
+            if (st_on) c_issue += clock64() - ti0;
+          }
+          __syncwarp();
+        }
+      }
+      if (st_on) {
+        // the elected lane may differ from call to call in principle; reduce the per-lane issue counters over the warp
+        for (int o = 16; o > 0; o >>= 1) c_issue += __shfl_xor_sync(0xffffffffu, c_issue, o);
+        if (lane == 0) {
+          long long* sp = a.stats + blockIdx.x * 16;
+          sp[0] += c_lo, sp[1] += c_acc, sp[10] += c_issue;
+          sp[7] += clock64() - tm0;
+          sp[8] += g;
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== a_lo splitter =====================
+    const int et = threadIdx.x - 256;  // 0..127
+    const int n_f4 = (a.R + 2) * a.Wp * 8;
+    const bool st_on = a.stats != nullptr && threadIdx.x == 256;
+    long long c_free = 0, c_hi = 0, c_work = 0;
+    int g = 0;
+    for (int it = blockIdx.x; it < a.total_items; it += gridDim.x) {
+      const Item t = decode_item(a, it);
+      int nchunks = 0;
+      for (int s = 0; s < a.nsrc; ++s)
+        if (src_valid(a, s, t.tframe)) nchunks += a.src_c[s] / 32;
+      for (int ci = 0; ci < nchunks; ++ci, ++g) {
+        const int st = g & 1;
+        if (g >= 2) timed_wait(bar_plane_free + 8 * st, ((g >> 1) - 1) & 1, st_on, c_free);  // a_lo[st] free
+        if (!(a.dbg & 8)) timed_wait(bar_hi_full + 8 * st, (g >> 1) & 1, st_on, c_hi);
+        const long long ts0 = st_on ? clock64() : 0;
+        const uint32_t hi = hi0 + st * kPlaneBytes, lo = lo0 + st * kPlaneBytes;
+        int i = (a.dbg & 1) ? n_f4 : et;
+        for (; i + 7 * 128 < n_f4; i += 1024) {  // eight independent 128-bit loads in flight per thread
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = lds128(hi + 16u * (i + 128 * u));
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            sts128(lo + 16u * (i + 128 * u), make_float4(split_lo(v[u].x), split_lo(v[u].y), split_lo(v[u].z), split_lo(v[u].w)));
+        }
+        for (; i < n_f4; i += 128) {
+          float4 v = lds128(hi + 16u * i);
+          sts128(lo + 16u * i, make_float4(split_lo(v.x), split_lo(v.y), split_lo(v.z), split_lo(v.w)));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(bar_lo_full + 8 * st);
+        if (st_on) c_work += clock64() - ts0;
+      }
+    }
+    if (st_on) {
+      long long* sp = a.stats + blockIdx.x * 16;
+      sp[3] += c_free, sp[4] += c_hi, sp[5] += c_work;
+    }
+  } else {
+    // ===================== drain + epilogue =====================
+    // thread = one TMEM lane (pixel row of an M tile) x one half of the tile's output channels
+    constexpr int CH = C / 2;
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    float acc[2][CH];
+    const bool st_on = a.stats != nullptr && threadIdx.x == 0;
+    long long c_full = 0, c_epi = 0;
+    int g = 0;
+    for (int it = blockIdx.x; it < a.total_items; it += gridDim.x) {
+      const Item t = decode_item(a, it);
+      int nchunks = 0;
+      for (int s = 0; s < a.nsrc; ++s)
+        if (src_valid(a, s, t.tframe)) nchunks += a.src_c[s] / 32;
+      for (int ci = 0; ci < nchunks; ++ci, ++g) {
+        const int st = g & 1;
+        timed_wait(bar_acc_full + 8 * st, (g >> 1) & 1, st_on, c_full);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tm_stage = tmem_base + lane_addr + (uint32_t)(st * a.mt * 2 * C);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          if (mi < a.mt) {
+#pragma unroll
+            for (int b16 = 0; b16 < CH / 16; ++b16) {
+              uint32_t vm[16], vc[16];
+              const uint32_t col = (uint32_t)(mi * 2 * C + half * CH + b16 * 16);
+              tmem_ld16(tm_stage + col, vm);
+              tmem_ld16(tm_stage + col + (uint32_t)C, vc);
+              tmem_ld_wait16(vm, vc);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float v = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
+                acc[mi][b16 * 16 + j] = ci == 0 ? v : acc[mi][b16 * 16 + j] + v;
+              }
+              if (a.dbg & 16) break;
+            }
+          }
+          if (a.dbg & 16) break;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(bar_acc_empty + 8 * st);
+      }
+      // epilogue of this work item
+      const long long te0 = st_on ? clock64() : 0;
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        if (mi < a.mt) {
+          const int m = quarter * 32 + lane;
+          int r, xc;
+          bool valid;
+          if (a.strip) {
+            r = (mi / a.mtx) * 16 + (m >> 3), xc = (mi % a.mtx) * 8 + (m & 7);
+            valid = true;
+          } else {
+            const int mm = mi * 128 + m;
+            r = mm / a.Wp, xc = mm % a.Wp;
+            valid = r < a.R && xc < a.Wt;
+          }
+          const int gy = t.y0 + r, gx = t.x0 + xc;
+          valid = valid && gy < a.H && gx < a.W && !(a.dbg & 2);
+          if (valid) {
+            const int cbase = t.co0 + half * CH;
+            float* orow = a.out + (((size_t)t.n * a.H + gy) * a.W + gx) * a.out_cstride + a.out_coff + cbase;
+            // 32 B per store instruction and thread = whole sectors (16 B pieces would reach L2 as partial-sector writes)
+#pragma unroll
+            for (int q = 0; q < CH / 8; ++q) {
+              float o[8];
+              // per-channel epilogue constants: 128-bit read-only loads (same address in every lane -> one broadcast each)
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + cbase + 8 * q));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + cbase + 8 * q + 4));
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int u = 0; u < 8; ++u) o[u] = acc[mi][8 * q + u] + bb[u];
+              if (a.bn_scale) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.bn_scale + cbase + 8 * q));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.bn_scale + cbase + 8 * q + 4));
+                const float4 h0 = __ldg(reinterpret_cast<const float4*>(a.bn_shift + cbase + 8 * q));
+                const float4 h1 = __ldg(reinterpret_cast<const float4*>(a.bn_shift + cbase + 8 * q + 4));
+                const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) o[u] = fmaf(o[u], ss[u], hh[u]);
+              }
+              if (a.relu) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) o[u] = fmaxf(o[u], 0.f);
+              }
+              if (a.store32) {
+                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + 8 * q), "f"(o[0]), "f"(o[1]),
+                             "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                             : "memory");
+              } else {
+                *reinterpret_cast<float4*>(orow + 8 * q) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(orow + 8 * q + 4) = make_float4(o[4], o[5], o[6], o[7]);
+              }
+            }
+          }
+        }
+      }
+      if (st_on) c_epi += clock64() - te0;
+    }
+    if (st_on) {
+      long long* sp = a.stats + blockIdx.x * 16;
+      sp[6] += c_full, sp[9] += c_epi;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 14) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+struct Cfg {
+  int c, mt, strip, mtx, R, Wt, Wp, tiles_x, tiles_y, n_ctile, total;
+};
+
+// pick the tile shape with the fewest tensor-core rounds over 148 SMs (ties: fewer wasted M rows, then larger tiles)
+bool choose(int n_img, int H, int W, int Cout, Cfg* best) {
+  if (Cout % 32) return false;
+  const int c = (Cout % 64 == 0) ? 64 : 32;
+  double best_cost = 1e30;
+  bool found = false;
+  for (int strip = 0; strip <= 1; ++strip) {
+    for (int mt = 1; mt <= 2; ++mt) {
+      for (int mtx = 1; mtx <= (strip ? mt : 1); ++mtx) {
+        for (int Wt = (strip ? 8 * mtx : 6); Wt <= (strip ? 8 * mtx : 41); ++Wt) {
+          Cfg k;
+          k.c = c, k.mt = mt, k.strip = strip, k.mtx = mtx, k.Wt = Wt, k.Wp = Wt + 2;
+          if (strip) {
+            k.R = 16 * (mt / mtx);
+          } else {
+            k.R = (mt * 128) / k.Wp;
+            if (k.R > H) k.R = H;
+            if (Wt > W) continue;
+          }
+          if (k.R < 1 || (k.R + 2) * k.Wp > kPlaneRows || k.R + 2 > 256) continue;
+          // last row a shifted view can touch must stay inside the plane buffer
+          const int last = strip ? ((k.R + 1) * k.Wp + (Wt - 8) + 2 + 7) : (mt * 128 + 2 * k.Wp + 1);
+          if (last >= kPlaneRows) continue;
+          k.tiles_x = cdiv(W, Wt), k.tiles_y = cdiv(H, k.R), k.n_ctile = Cout / c;
+          k.total = n_img * k.tiles_x * k.tiles_y * k.n_ctile;
+          const double rounds = (double)cdiv(k.total, 148);
+          // cost ~ rounds x (MMA time of one item + fixed per-item overhead); one M tile leaves the second issuer idle
+          const double cost = rounds * (mt == 2 ? 2.15 : 1.35) + 1e-3 * (double)k.total * mt * 128 / ((double)n_img * H * W * k.n_ctile);
+          if (cost < best_cost - 1e-9) best_cost = cost, *best = k, found = true;
+        }
+      }
+    }
+  }
+  return found;
+}
+
+size_t smem_bytes(int c) { return (size_t)4 * kPlaneBytes + (size_t)kWStages * 2 * c * 128 + 256 + 1024; }
+
+}  // namespace v2
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -399,6 +876,9 @@ bool choose_cfg(int H, int W, int Cout, TileCfg* c) {
 
 int g_base_offset_mode = 0;
 int g_min_hw = 16;
+long long* g_stats = nullptr;
+int g_dbg = 0;
+int g_impl = 2;  // 2: persistent pipelined kernel (v2); 1: the first-generation kernel
 
 }  // namespace
 
@@ -407,7 +887,24 @@ extern "C" int pcab_conv3x3_tc_set_base_offset_mode(int mode) {
   g_tile_mode = ((mode >> 1) & 1) ^ 1;  // bit 1 set selects the large 1-CTA/SM tile shape (tuning knob)
   g_min_hw = (mode & 4) ? 32 : 16;        // bit 2 set: leave maps below 32x32 to the FP32 path
   g_max_stages = (mode & 8) ? 2 : 4;      // bit 3 set: 2-stage weight pipeline
+  g_impl = (mode & 16) ? 1 : 2;           // bit 4 set: first-generation kernel
+  g_dbg = (mode >> 5) & 31;               // bits 5-7: v2 timing experiments (results are wrong when set)
   return 0;
+}
+
+// debug: device buffer of 148*16 int64 wait-cycle counters filled by the v2 kernel (null = off)
+extern "C" int pcab_conv3x3_tc_set_stats(long long* device_counters) {
+  g_stats = device_counters;
+  return 0;
+}
+
+// the tile plan the v2 kernel would use: out[0..9] = c, mt, strip, mtx, R, Wt, tiles_x, tiles_y, cout tiles, work items
+extern "C" int pcab_conv3x3_tc_plan(int n_images, int H, int W, int Cout, int* out10) {
+  v2::Cfg k;
+  PCAB_REQUIRE(v2::choose(n_images, H, W, Cout, &k), "unsupported shape");
+  int v[10] = {k.c, k.mt, k.strip, k.mtx, k.R, k.Wt, k.tiles_x, k.tiles_y, k.n_ctile, k.total};
+  for (int i = 0; i < 10; ++i) out10[i] = v[i];
+  return PCAB_OK;
 }
 
 extern "C" int pcab_conv3x3_tc_supported(int n_sources, int c0, int c1, int c2, int Cout, int H, int W) {
@@ -415,6 +912,10 @@ extern "C" int pcab_conv3x3_tc_supported(int n_sources, int c0, int c1, int c2, 
   int cs[3] = {c0, c1, c2};
   for (int s = 0; s < n_sources; ++s)
     if (cs[s] <= 0 || cs[s] % 32) return 0;
+  if (g_impl == 2) {
+    v2::Cfg k;
+    return (H >= 8 && W >= 8 && v2::choose(1, H, W, Cout, &k)) ? 1 : 0;
+  }
   if (H < g_min_hw || W < g_min_hw) return 0;  // the smallest maps keep the FP32 CUDA-core path (too few tiles for 148 SMs)
   TileCfg c;
   return choose_cfg(H, W, Cout, &c) ? 1 : 0;
@@ -422,6 +923,83 @@ extern "C" int pcab_conv3x3_tc_supported(int n_sources, int c0, int c1, int c2, 
 
 // floats in the tensor-core weight pack: [2 (hi, lo)][Cout][9 * cin_total]
 extern "C" size_t pcab_conv3x3_tc_pack_floats(int cin_total, int Cout) { return (size_t)2 * Cout * 9 * cin_total; }
+
+namespace {
+int conv3x3_tc_v2(EncodeTiledFn enc, const float* src0, int c0, const float* src1, int c1, const float* src2, int c2,
+                  int temporal_T, const float* weight_tc_packed, const float* bias, const float* bn_scale,
+                  const float* bn_shift, int relu, float* out, int n_images, int H, int W, int Cout, int out_cstride,
+                  int out_coff, cudaStream_t stream) {
+  v2::Cfg cfg;
+  PCAB_REQUIRE(v2::choose(n_images, H, W, Cout, &cfg), "unsupported shape");
+  PCAB_REQUIRE(out_cstride % 4 == 0 && out_coff % 4 == 0 && ((uintptr_t)out & 15) == 0, "output channel layout must be 16B aligned");
+  PCAB_REQUIRE(((uintptr_t)bias & 15) == 0 && ((uintptr_t)bn_scale & 15) == 0 && ((uintptr_t)bn_shift & 15) == 0,
+               "bias / BN vectors must be 16B aligned");
+  const float* srcs[3] = {src0, src1, src2};
+  int cs[3] = {c0, c1, c2};
+  int nsrc = src2 ? 3 : (src1 ? 2 : 1);
+  int T = temporal_T > 1 ? temporal_T : 1;
+  if (T > 1) PCAB_REQUIRE(nsrc == 3 && src0 == src1 && src1 == src2, "temporal mode takes the same tensor three times");
+  int cin_total = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    PCAB_REQUIRE(cs[s] > 0 && cs[s] % 32 == 0, "source channels must be a multiple of 32");
+    cin_total += cs[s];
+  }
+  CUtensorMap maps[4];
+  for (int s = 0; s < 3; ++s) {
+    int ss = s < nsrc ? s : 0;
+    cuuint64_t dims[4] = {(cuuint64_t)cs[ss], (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_images};
+    cuuint64_t strides[3] = {(cuuint64_t)cs[ss] * 4, (cuuint64_t)W * cs[ss] * 4, (cuuint64_t)H * W * cs[ss] * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)cfg.Wp, (cuuint32_t)(cfg.R + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&maps[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)srcs[ss], dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      pcab_set_error("pcab_conv3x3_tc: cuTensorMapEncodeTiled(A%d) failed: %d", s, (int)r);
+      return PCAB_ERR_CUDA;
+    }
+  }
+  {
+    cuuint64_t K = (cuuint64_t)9 * cin_total;
+    cuuint64_t dims[2] = {K, (cuuint64_t)2 * Cout};
+    cuuint64_t strides[1] = {K * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)cfg.c};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&maps[3], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)weight_tc_packed, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      pcab_set_error("pcab_conv3x3_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+      return PCAB_ERR_CUDA;
+    }
+  }
+  v2::Args a;
+  a.nsrc = nsrc;
+  for (int s = 0; s < 3; ++s) a.src_c[s] = cs[s];
+  a.T = T;
+  a.N = n_images, a.H = H, a.W = W, a.Cout = Cout;
+  a.c = cfg.c, a.mt = cfg.mt, a.strip = cfg.strip, a.mtx = cfg.mtx, a.R = cfg.R, a.Wt = cfg.Wt, a.Wp = cfg.Wp;
+  a.store32 = (out_cstride % 8 == 0 && out_coff % 8 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0;
+  a.tiles_x = cfg.tiles_x, a.tiles_y = cfg.tiles_y, a.n_ctile = cfg.n_ctile, a.total_items = cfg.total;
+  a.relu = relu, a.out_cstride = out_cstride, a.out_coff = out_coff;
+  a.bias = bias, a.bn_scale = bn_scale, a.bn_shift = bn_shift, a.out = out;
+  a.stats = g_stats;
+  a.dbg = g_dbg;
+  static bool configured = false;
+  if (!configured) {
+    PCAB_CUDA(cudaFuncSetAttribute(v2::k_conv3x3_tc2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::smem_bytes(32)));
+    PCAB_CUDA(cudaFuncSetAttribute(v2::k_conv3x3_tc2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::smem_bytes(64)));
+    configured = true;
+  }
+  const int grid = cfg.total < 148 ? cfg.total : 148;
+  if (cfg.c == 64)
+    v2::k_conv3x3_tc2<64><<<grid, v2::kThreads2, v2::smem_bytes(64), stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+  else
+    v2::k_conv3x3_tc2<32><<<grid, v2::kThreads2, v2::smem_bytes(32), stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+  PCAB_CHECK_LAUNCH("pcab_conv3x3_tc(v2)");
+  return PCAB_OK;
+}
+}  // namespace
 
 extern "C" int pcab_conv3x3_tc(const float* src0, int c0, const float* src1, int c1, const float* src2, int c2,
                                int temporal_T, const float* weight_tc_packed, const float* bias, const float* bn_scale,
@@ -432,6 +1010,9 @@ extern "C" int pcab_conv3x3_tc(const float* src0, int c0, const float* src1, int
     pcab_set_error("pcab_conv3x3_tc: cuTensorMapEncodeTiled unavailable");
     return PCAB_ERR_CUDA;
   }
+  if (g_impl == 2)
+    return conv3x3_tc_v2(enc, src0, c0, src1, c1, src2, c2, temporal_T, weight_tc_packed, bias, bn_scale, bn_shift, relu, out,
+                         n_images, H, W, Cout, out_cstride, out_coff, stream);
   TileCfg cfg;
   PCAB_REQUIRE(choose_cfg(H, W, Cout, &cfg), "unsupported shape");
   PCAB_REQUIRE(out_cstride % 4 == 0 && out_coff % 4 == 0, "output channel layout must be 16B aligned");

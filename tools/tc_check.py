@@ -73,5 +73,21 @@ for n, cs, cout, H, W, T in shapes:
         e1.record()
         torch.cuda.synchronize()
         ts[name] = e0.elapsed_time(e1) / 10
+    import ctypes
+    plan = (ctypes.c_int * 10)()
+    _lib.lib().pcab_conv3x3_tc_plan(I(n), I(H), I(W), I(cout), plan)
+    print("   plan c=%d mt=%d strip=%d mtx=%d R=%d Wt=%d tiles=%dx%d ctiles=%d items=%d (%.2f rounds)" % (*list(plan), plan[9] / 148))
+    if "--stats" in sys.argv:
+        st = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+        _lib.lib().pcab_conv3x3_tc_set_stats(P(st))
+        call("pcab_conv3x3_tc", *args(tcw, out))
+        torch.cuda.synchronize()
+        _lib.lib().pcab_conv3x3_tc_set_stats(P(None))
+        s2 = st.view(148, 16).double()
+        act = s2[:, 8] > 0
+        m = s2[act].mean(0)
+        names = ["mma:wait_lo", "mma:wait_acc", "mma:wait_w", "split:wait_free", "split:wait_hi", "split:work", "drain:wait_acc", "mma:total", "chunks", "epilogue", "mma:issue"]
+        print("   stats (mean cycles per CTA, %d CTAs): " % int(act.sum()) + ", ".join(f"{nm}={m[i].item():.0f}" for i, nm in enumerate(names)),
+              "| per chunk: total %.0f" % (m[7] / m[8]).item())
     print(f"n={n} cs={cs} cout={cout} {H}x{W} T={T}: maxerr {err:.3e} (ref max {ref.abs().max().item():.1f}) nan {nan} | "
           f"f32 {ts['f32']:.3f} ms {flops / ts['f32'] / 1e9:.1f} TF/s | tc {ts['tc']:.3f} ms {flops / ts['tc'] / 1e9:.1f} TF/s")
