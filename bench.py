@@ -37,33 +37,70 @@ def env_int(name, default):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region, sampled in-process through NVML every 100 ms
+    (forking nvidia-smi five times a second perturbs a multi-threaded timed region; it stays as the fallback)."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.rows = []  # (sm_mhz, sm_max_mhz, [active reasons])
         self.stop_flag = False
+        self.nvml = None
+        try:
+            import pynvml
 
-    def run(self):
+            pynvml.nvmlInit()
+            idx = index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[index])
+                except ValueError:
+                    idx = index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+        self.rows.append((sm, self.sm_max, [k for k, b in bits.items() if mask & b]))
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            c = [x.strip() for x in out.split(",")]
+            self.rows.append((float(c[0]), float(c[1]), [n for i, n in enumerate(self.NAMES) if c[2 + i].lower().startswith("active")]))
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1 if self.nvml is not None else 0.5)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        rows = list(self.rows)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(r[0] for r in rows)
+        reasons = sorted(set(x for r in rows for x in r[2]))
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": rows[0][1], "reasons": reasons, "samples": len(rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def make_scenes(workload, rank, n):
@@ -143,6 +180,7 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="force the FP32 CUDA-core convolution path")
+    ap.add_argument("--in-flight", type=int, default=3, help="independent scenes kept in flight per GPU (1 = serial)")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
@@ -157,7 +195,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from pcaccumulation_b200.runner import SceneRunner, scene_to_points4
+    from pcaccumulation_b200.runner import ScenePipeline, SceneRunner, scene_to_points4
 
     cfg = config.workload_config(args.workload)
     runner = SceneRunner(cfg, device=dev)
@@ -165,6 +203,9 @@ def main():
     sd = fixture.fixture_state_dict(model.state_dict(), 42)
     model.load_state_dict(sd)
     model.use_tensor_cores = not args.no_tc
+    pipe = ScenePipeline(cfg, sd, depth=max(1, args.in_flight), device=dev)
+    for r in pipe.runners:
+        r.model.use_tensor_cores = not args.no_tc
     scenes = make_scenes(args.workload, rank, N_SCENES)
     host_pts = [torch.from_numpy(scene_to_points4(s)).pin_memory() for s in scenes]
     host_ego = [torch.from_numpy(s["ego_motion_gt"])[None].contiguous().pin_memory() for s in scenes]
@@ -191,6 +232,7 @@ def main():
         return runner.run_host(host_pts[k], nums[k], ego_motion_gt_host=host_ego[k], out=out_bufs[k])
 
     def timed(fn, steps):
+        """K serial steps on the current stream (used for the per-kernel roofline events)."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -203,9 +245,54 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    def timed_pipeline(steps, host):
+        """EXACTLY K scenes through the pipeline (``in_flight`` of them concurrently), device time start -> last result."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        futs = []
+        for i in range(steps):
+            k = i % N_SCENES
+            if host:
+                futs.append(pipe.submit(host_pts[k], nums[k], ego=host_ego[k], seed=1000 + i, out=out_bufs[i % len(out_bufs)], host=True))
+            else:
+                futs.append(pipe.submit(dev_pts[k], nums[k], ego=dev_ego[k], seed=1000 + i))
+        cur = torch.cuda.current_stream()
+        for f in futs:
+            _, done = f.result()
+            cur.wait_event(done)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # one set of pinned result buffers per in-flight scene and per distinct scene size
+    out_bufs = out_bufs * max(1, args.in_flight)
+    out_bufs = [{k: torch.empty_like(v).pin_memory() for k, v in o.items()} for o in out_bufs]
+
+    sampler = ClockSampler(local)
+    sampler.start()  # started before the warm-up: its first fork/exec of nvidia-smi stays outside the timed regions
     for i in range(args.warmup):
         step_dev(i)
         step_host(i)
+    # every slot (stream + caching-allocator pool) has to see every scene size before its pool stops growing
+    # (cudaMalloc synchronises the device): warm up with two full cycles of the scenes through the slots
+    n_warm = max(args.warmup, 2 * N_SCENES * max(1, args.in_flight))
+    timed_pipeline(n_warm, host=False)
+    timed_pipeline(n_warm, host=True)
+    sampler.rows.clear()
+    ms_dev = timed_pipeline(args.steps, host=False)
+    ms_host = timed_pipeline(args.steps, host=True)
+    # serial pass on one stream: latency of one scene and CUDA-event brackets around every conv launch (roofline)
+    model.conv_events = []
+    ms_serial = timed(step_dev, args.steps)
+    events = model.conv_events
+    model.conv_events = None
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
     # kernel launch census of one step (our kernels only: everything that is not an ATen kernel)
     launches_per_step = None
     try:
@@ -220,15 +307,6 @@ def main():
     except Exception:
         pass
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    model.conv_events = []
-    ms_dev = timed(step_dev, args.steps)
-    events = model.conv_events
-    model.conv_events = None
-    ms_host = timed(step_host, args.steps)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
 
     # roofline of the convolution kernels (dominant): algorithmic FLOPs / event time
     tot_flops = sum(f for _, _, f, _ in events)
@@ -262,22 +340,39 @@ def main():
         dt = time.perf_counter() - t0
         cpu_base = {"value": n_cpu / dt, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
                     "sample": f"{n_cpu} scenes of {args.workload} (voxelise+collate+forward) after 1 warm-up, oracle/oracle.py"}
-        # EPE of the accumulated points against the oracle on the same scenes (the metric's parity half)
-        errs = []
+        # parity half of the metric: the free-running CUDA forward against the oracle on the same scenes and seed.
+        # Labels are integer decisions (bit-exact target); a point whose two logits tie to ~1e-6 can flip between FP32
+        # summation orders, and the TubeNet poses of the instance it joins then differ (random-weight fixture), so the
+        # EPE is reported as median / fraction of points within 1 mm next to the mean.
+        fb_mis, mos_mis, inst_mis, pose_err, epe_mean, epe_med, within = 0, 0, 0, 0.0, [], [], []
+        n_pts = 0
         for i in range(n_cpu):
             torch.manual_seed(42)
             res = runner.run_device(dev_pts[i], nums[i], ego_motion_gt=dev_ego[i])
-            errs.append(float((res["rec_est"].cpu() - refs[i]["rec_est"]).norm(dim=1).mean()))
-        epe = float(np.mean(errs))
+            ref = refs[i]
+            n_pts += dev_pts[i].shape[0]
+            fb_mis += int((res["fb_est_per_points"].cpu() != ref["fb_est_per_points"]).sum())
+            mos_mis += int((res["mos_est"].cpu().argmax(1) != ref["mos_est"].argmax(1)).sum())
+            if "inst_labels_est" in ref:
+                inst_mis += int((res["inst_labels_est"].cpu() != ref["inst_labels_est"]).sum())
+            pose_err = max(pose_err, float((res["ego_motion_est"].cpu() - ref["ego_motion_est"]).abs().max()))
+            d = (res["rec_est"].cpu() - ref["rec_est"]).norm(dim=1)
+            epe_mean.append(float(d.mean()))
+            epe_med.append(float(d.median()))
+            within.append(float((d < 1e-3).float().mean()))
+        epe = {"scenes": n_cpu, "points": n_pts, "fb_label_mismatches": fb_mis, "mos_label_mismatches": mos_mis,
+               "inst_label_mismatches": inst_mis, "ego_pose_max_abs_err": pose_err, "epe_mean_m": float(np.mean(epe_mean)),
+               "epe_median_m": float(np.mean(epe_med)), "frac_points_within_1mm": float(np.mean(within))}
 
     if rank == 0:
         line = {
             "metric": "scenes/sec", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": n_warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (tensor path: 3xTF32 split, FP32 accumulate)" if "tc" in paths else "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {workload_desc(args.workload)}", "batch": 1, "mode": "test",
-                       "scenes_per_rank": N_SCENES, "parallelism": f"dp{world} (scene sharding, no data-path collective)",
+                       "scenes_per_rank": N_SCENES, "scenes_in_flight": max(1, args.in_flight),
+                       "serial_ms_per_scene": ms_serial / args.steps, "parallelism": f"dp{world} (scene sharding, no data-path collective)",
                        "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "conv_path": paths},
             "e2e": {"value": e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -285,9 +380,9 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "kernel": "conv3x3 (all launches, %.0f per step)" % n_conv, "achieved": achieved,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
-                         "conv_ms_per_step": tot_ms / max(args.steps, 1), "conv_share_of_step": tot_ms / ms_dev},
+                         "conv_ms_per_step": tot_ms / max(args.steps, 1), "conv_share_of_step": tot_ms / ms_serial},
             "cpu_baseline": cpu_base,
-            "epe_vs_oracle_m": epe,
+            "parity_vs_oracle": epe,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -230,6 +230,7 @@ class MotionNet(nn.Module):
         # 'offset_est' [N,2], 'inst_labels_est' [N]
         self.inject = {}
         self.stage_marks = None  # when a list: (name, cuda event) at stage boundaries (profiling aid)
+        self.rng = None  # torch.Generator for the keypoint permutations (None = the global CPU generator, as upstream)
         self.conv_events = None  # when a list: (start_event, end_event, flops, path) per conv launch (bench roofline)
 
     # ------------------------------------------------------------------------------------------
@@ -618,7 +619,7 @@ class MotionNet(nn.Module):
             if n <= 0:
                 raise IndexError("no background pillars to register (models/egomotion.py:169)")
             if n > N_KPTS:
-                return torch.randperm(n)[:N_KPTS]
+                return torch.randperm(n, generator=self.rng)[:N_KPTS]
             c = torch.arange(N_KPTS)
             c[n:] = n - 1
             return c

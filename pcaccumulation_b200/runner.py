@@ -5,6 +5,9 @@ except that voxelisation and collation run on the device (``libs/voxel_generator
 ``libs/dataloader.py:7-40`` are CPU code in the reference).  ``run_host`` is the end-to-end entry used by the
 benchmark: pinned host buffers in, host results out, with the H2D/D2H copies on the caller's stream.
 """
+import queue
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 import torch
 
@@ -93,6 +96,65 @@ class SceneRunner:
                 out[key].copy_(src, non_blocking=True)
                 d2h += src.numel() * src.element_size()
         return res, h2d, d2h
+
+
+class ScenePipeline:
+    """Keeps ``depth`` independent scenes in flight on ONE GPU.
+
+    Scenes never interact, but one forward has ~7 host round trips (pillar count, background
+    counts for the keypoint draw, FG / instance counts) and many small latency-bound kernels (ego pairs, DBSCAN
+    union-find, the 18x18 / 36x36 maps).  Each slot owns a host thread, a CUDA stream, a ``SceneRunner`` (its own
+    activations, pinned staging and keypoint generator; weights are loaded per slot, 44 MB) so that the bubbles of
+    one scene are filled with the kernels of another.  ``depth=1`` is the plain serial runner on a side stream.
+    """
+
+    def __init__(self, cfg, state_dict=None, depth=2, device="cuda"):
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.depth = int(depth)
+        self.runners = [SceneRunner(cfg, device=self.device) for _ in range(self.depth)]
+        self._free = queue.SimpleQueue()
+        for r in self.runners:
+            r.model.rng = torch.Generator()  # per-slot CPU generator: the global one would interleave between threads
+            self._free.put((r, torch.cuda.Stream(device=self.device)))
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+        # torch initialises its linear-algebra backend lazily and not thread-safely: touch it once from this thread
+        eye = torch.eye(4, device=self.device).repeat(2, 1, 1)
+        torch.linalg.inv(eye)
+        torch.linalg.svd(eye[:, :3, :3])
+        torch.cuda.synchronize(self.device)
+        self._pool = ThreadPoolExecutor(max_workers=self.depth, thread_name_prefix="pcab-scene")
+
+    def load_state_dict(self, state_dict):
+        for r in self.runners:
+            r.model.load_state_dict(state_dict)
+
+    def _work(self, points4, num_points, ego, seed, out, host):
+        runner, stream = self._free.get()
+        try:
+            torch.cuda.set_device(self.device)
+            with torch.cuda.stream(stream):
+                if seed is not None:
+                    runner.model.rng.manual_seed(int(seed))
+                if host:
+                    res = runner.run_host(points4, num_points, ego_motion_gt_host=ego, out=out)[0]
+                else:
+                    res = runner.run_device(points4, num_points, ego_motion_gt=ego)
+                done = torch.cuda.Event()
+                done.record(stream)
+            return res, done
+        finally:
+            self._free.put((runner, stream))
+
+    def submit(self, points4, num_points, ego=None, seed=None, out=None, host=False):
+        """Queue one scene; returns a future of ``(results, cuda_event)``.  The results live on the slot's stream:
+        wait for the event (``event.synchronize()`` or ``stream.wait_event``) before reading them."""
+        return self._pool.submit(self._work, points4, num_points, ego, seed, out, host)
+
+    def close(self):
+        self._pool.shutdown(wait=True)
 
 
 def scene_to_points4(scene):
