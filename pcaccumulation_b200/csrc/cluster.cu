@@ -116,80 +116,121 @@ __device__ __forceinline__ int lower_bound(const unsigned int* a, int n, unsigne
   return lo;
 }
 
+// Neighbour search is shared by FOUR lanes per point: lane `part` walks cells part, part+4, part+8 of the 3x3 block, so
+// the serial scan per thread is a quarter as long and four times as many warps are resident to hide its latency
+// (a scene has only ~10^4..10^5 de-duplicated dynamic points: one thread per point leaves the SMs nearly empty).
+constexpr int kParts = 4;
+
 template <typename F>
 __device__ __forceinline__ void for_neighbors(int u, const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
                                               const int* __restrict__ cval_sorted, int U, unsigned int mykey, double eps,
-                                              F&& fn) {
+                                              int part, F&& fn) {
   int cx = mykey & 0xffff, cy = mykey >> 16;
   double x = pxy[2 * u], y = pxy[2 * u + 1];
-  for (int dy = -1; dy <= 1; ++dy)
-    for (int dx = -1; dx <= 1; ++dx) {
-      unsigned int k = cell_key(cx + dx, cy + dy);
-      for (int j = lower_bound(ckey_sorted, U, k); j < U && ckey_sorted[j] == k; ++j) {
-        int v = cval_sorted[j];
-        double ex = (double)pxy[2 * v] - x, ey = (double)pxy[2 * v + 1] - y;
-        if (sqrt(ex * ex + ey * ey) <= eps) fn(v);
-      }
+  for (int c = part; c < 9; c += kParts) {
+    unsigned int k = cell_key(cx + (c % 3) - 1, cy + (c / 3) - 1);
+    for (int j = lower_bound(ckey_sorted, U, k); j < U && ckey_sorted[j] == k; ++j) {
+      int v = cval_sorted[j];
+      double ex = (double)pxy[2 * v] - x, ey = (double)pxy[2 * v + 1] - y;
+      if (sqrt(ex * ex + ey * ey) <= eps) fn(v);
     }
+  }
+}
+
+// warp-uniform loop over groups of kParts lanes: j0 is the first point of this warp's current batch of 32/kParts points
+#define PCAB_GROUP_LOOP(j, ok, part, U)                                                                   \
+  const int part = threadIdx.x & (kParts - 1), grp_in_warp = (threadIdx.x & 31) / kParts;                 \
+  const int grp_stride = (gridDim.x * blockDim.x) / kParts;                                               \
+  for (int j0 = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / kParts, j = j0 + grp_in_warp, ok = j < (U); j0 < (U); \
+       j0 += grp_stride, j = j0 + grp_in_warp, ok = j < (U))
+
+__device__ __forceinline__ int group_sum(int v) {
+#pragma unroll
+  for (int o = 1; o < kParts; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int group_min(int v) {
+#pragma unroll
+  for (int o = 1; o < kParts; o <<= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
 }
 
 __global__ void k_core(const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
                        const int* __restrict__ cval_sorted, const Counts* __restrict__ cnt, double eps, int min_samples,
                        int* __restrict__ key_of /* unsorted cell key per point */, int* __restrict__ core,
                        int* __restrict__ parent) {
-  int U = cnt->n_unique;
-  int stride = gridDim.x * blockDim.x;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < U; j += stride) {
-    int u = cval_sorted[j];
-    key_of[u] = (int)ckey_sorted[j];
-    int c = 0;
-    for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, ckey_sorted[j], eps, [&](int) { ++c; });
-    core[u] = c >= min_samples;
-    parent[u] = u;
+  const int U = cnt->n_unique;
+  PCAB_GROUP_LOOP(j, ok, part, U) {
+    int c = 0, u = 0;
+    if (ok) {
+      u = cval_sorted[j];
+      for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, ckey_sorted[j], eps, part, [&](int) { ++c; });
+    }
+    c = group_sum(c);
+    if (ok && part == 0) {
+      key_of[u] = (int)ckey_sorted[j];
+      core[u] = c >= min_samples;
+      parent[u] = u;
+    }
   }
 }
 
-__device__ int uf_find(int* parent, int i) {
+// Union-find over the core points.  Roots only ever move to smaller indices (the larger root is linked under the
+// smaller one), so the root of a finished component is its lowest-index core point whatever the order of the unions.
+// Reads go to L2 (ld.global.cg): a stale L1 line could show a node as its own root long after it was linked and make
+// the CAS loop spin until the line happens to be evicted.
+__device__ __forceinline__ int uf_find(int* parent, int i) {
   while (true) {
-    int p = parent[i];
+    int p = __ldcg(parent + i);
     if (p == i) return i;
-    int gp = parent[p];
-    if (gp != p) parent[i] = gp;
+    int gp = __ldcg(parent + p);
+    if (gp != p) parent[i] = gp;  // path halving: gp is an ancestor of i at every moment, so the store is always valid
     i = p;
   }
 }
 
-__device__ void uf_union(int* parent, int a, int b) {
+// links the roots of a and b (larger index under the smaller one) and returns the surviving root
+__device__ __forceinline__ int uf_union(int* parent, int a, int b) {
   while (true) {
     a = uf_find(parent, a), b = uf_find(parent, b);
-    if (a == b) return;
-    if (a < b) { int t = a; a = b; b = t; }  // link the larger root under the smaller one
+    if (a == b) return a;
+    if (a < b) { int t = a; a = b; b = t; }
     int old = atomicCAS(parent + a, a, b);
-    if (old == a) return;
+    if (old == a) return b;
   }
 }
 
+// Dense clusters make almost every neighbour pair redundant (both ends already hang under the same root), so each
+// lane keeps its current root in a register and skips a neighbour whose parent pointer already equals it: one load
+// per pair instead of two pointer chases and a CAS attempt.
 __global__ void k_union(const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
                         const int* __restrict__ cval_sorted, const Counts* __restrict__ cnt, double eps,
-                        const int* __restrict__ key_of, const int* __restrict__ core, int* __restrict__ parent) {
-  int U = cnt->n_unique;
-  int stride = gridDim.x * blockDim.x;
-  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += stride) {
-    if (!core[u]) continue;
-    for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, (unsigned int)key_of[u], eps, [&](int v) {
-      if (v < u && core[v]) uf_union(parent, u, v);
+                        const int* __restrict__ key_of, const int* __restrict__ core, int* parent) {
+  const int U = cnt->n_unique;
+  PCAB_GROUP_LOOP(u, ok, part, U) {
+    if (!ok || !core[u]) continue;
+    int ru = uf_find(parent, u);
+    for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, (unsigned int)key_of[u], eps, part, [&](int v) {
+      if (v < u && core[v]) {
+        int pv = __ldcg(parent + v);
+        if (pv != ru) ru = uf_union(parent, ru, pv);
+      }
     });
   }
 }
 
-__global__ void k_roots(const Counts* __restrict__ cnt, const int* __restrict__ core, int* __restrict__ parent,
+// parent[u] := root(u) for every core point.  Read-only walk (no path halving here: a halving store could land AFTER
+// another thread has finalised that entry and replace the root by an intermediate ancestor, which k_labels would then
+// read as a cluster id); concurrent finalising stores only ever shorten the walk.
+__global__ void k_roots(const Counts* __restrict__ cnt, const int* __restrict__ core, int* parent,
                         int* __restrict__ is_root, int cap) {
   int U = cnt->n_unique;
   int stride = gridDim.x * blockDim.x;
   for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < cap; u += stride) {
     int r = 0;
     if (u < U && core[u]) {
-      int root = uf_find(parent, u);
+      int root = u;
+      for (int p = __ldcg(parent + root); p != root; p = __ldcg(parent + root)) root = p;
       parent[u] = root;
       r = root == u;
     }
@@ -202,22 +243,21 @@ __global__ void k_labels(const float* __restrict__ pxy, const unsigned int* __re
                          const int* __restrict__ cval_sorted, Counts* cnt, double eps, const int* __restrict__ key_of,
                          const int* __restrict__ core, const int* __restrict__ parent, const int* __restrict__ root_rank,
                          const int* __restrict__ is_root, int cap, int* __restrict__ label, int* __restrict__ size) {
-  int U = cnt->n_unique;
-  int stride = gridDim.x * blockDim.x;
-  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += stride) {
-    int l = -1;
-    if (core[u]) {
-      l = root_rank[parent[u]];
-    } else {
-      int best = INT_MAX;
-      for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, (unsigned int)key_of[u], eps, [&](int v) {
+  const int U = cnt->n_unique;
+  PCAB_GROUP_LOOP(u, ok, part, U) {
+    int best = INT_MAX;
+    const bool is_core = ok && core[u];
+    if (ok && !is_core)
+      for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, (unsigned int)key_of[u], eps, part, [&](int v) {
         if (core[v]) best = min(best, root_rank[parent[v]]);
       });
-      if (best != INT_MAX) l = best;
+    best = group_min(best);
+    if (ok && part == 0) {
+      int l = is_core ? root_rank[parent[u]] : (best != INT_MAX ? best : -1);
+      label[u] = l;
+      if (l >= 0) atomicAdd(size + l, 1);
+      if (u == 0) cnt->n_clusters = root_rank[cap - 1] + is_root[cap - 1];
     }
-    label[u] = l;
-    if (l >= 0) atomicAdd(size + l, 1);
-    if (u == 0) cnt->n_clusters = root_rank[cap - 1] + is_root[cap - 1];
   }
 }
 
@@ -316,6 +356,7 @@ extern "C" int pcab_cluster_scene(const float* transformed_points, const float* 
 
   const int B = 256;
   int g = grid_for(s, B);
+  int g4 = grid_for((long long)s * kParts, B);
   k_init_counts<<<1, 1, 0, stream>>>(cnt);
   k_quant<<<g, B, 0, stream>>>(transformed_points, offset, sel, n0, s, dedupe_voxel, q, c, cnt);
   k_hash<<<g, B, 0, stream>>>(c, s, cnt, key, val);
@@ -325,12 +366,12 @@ extern "C" int pcab_cluster_scene(const float* transformed_points, const float* 
   k_unique<<<g, B, 0, stream>>>(head, rank, val_s, q, s, pxy, inverse, cnt);
   k_cellkeys<<<g, B, 0, stream>>>(pxy, cnt, dedupe_voxel, (float)eps * 1.001f, s, ckey, cval);
   PCAB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, sort32, ckey, ckey_s, cval, cval_s, s, 0, 32, stream));
-  k_core<<<g, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, min_samples, key_of, core, parent);
-  k_union<<<g, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, key_of, core, parent);
+  k_core<<<g4, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, min_samples, key_of, core, parent);
+  k_union<<<g4, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, key_of, core, parent);
   k_roots<<<g, B, 0, stream>>>(cnt, core, parent, is_root, s);
   PCAB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, scan, is_root, root_rank, s, stream));
   PCAB_CUDA(cudaMemsetAsync(size, 0, (size_t)s * 4, stream));
-  k_labels<<<g, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, key_of, core, parent, root_rank, is_root, s, label, size);
+  k_labels<<<g4, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, key_of, core, parent, root_rank, is_root, s, label, size);
   k_keep<<<g, B, 0, stream>>>(size, cnt, min_p_cluster, s, keep);
   PCAB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, scan, keep, keep_rank, s, stream));
   k_final<<<g, B, 0, stream>>>(label, keep, keep_rank, inverse, sel, n0, s, s, cnt, inst_out);

@@ -151,65 +151,102 @@ __global__ void __launch_bounds__((TH * TW / 4) * (COT / 16)) k_conv3x3(ConvArgs
 }
 
 // ConvTranspose2d(kernel 2, stride 2): out[n, 2y+dy, 2x+dx, co] = b[co] + sum_ci in[n,y,x,ci] * W[dy*2+dx][ci][co]
-// Thread tile: 1 input pixel x 4 taps x 8 couts; CTA: 64 pixels x 32 couts, 256 threads.
-__global__ void __launch_bounds__(256) k_convT2x2(const float* __restrict__ in, const float* __restrict__ w,
-                                                  const float* __restrict__ bias, float* __restrict__ out, int npix_in,
-                                                  int H, int W, int Cin, int Cout, int out_cstride, int out_coff) {
-  __shared__ float s_in[64][CK + 1];
-  __shared__ float s_w[4][CK][32];
+// = a GEMM [pixels x Cin] . [Cin x (4 taps x Cout)] with a scattered store.  CTA: 128 threads own 64 input pixels x
+// (4 taps x 32 couts); thread tile 8 pixels x 8 outputs (two float4 groups = two taps x 4 couts), 16 FMAs per 128-bit
+// shared-memory load.  The activation chunk is transposed to channel-major on its way into shared memory (through
+// registers, loaded one chunk ahead); the weight chunk streams in with cp.async, double-buffered.  Each output is one
+// fmaf chain over ascending ci, then + bias.
+constexpr int TK = 32;              // input channels per chunk
+constexpr int TLD = 64 + 4;         // row stride of the transposed activation chunk
+__global__ void __launch_bounds__(128, 3) k_convT2x2(const float* __restrict__ in, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, float* __restrict__ out, int npix_in,
+                                                     int H, int W, int Cin, int Cout, int out_cstride, int out_coff) {
+  extern __shared__ __align__(16) float s_dyn[];
+  float(*s_a)[TK * TLD] = reinterpret_cast<float(*)[TK * TLD]>(s_dyn);                  // [2][TK*TLD]
+  float(*s_b)[TK * 128] = reinterpret_cast<float(*)[TK * 128]>(s_dyn + 2 * TK * TLD);  // [2][TK*128]
   const int tid = threadIdx.x;
-  const int pl = tid & 63, cg = tid >> 6;  // 4 cout groups of 8
+  const int tr = tid >> 4, tc = tid & 15;
   const int p0 = blockIdx.x * 64;
   const int co0 = blockIdx.y * 32;
-  float acc[4][8];
+  const int nch = Cin / TK;
+  float acc[8][8];
 #pragma unroll
-  for (int t = 0; t < 4; ++t)
+  for (int o = 0; o < 8; ++o)
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[t][o] = 0.f;
-  for (int c0 = 0; c0 < Cin; c0 += CK) {
-    __syncthreads();
-    for (int e = tid; e < 64 * CK; e += 256) {
-      int k = e % CK, p = e / CK;
-      s_in[p][k] = (p0 + p < npix_in) ? in[(size_t)(p0 + p) * Cin + c0 + k] : 0.f;
+    for (int p = 0; p < 8; ++p) acc[o][p] = 0.f;
+
+  // activation chunk: 64 px x 32 ch = 512 float4, four per thread (px = e / 8, k4 = e % 8)
+  float4 areg[4];
+  auto load_a = [&](int ch) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 128 * i, px = e >> 3, k4 = e & 7;
+      areg[i] = (p0 + px < npix_in) ? *reinterpret_cast<const float4*>(in + (size_t)(p0 + px) * Cin + ch * TK + 4 * k4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int e = tid; e < 4 * CK * 32; e += 256) {
-      int o = e % 32, k = (e / 32) % CK, t = e / (32 * CK);
-      s_w[t][k][o] = (co0 + o < Cout) ? w[((size_t)t * Cin + c0 + k) * Cout + co0 + o] : 0.f;
+  };
+  auto store_a = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 128 * i, px = e >> 3, k4 = e & 7;
+      float* d = s_a[buf] + (4 * k4) * TLD + px;
+      d[0] = areg[i].x, d[TLD] = areg[i].y, d[2 * TLD] = areg[i].z, d[3 * TLD] = areg[i].w;
     }
-    __syncthreads();
+  };
+  // weight chunk: [k][tap*32 + co] <- w[(tap*Cin + ch*TK + k)*Cout + co0 + co]; 32 k x 4 taps x 8 float4
+  auto load_b = [&](int ch, int buf) {
+    for (int e = tid; e < TK * 32; e += 128) {
+      const int q = e & 7, t = (e >> 3) & 3, k = e >> 5;
+      const float* src = w + ((size_t)t * Cin + ch * TK + k) * Cout + co0 + 4 * q;
+      uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_b[buf] + k * 128 + t * 32 + 4 * q);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  load_a(0);
+  load_b(0, 0);
+  for (int ch = 0; ch < nch; ++ch) {
+    const int buf = ch & 1;
+    store_a(buf);
+    if (ch + 1 < nch) load_a(ch + 1);  // global loads of the next chunk fly during this chunk's FMAs
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // chunk ch is in shared memory; every thread has finished chunk ch-1 (its buffers are reused next)
+    if (ch + 1 < nch) load_b(ch + 1, buf ^ 1);
+    const float* A = s_a[buf];
+    const float* B = s_b[buf];
+#pragma unroll 4
+    for (int k = 0; k < TK; ++k) {
+      const float4 xa = *reinterpret_cast<const float4*>(A + k * TLD + tr * 8);
+      const float4 xb = *reinterpret_cast<const float4*>(A + k * TLD + tr * 8 + 4);
+      const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-    for (int k = 0; k < CK; ++k) {
-      float x = s_in[pl][k];
+      for (int g = 0; g < 2; ++g) {
+        const float4 wq = *reinterpret_cast<const float4*>(B + k * 128 + g * 64 + tc * 4);
+        const float wv[4] = {wq.x, wq.y, wq.z, wq.w};
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float4* w4 = reinterpret_cast<const float4*>(&s_w[t][k][cg * 8]);
-        float4 w0 = w4[0], w1 = w4[1];
-        acc[t][0] = fmaf(x, w0.x, acc[t][0]);
-        acc[t][1] = fmaf(x, w0.y, acc[t][1]);
-        acc[t][2] = fmaf(x, w0.z, acc[t][2]);
-        acc[t][3] = fmaf(x, w0.w, acc[t][3]);
-        acc[t][4] = fmaf(x, w1.x, acc[t][4]);
-        acc[t][5] = fmaf(x, w1.y, acc[t][5]);
-        acc[t][6] = fmaf(x, w1.z, acc[t][6]);
-        acc[t][7] = fmaf(x, w1.w, acc[t][7]);
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int p = 0; p < 8; ++p) acc[4 * g + u][p] = fmaf(xv[p], wv[u], acc[4 * g + u][p]);
       }
     }
   }
-  int p = p0 + pl;
-  if (p >= npix_in) return;
-  int n = p / (H * W), rem = p % (H * W), y = rem / W, x = rem % W;
-  int co = co0 + cg * 8;
-  if (co >= Cout) return;
+  // thread's outputs: pixels p0 + tr*8 .. +7; group g -> tap = 2g + tc/8, couts co0 + (tc%8)*4 .. +3
+  const int co = co0 + (tc & 7) * 4;
+  const float4 bq = *reinterpret_cast<const float4*>(bias + co);
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    int oy = 2 * y + (t >> 1), ox = 2 * x + (t & 1);
-    float* o = out + (((size_t)n * 2 * H + oy) * (2 * W) + ox) * out_cstride + out_coff + co;
-    float4 r0 = make_float4(acc[t][0] + bias[co], acc[t][1] + bias[co + 1], acc[t][2] + bias[co + 2],
-                            acc[t][3] + bias[co + 3]);
-    float4 r1 = make_float4(acc[t][4] + bias[co + 4], acc[t][5] + bias[co + 5], acc[t][6] + bias[co + 6],
-                            acc[t][7] + bias[co + 7]);
-    reinterpret_cast<float4*>(o)[0] = r0;
-    reinterpret_cast<float4*>(o)[1] = r1;
+  for (int p = 0; p < 8; ++p) {
+    const int pix = p0 + tr * 8 + p;
+    if (pix >= npix_in) continue;
+    const int n = pix / (H * W), rem = pix % (H * W), y = rem / W, x = rem % W;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int t = 2 * g + (tc >> 3);
+      const int oy = 2 * y + (t >> 1), ox = 2 * x + (t & 1);
+      float* o = out + (((size_t)n * 2 * H + oy) * (2 * W) + ox) * out_cstride + out_coff + co;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[4 * g][p] + bq.x, acc[4 * g + 1][p] + bq.y, acc[4 * g + 2][p] + bq.z,
+                                                  acc[4 * g + 3][p] + bq.w);
+    }
   }
 }
 
@@ -296,10 +333,19 @@ extern "C" int pcab_conv3x3_f32(const float* src0, int c0, const float* src1, in
 extern "C" int pcab_convT2x2_f32(const float* in, const float* weight_packed, const float* bias, float* out,
                                  int n_images, int H, int W, int Cin, int Cout, int out_cstride, int out_coff,
                                  cudaStream_t stream) {
-  PCAB_REQUIRE(Cin % 16 == 0 && Cout % 8 == 0, "Cin%16, Cout%8");
+  PCAB_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0, "Cin%32, Cout%32");
+  PCAB_REQUIRE(out_cstride % 4 == 0 && out_coff % 4 == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)in & 15) == 0 &&
+                   ((uintptr_t)weight_packed & 15) == 0 && ((uintptr_t)bias & 15) == 0,
+               "16B alignment of in / weights / bias / output channel layout");
   int npix = n_images * H * W;
-  dim3 grid(cdiv(npix, 64), cdiv(Cout, 32));
-  k_convT2x2<<<grid, 256, 0, stream>>>(in, weight_packed, bias, out, npix, H, W, Cin, Cout, out_cstride, out_coff);
+  dim3 grid(cdiv(npix, 64), Cout / 32);
+  const size_t smem = (size_t)(2 * TK * TLD + 2 * TK * 128) * sizeof(float);
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(k_convT2x2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cfg = true;
+  }
+  k_convT2x2<<<grid, 128, smem, stream>>>(in, weight_packed, bias, out, npix, H, W, Cin, Cout, out_cstride, out_coff);
   PCAB_CHECK_LAUNCH("pcab_convT2x2_f32");
   return PCAB_OK;
 }

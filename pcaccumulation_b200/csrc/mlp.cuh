@@ -1,83 +1,100 @@
-// Block-level dense layers for per-point MLPs: a CTA of 256 threads owns PTS = 64 rows whose
-// activations live in shared memory CHANNEL-MAJOR ([C][LDP], LDP = PTS + 4); weights stream through a shared-memory
-// k-chunk.  Thread tile is 4 rows x (OUT/16) contiguous outputs: per k one 128-bit activation load
-// (4 rows) and OUT/64 128-bit weight loads feed 4*OUT/16 FMAs.
+// Block-level dense layers for per-point MLPs: a CTA of NT = 128 threads owns PTS = 64 rows whose
+// activations live in shared memory CHANNEL-MAJOR ([C][LDP], LDP = PTS + 4); weights stream through a double-buffered
+// shared-memory k-chunk filled with cp.async (the next chunk lands while the current one is consumed).  Thread tile is
+// 8 rows x (OUT/16) outputs: per k two 128-bit activation loads (8 rows, warp-broadcast) and OUT/64 128-bit weight
+// loads (a quarter warp reads 128 contiguous bytes: conflict-free) feed 8*OUT/16 FMAs - 16 FMAs per shared-memory
+// load at OUT = 128, so the FP32 pipe, not the LSU, is the limiter.  Every output is one fmaf chain over ascending k
+// (then + bias), i.e. the same rounding sequence whatever the tiling.
 #pragma once
 #include "common.cuh"
 
 namespace mlp {
 
+constexpr int NT = 128;   // threads per CTA of every kernel built on block_dense
 constexpr int PTS = 64;
 constexpr int LDP = PTS + 4;  // row stride of the channel-major activation buffers (keeps float4 alignment, spreads banks)
 constexpr int KC = 32;  // weight rows staged per chunk
+constexpr int SW_FLOATS = 2 * KC * 128;  // shared scratch block_dense needs (two chunks of the widest layer)
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Y[OUT][PTS] = epilogue(W[IN][OUT]^T applied to X[IN][PTS] + b).  X, Y: shared memory, channel-major.
-// W is [in][out] row-major in global memory.  epilogue: optional BatchNorm(eval) scale/shift, optional ReLU.
-// s_w: shared scratch of KC*OUT floats.  All 256 threads must call.  X and Y must not alias.
+// W is [in][out] row-major in global memory (16 B aligned).  epilogue: optional BatchNorm(eval) scale/shift, optional
+// ReLU.  s_w: shared scratch of SW_FLOATS floats.  All NT threads must call.  X and Y must not alias.
 template <int IN, int OUT>
 __device__ __forceinline__ void block_dense(const float* X, const float* __restrict__ W, const float* __restrict__ b,
                                             const float* __restrict__ scale, const float* __restrict__ shift, bool relu,
                                             float* Y, float* s_w) {
-  constexpr int OPT = OUT / 16;
-  static_assert(OUT % 32 == 0, "OUT must be a multiple of 32");
+  constexpr int OPT = OUT / 16;         // outputs per thread: 8 (two float4 groups 64 apart), 4 (one float4) or 2 (float2)
+  constexpr int NG = OPT >= 4 ? OPT / 4 : 1;
+  constexpr int NCH = (IN + KC - 1) / KC;
+  static_assert(OUT == 32 || OUT == 64 || OUT == 128, "OUT must be 32, 64 or 128");
   const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
-  float acc[OPT][4];
+  float acc[OPT][8];
 #pragma unroll
   for (int o = 0; o < OPT; ++o)
 #pragma unroll
-    for (int p = 0; p < 4; ++p) acc[o][p] = 0.f;
-  for (int k0 = 0; k0 < IN; k0 += KC) {
+    for (int p = 0; p < 8; ++p) acc[o][p] = 0.f;
+  auto stage = [&](int ch) {
+    const int k0 = ch * KC;
     const int kc = (IN - k0) < KC ? (IN - k0) : KC;
-    __syncthreads();
-    for (int e = threadIdx.x; e < kc * OUT / 4; e += 256)
-      reinterpret_cast<float4*>(s_w)[e] = reinterpret_cast<const float4*>(W + (size_t)k0 * OUT)[e];
-    __syncthreads();
+    float* dst = s_w + (ch & 1) * KC * OUT;
+    const float* src = W + (size_t)k0 * OUT;
+    for (int e = threadIdx.x; e < kc * OUT / 4; e += NT) cp_async16(dst + 4 * e, src + 4 * e);
+    cp_async_commit();
+  };
+  stage(0);  // callers synchronise after writing X, and every block_* helper ends with a barrier: s_w is free here
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    cp_async_wait_all();
+    __syncthreads();  // chunk ch visible to everyone; everyone is done with chunk ch-1, whose buffer chunk ch+1 reuses
+    if (ch + 1 < NCH) stage(ch + 1);
+    const int k0 = ch * KC;
+    const int kc = (IN - k0) < KC ? (IN - k0) : KC;
+    const float* wbuf = s_w + (ch & 1) * KC * OUT;
 #pragma unroll 4
     for (int k = 0; k < kc; ++k) {
-      float4 x = *reinterpret_cast<const float4*>(X + (k0 + k) * LDP + tr * 4);
-      const float* wrow = s_w + k * OUT + tc * OPT;
-      if constexpr (OPT % 4 == 0) {
+      const float4 xa = *reinterpret_cast<const float4*>(X + (k0 + k) * LDP + tr * 8);
+      const float4 xb = *reinterpret_cast<const float4*>(X + (k0 + k) * LDP + tr * 8 + 4);
+      const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+      if constexpr (OPT >= 4) {
 #pragma unroll
-        for (int o4 = 0; o4 < OPT / 4; ++o4) {
-          float4 w = *reinterpret_cast<const float4*>(wrow + 4 * o4);
+        for (int g = 0; g < NG; ++g) {
+          const float4 w = *reinterpret_cast<const float4*>(wbuf + k * OUT + g * 64 + tc * 4);
           const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            acc[4 * o4 + u][0] = fmaf(x.x, wv[u], acc[4 * o4 + u][0]);
-            acc[4 * o4 + u][1] = fmaf(x.y, wv[u], acc[4 * o4 + u][1]);
-            acc[4 * o4 + u][2] = fmaf(x.z, wv[u], acc[4 * o4 + u][2]);
-            acc[4 * o4 + u][3] = fmaf(x.w, wv[u], acc[4 * o4 + u][3]);
-          }
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int p = 0; p < 8; ++p) acc[4 * g + u][p] = fmaf(xv[p], wv[u], acc[4 * g + u][p]);
         }
       } else {
+        const float2 w = *reinterpret_cast<const float2*>(wbuf + k * OUT + tc * 2);
 #pragma unroll
-        for (int o2 = 0; o2 < OPT / 2; ++o2) {
-          float2 w = *reinterpret_cast<const float2*>(wrow + 2 * o2);
-          acc[2 * o2][0] = fmaf(x.x, w.x, acc[2 * o2][0]);
-          acc[2 * o2][1] = fmaf(x.y, w.x, acc[2 * o2][1]);
-          acc[2 * o2][2] = fmaf(x.z, w.x, acc[2 * o2][2]);
-          acc[2 * o2][3] = fmaf(x.w, w.x, acc[2 * o2][3]);
-          acc[2 * o2 + 1][0] = fmaf(x.x, w.y, acc[2 * o2 + 1][0]);
-          acc[2 * o2 + 1][1] = fmaf(x.y, w.y, acc[2 * o2 + 1][1]);
-          acc[2 * o2 + 1][2] = fmaf(x.z, w.y, acc[2 * o2 + 1][2]);
-          acc[2 * o2 + 1][3] = fmaf(x.w, w.y, acc[2 * o2 + 1][3]);
+        for (int p = 0; p < 8; ++p) {
+          acc[0][p] = fmaf(xv[p], w.x, acc[0][p]);
+          acc[1][p] = fmaf(xv[p], w.y, acc[1][p]);
         }
       }
     }
   }
 #pragma unroll
   for (int o = 0; o < OPT; ++o) {
-    int c = tc * OPT + o;
+    const int c = OPT >= 4 ? (o >> 2) * 64 + tc * 4 + (o & 3) : tc * 2 + o;
     float bb = b ? b[c] : 0.f;
     float sc = scale ? scale[c] : 1.f, sh = scale ? shift[c] : 0.f;
-    float v[4];
+    float v[8];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
+    for (int p = 0; p < 8; ++p) {
       float t = acc[o][p] + bb;
       if (scale) t = fmaf(t, sc, sh);
       v[p] = relu ? fmaxf(t, 0.f) : t;
     }
-    *reinterpret_cast<float4*>(Y + c * LDP + tr * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(Y + c * LDP + tr * 8) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(Y + c * LDP + tr * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
   }
   __syncthreads();
 }
@@ -86,7 +103,7 @@ __device__ __forceinline__ void block_dense(const float* X, const float* __restr
 template <int IN, int OUT>
 __device__ __forceinline__ void block_dense_small(const float* X, const float* __restrict__ W,
                                                   const float* __restrict__ b, float* Y) {
-  for (int e = threadIdx.x; e < PTS * OUT; e += 256) {
+  for (int e = threadIdx.x; e < PTS * OUT; e += NT) {
     int p = e % PTS, o = e / PTS;
     float a = 0.f;
     for (int k = 0; k < IN; ++k) a = fmaf(X[k * LDP + p], W[(size_t)k * OUT + o], a);

@@ -96,22 +96,34 @@ __global__ void __launch_bounds__(128) k_pfn_stage0(const float* __restrict__ xy
   }
 }
 
-// pooled[m][c] = max over the pillar's points; one warp-lane per channel, one warp per pillar
+// pooled[m][c] = max over the pillar's points.  Eight lanes per pillar (one float4 of channels each), four pillars per
+// warp, rows of a pillar loaded two at a time: a pillar holds ~3 points, so the kernel is bound by the number of
+// independent loads in flight, not by arithmetic.
 __global__ void k_segmax32(const float* __restrict__ net, const int* __restrict__ pstart, int m,
                            float* __restrict__ pooled, const int* __restrict__ cell_of_pillar,
                            float* __restrict__ canvas) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  int nwarp = (gridDim.x * blockDim.x) >> 5;
-  for (int p = warp; p < m; p += nwarp) {
-    int s = pstart[p], e = pstart[p + 1];
-    float v = 0.f;  // torch_scatter leaves empty segments at 0
-    for (int j = s; j < e; ++j) {
-      float a = net[(size_t)j * 32 + lane];
-      v = (j == s) ? a : fmaxf(v, a);
+  const int sub = threadIdx.x & 7;
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int ngroup = (gridDim.x * blockDim.x) >> 3;
+  const float4* net4 = reinterpret_cast<const float4*>(net);
+  for (int p = group; p < m; p += ngroup) {
+    const int s = pstart[p], e = pstart[p + 1];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // torch_scatter leaves empty segments at 0
+    if (s < e) {
+      v = net4[(size_t)s * 8 + sub];
+      int j = s + 1;
+      for (; j + 1 < e; j += 2) {
+        const float4 a = net4[(size_t)j * 8 + sub], b = net4[(size_t)(j + 1) * 8 + sub];
+        v.x = fmaxf(v.x, fmaxf(a.x, b.x)), v.y = fmaxf(v.y, fmaxf(a.y, b.y));
+        v.z = fmaxf(v.z, fmaxf(a.z, b.z)), v.w = fmaxf(v.w, fmaxf(a.w, b.w));
+      }
+      if (j < e) {
+        const float4 a = net4[(size_t)j * 8 + sub];
+        v.x = fmaxf(v.x, a.x), v.y = fmaxf(v.y, a.y), v.z = fmaxf(v.z, a.z), v.w = fmaxf(v.w, a.w);
+      }
     }
-    pooled[(size_t)p * 32 + lane] = v;
-    if (canvas) canvas[(size_t)cell_of_pillar[p] * 32 + lane] = v;
+    reinterpret_cast<float4*>(pooled)[(size_t)p * 8 + sub] = v;
+    if (canvas) reinterpret_cast<float4*>(canvas)[(size_t)cell_of_pillar[p] * 8 + sub] = v;
   }
 }
 
@@ -203,7 +215,7 @@ extern "C" int pcab_pillar_encode(const float* xyz, const int* point_time, const
   g.n_frames = (float)n_sweeps;
   const int B = 128;
   int gp = grid_for(n_points, B, 8);
-  int gw = grid_for((long long)n_pillars * 32, 256, 8);
+  int gw = grid_for((long long)n_pillars * 8, 256, 8);
   size_t sm0 = (size_t)(kBlk0 + kBlkSize) * 4, sm1 = (size_t)kBlkSize * 4, sm2 = (size_t)(kBlkSize + 32 * 32 + 32) * 4;
   k_pfn_stage0<<<gp, B, sm0, stream>>>(xyz, point_time, order, p2v, coords_zyxt, pillar_mean, weight_pack, n_points, g,
                                        net_a);

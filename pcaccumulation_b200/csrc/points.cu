@@ -61,7 +61,7 @@ constexpr int S_O0W = S_M3B + 2 + 2 /*pad to 4*/, S_O0B = S_O0W + 128 * 128, S_O
 constexpr int S_O3W = S_O0T + 128, S_O3B = S_O3W + 128 * 2;
 constexpr int S_PACK = S_O3B + 2 + 2;
 
-__global__ void __launch_bounds__(256) k_stpn_head(const float* __restrict__ mos_feats /* [B,H,W,64] */, int H, int W,
+__global__ void __launch_bounds__(mlp::NT, 2) k_stpn_head(const float* __restrict__ mos_feats /* [B,H,W,64] */, int H, int W,
                                                    const float* __restrict__ tp, const int* __restrict__ pbatch,
                                                    const int* __restrict__ fg_idx, int k, const float* __restrict__ pk,
                                                    float x_abs, float y_abs, float* __restrict__ mos_out,
@@ -70,14 +70,14 @@ __global__ void __launch_bounds__(256) k_stpn_head(const float* __restrict__ mos
   float* E = sm;                  // [128][LDP]
   float* F = E + 128 * LDP;       // [128][LDP]
   float* G = E;                   // the hidden layer of the motion head reuses E (dead after final_proj)
-  float* s_w = F + 128 * LDP;     // [KC*128]
-  float* s_o = s_w + mlp::KC * 128;  // [4][LDP]
+  float* s_w = F + 128 * LDP;     // [SW_FLOATS]
+  float* s_o = s_w + mlp::SW_FLOATS;  // [4][LDP]
   __shared__ int s_idx[PTS];
   const int base = blockIdx.x * PTS;
   if (threadIdx.x < PTS) s_idx[threadIdx.x] = (base + threadIdx.x < k) ? fg_idx[base + threadIdx.x] : -1;
   __syncthreads();
   // inputs: pos = p / |x_min| (all three by x scale, models/stpn.py:94), channel-major into G[0..2]
-  for (int e = threadIdx.x; e < 3 * PTS; e += 256) {
+  for (int e = threadIdx.x; e < 3 * PTS; e += mlp::NT) {
     int c = e / PTS, p = e % PTS;
     int i = s_idx[p];
     G[c * LDP + p] = i >= 0 ? tp[3 * i + c] / x_abs : 0.f;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) k_stpn_head(const float* __restrict__ mos
   mlp::block_dense<3, 32>(G, pk + S_PE0W, pk + S_PE0B, nullptr, nullptr, true, F, s_w);
   mlp::block_dense<32, 64>(F, pk + S_PE2W, pk + S_PE2B, nullptr, nullptr, true, E, s_w);
   // bilinear pickup of the 64 motion-feature channels into E[64..127]
-  for (int e = threadIdx.x; e < PTS * 16; e += 256) {
+  for (int e = threadIdx.x; e < PTS * 16; e += mlp::NT) {
     int p = e / 16, q = e % 16;
     int i = s_idx[p];
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) k_stpn_head(const float* __restrict__ mos
   mlp::block_dense_small<128, 2>(G, pk + S_M3W, pk + S_M3B, s_o);
   mlp::block_dense<128, 128>(F, pk + S_O0W, pk + S_O0B, pk + S_O0S, pk + S_O0T, true, E, s_w);
   mlp::block_dense_small<128, 2>(E, pk + S_O3W, pk + S_O3B, s_o + 2 * LDP);
-  for (int e = threadIdx.x; e < PTS * 2; e += 256) {
+  for (int e = threadIdx.x; e < PTS * 2; e += mlp::NT) {
     int p = e % PTS, o = e / PTS;
     int i = s_idx[p];
     if (i < 0) continue;
@@ -146,13 +146,14 @@ __device__ void embed_and_max(float* A, float* Bf, float* s_w, const float* __re
   mlp::block_dense<H1, H2>(Bf, W1, b1, nullptr, nullptr, true, A, s_w);
   mlp::block_dense<H2, 128>(A, W2, b2, nullptr, nullptr, false, Bf, s_w);
   // points arrive sorted by segment, so a CTA sees a few runs: reduce each run in shared memory and issue ONE
-  // atomic per (run, channel).  Two threads per channel, each scanning half of the rows.
+  // atomic per (run, channel).  One thread per channel scans the rows.
   {
-    const int c = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int c = threadIdx.x;
+    static_assert(mlp::NT == 128, "one thread per output channel");
     const float* row = Bf + c * LDP;
     int cur_seg = -1;
     float cur = -INFINITY;
-    for (int p = half * (PTS / 2); p < (half + 1) * (PTS / 2); ++p) {
+    for (int p = 0; p < PTS; ++p) {
       int s = s_seg[p];
       if (s != cur_seg) {
         if (cur_seg >= 0) mlp::atomic_max_float(dst + (size_t)cur_seg * 128 + c, cur);
@@ -167,7 +168,7 @@ __device__ void embed_and_max(float* A, float* Bf, float* s_w, const float* __re
 }
 
 // motion (64->64->128->128) and geometry (32->32->64->128) embeddings, max-pooled per instance
-__global__ void __launch_bounds__(256) k_tpn_static_embed(const float* __restrict__ mos_feat,
+__global__ void __launch_bounds__(mlp::NT, 2) k_tpn_static_embed(const float* __restrict__ mos_feat,
                                                           const float* __restrict__ geo_feat,
                                                           const int* __restrict__ src_idx, const int* __restrict__ inst,
                                                           int n, const float* __restrict__ pk_motion,
@@ -185,13 +186,13 @@ __global__ void __launch_bounds__(256) k_tpn_static_embed(const float* __restric
     s_src[threadIdx.x] = j < n ? src_idx[j] : -1;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < PTS * 64; e += 256) {
+  for (int e = threadIdx.x; e < PTS * 64; e += mlp::NT) {
     int p = e / 64, c = e % 64;
     A[c * LDP + p] = s_src[p] >= 0 ? mos_feat[(size_t)s_src[p] * 64 + c] : 0.f;
   }
   __syncthreads();
   embed_and_max<64, 64, 128>(A, Bf, s_w, pk_motion, s_seg, mos_emb);
-  for (int e = threadIdx.x; e < PTS * 32; e += 256) {
+  for (int e = threadIdx.x; e < PTS * 32; e += mlp::NT) {
     int p = e / 32, c = e % 32;
     A[c * LDP + p] = s_src[p] >= 0 ? geo_feat[(size_t)s_src[p] * 32 + c] : 0.f;
   }
@@ -229,7 +230,7 @@ __global__ void k_tpn_frame_sums(const float* __restrict__ pts, const int* __res
 }
 
 // positional embedding of [p - anchor_centroid(inst), t/T] (4->32->64->128), max-pooled per (inst, frame)
-__global__ void __launch_bounds__(256) k_tpn_pos_embed(const float* __restrict__ pts, const int* __restrict__ inst,
+__global__ void __launch_bounds__(mlp::NT, 2) k_tpn_pos_embed(const float* __restrict__ pts, const int* __restrict__ inst,
                                                        const int* __restrict__ tidx, int n, int T,
                                                        const double* __restrict__ sums, const float* __restrict__ pk_pos,
                                                        float* __restrict__ frame_emb) {
@@ -508,13 +509,13 @@ extern "C" int pcab_stpn_head(const float* mos_feats_nhwc, int H, int W, const f
                               const int* point_batch, const int* fg_idx, int n_fg, const float* weight_pack,
                               float x_abs, float y_abs, float* mos_out, float* offset_out, cudaStream_t stream) {
   if (n_fg <= 0) return PCAB_OK;
-  size_t smem = (size_t)(2 * 128 * LDP + mlp::KC * 128 + 4 * LDP) * sizeof(float);
+  size_t smem = (size_t)(2 * 128 * LDP + mlp::SW_FLOATS + 4 * LDP) * sizeof(float);
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(k_stpn_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cfg = true;
   }
-  k_stpn_head<<<cdiv(n_fg, PTS), 256, smem, stream>>>(mos_feats_nhwc, H, W, transformed_points, point_batch, fg_idx,
+  k_stpn_head<<<cdiv(n_fg, PTS), mlp::NT, smem, stream>>>(mos_feats_nhwc, H, W, transformed_points, point_batch, fg_idx,
                                                       n_fg, weight_pack, x_abs, y_abs, mos_out, offset_out);
   PCAB_CHECK_LAUNCH("pcab_stpn_head");
   return PCAB_OK;
@@ -571,7 +572,7 @@ extern "C" int pcab_tpn_rows(const long long* inst, const long long* tidx, int n
 extern "C" int pcab_tpn_static_embed(const float* mos_feat, const float* geo_feat, const int* src_idx, const int* inst,
                                      int n, int K, const float* pack_motion, const float* pack_geo, float* mos_emb,
                                      float* geo_emb, cudaStream_t stream) {
-  size_t smem = (size_t)(2 * 128 * LDP + mlp::KC * 128) * sizeof(float);
+  size_t smem = (size_t)(2 * 128 * LDP + mlp::SW_FLOATS) * sizeof(float);
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(k_tpn_static_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -579,7 +580,7 @@ extern "C" int pcab_tpn_static_embed(const float* mos_feat, const float* geo_fea
   }
   k_fill<<<grid_for((long long)K * 128, 256), 256, 0, stream>>>(mos_emb, (long long)K * 128, -INFINITY);
   k_fill<<<grid_for((long long)K * 128, 256), 256, 0, stream>>>(geo_emb, (long long)K * 128, -INFINITY);
-  k_tpn_static_embed<<<cdiv(n, PTS), 256, smem, stream>>>(mos_feat, geo_feat, src_idx, inst, n, pack_motion, pack_geo,
+  k_tpn_static_embed<<<cdiv(n, PTS), mlp::NT, smem, stream>>>(mos_feat, geo_feat, src_idx, inst, n, pack_motion, pack_geo,
                                                           mos_emb, geo_emb);
   k_fix_neg_inf<<<grid_for((long long)K * 128, 256), 256, 0, stream>>>(mos_emb, (long long)K * 128);
   k_fix_neg_inf<<<grid_for((long long)K * 128, 256), 256, 0, stream>>>(geo_emb, (long long)K * 128);
@@ -614,7 +615,7 @@ extern "C" int pcab_tpn_iteration(const float* points, const int* inst, const in
   f += kt * 8;
   double* sums = (double*)((char*)workspace + al256p(kt * (128 + 512 + 256 + 128 + 8) * 4));
   PCAB_CUDA(cudaMemsetAsync(sums, 0, kt * 4 * 8, stream));
-  size_t smem = (size_t)(2 * 128 * LDP + mlp::KC * 128) * sizeof(float);
+  size_t smem = (size_t)(2 * 128 * LDP + mlp::SW_FLOATS) * sizeof(float);
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(k_tpn_pos_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -622,7 +623,7 @@ extern "C" int pcab_tpn_iteration(const float* points, const int* inst, const in
   }
   k_tpn_frame_sums<<<grid_for(n, 256), 256, 0, stream>>>(points, inst, tidx, T, n, sums);
   k_fill<<<grid_for((long long)kt * 128, 256), 256, 0, stream>>>(frame_emb, (long long)kt * 128, -INFINITY);
-  k_tpn_pos_embed<<<cdiv(n, PTS), 256, smem, stream>>>(points, inst, tidx, n, T, sums, pack_pos, frame_emb);
+  k_tpn_pos_embed<<<cdiv(n, PTS), mlp::NT, smem, stream>>>(points, inst, tidx, n, T, sums, pack_pos, frame_emb);
   k_fix_neg_inf<<<grid_for((long long)kt * 128, 256), 256, 0, stream>>>(frame_emb, (long long)kt * 128);
   k_tpn_regressor_input<<<grid_for((long long)kt * 512, 256), 256, 0, stream>>>(geo_emb, mos_emb, frame_emb, (int)kt, T, X);
   const float* W0 = pack_regressor;
