@@ -200,20 +200,40 @@ __device__ __forceinline__ int uf_union(int* parent, int a, int b) {
   }
 }
 
-// Dense clusters make almost every neighbour pair redundant (both ends already hang under the same root), so each
-// lane keeps its current root in a register and skips a neighbour whose parent pointer already equals it: one load
-// per pair instead of two pointer chases and a CAS attempt.
+// Hooking pass: every core point points at its lowest-index core neighbour (itself included).  Pointers only go to
+// smaller indices, so this is a forest; after k_roots has flattened it, a dense cluster consists of a handful of trees
+// (one per local index minimum) and k_union only has to stitch those together.
+__global__ void k_hook_min(const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
+                           const int* __restrict__ cval_sorted, const Counts* __restrict__ cnt, double eps,
+                           const int* __restrict__ key_of, const int* __restrict__ core, int* __restrict__ parent) {
+  const int U = cnt->n_unique;
+  PCAB_GROUP_LOOP(u, ok, part, U) {
+    int m = INT_MAX;
+    const bool is_core = ok && core[u];
+    if (is_core)
+      for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, (unsigned int)key_of[u], eps, part, [&](int v) {
+        if (core[v]) m = min(m, v);
+      });
+    m = group_min(m);
+    if (is_core && part == 0) parent[u] = min(m, u);
+  }
+}
+
+// Stitching pass over the flattened forest: a lane remembers the root its point started under (r0) and its current root
+// (ru) and skips every neighbour whose parent pointer equals either - one L2 load per pair.  Only pairs that straddle two
+// trees reach the union-find proper (two dependent pointer chases and a CAS attempt).
 __global__ void k_union(const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
                         const int* __restrict__ cval_sorted, const Counts* __restrict__ cnt, double eps,
                         const int* __restrict__ key_of, const int* __restrict__ core, int* parent) {
   const int U = cnt->n_unique;
   PCAB_GROUP_LOOP(u, ok, part, U) {
     if (!ok || !core[u]) continue;
-    int ru = uf_find(parent, u);
+    const int r0 = __ldcg(parent + u);
+    int ru = r0;
     for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, (unsigned int)key_of[u], eps, part, [&](int v) {
       if (v < u && core[v]) {
         int pv = __ldcg(parent + v);
-        if (pv != ru) ru = uf_union(parent, ru, pv);
+        if (pv != ru && pv != r0) ru = uf_union(parent, ru, pv);
       }
     });
   }
@@ -367,6 +387,8 @@ extern "C" int pcab_cluster_scene(const float* transformed_points, const float* 
   k_cellkeys<<<g, B, 0, stream>>>(pxy, cnt, dedupe_voxel, (float)eps * 1.001f, s, ckey, cval);
   PCAB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, sort32, ckey, ckey_s, cval, cval_s, s, 0, 32, stream));
   k_core<<<g4, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, min_samples, key_of, core, parent);
+  k_hook_min<<<g4, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, key_of, core, parent);
+  k_roots<<<g, B, 0, stream>>>(cnt, core, parent, is_root, s);  // flatten the hooking forest
   k_union<<<g4, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, key_of, core, parent);
   k_roots<<<g, B, 0, stream>>>(cnt, core, parent, is_root, s);
   PCAB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, scan, is_root, root_rank, s, stream));

@@ -21,40 +21,68 @@ constexpr int kBlkSize = 64 * 32 + 32 + 32 * 32 + 32 + 64 * 32;
 constexpr int kFcC = kBlk0 + 3 * kBlkSize;
 constexpr int kPackSize = kFcC + 32 * 32 + 32;
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tiled formulation.  A CTA of 128 threads owns tiles of PT = 128 pillar-sorted points (persistent: the stage's weights
+// are loaded into shared memory once per CTA).  Activations sit in shared memory channel-major ([C][LD]); a thread
+// computes 8 points x (OUT/8) outputs, so one 128-bit weight load feeds 32 FMAs and the FP32 pipe is the limiter (the
+// earlier thread-per-point kernels issued one broadcast weight load per 4 FMAs and were bound by the LSU).  Every
+// output is the same rounding sequence as before: accumulator initialised with the bias, one fmaf per input channel in
+// ascending order.
+// The segment max over a pillar's points is fused: points are sorted by pillar, so a tile holds a few runs; a run that
+// lies strictly inside one thread's scan range is written with a plain store, runs touching a range edge go through
+// atomic max (exact and order-independent for floats) into a buffer pre-filled with -inf.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PT = 128;       // points per tile
+constexpr int LD = PT + 4;    // channel-major row stride
+constexpr int NTP = 128;      // threads per CTA
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f)
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// acc[o][p]: thread (tr = tid>>3, tc = tid&7) owns points tr*8+p and outputs g*32 + 4*tc + u  (o = 4*g + u)
 template <int IN, int OUT, bool RELU_IN>
-__device__ __forceinline__ void dense(const float* __restrict__ W, const float* __restrict__ b, const float (&x)[IN],
-                                      float (&y)[OUT]) {
+__device__ __forceinline__ void tile_dense(const float* __restrict__ X, const float* __restrict__ W,
+                                           const float* __restrict__ b, float (&acc)[OUT / 8][8], int tr, int tc) {
+  constexpr int NG = OUT / 32;
 #pragma unroll
-  for (int o = 0; o < OUT; ++o) y[o] = b ? b[o] : 0.f;
+  for (int o = 0; o < OUT / 8; ++o) {
+    const float bb = b ? b[(o >> 2) * 32 + 4 * tc + (o & 3)] : 0.f;
 #pragma unroll
+    for (int p = 0; p < 8; ++p) acc[o][p] = bb;
+  }
+#pragma unroll 4
   for (int k = 0; k < IN; ++k) {
-    float xv = RELU_IN ? fmaxf(x[k], 0.f) : x[k];
-    const float4* w4 = reinterpret_cast<const float4*>(W + k * OUT);
+    const float4 xa = *reinterpret_cast<const float4*>(X + k * LD + tr * 8);
+    const float4 xb = *reinterpret_cast<const float4*>(X + k * LD + tr * 8 + 4);
+    float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    if (RELU_IN) {
 #pragma unroll
-    for (int o4 = 0; o4 < OUT / 4; ++o4) {
-      float4 w = w4[o4];
-      y[4 * o4 + 0] = fmaf(xv, w.x, y[4 * o4 + 0]);
-      y[4 * o4 + 1] = fmaf(xv, w.y, y[4 * o4 + 1]);
-      y[4 * o4 + 2] = fmaf(xv, w.z, y[4 * o4 + 2]);
-      y[4 * o4 + 3] = fmaf(xv, w.w, y[4 * o4 + 3]);
+      for (int p = 0; p < 8; ++p) xv[p] = fmaxf(xv[p], 0.f);
+    }
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const float4 w = *reinterpret_cast<const float4*>(W + k * OUT + g * 32 + 4 * tc);
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) acc[4 * g + u][p] = fmaf(xv[p], wv[u], acc[4 * g + u][p]);
     }
   }
 }
 
-// ResnetBlockFC 64 -> 32 (pre-activation; models/pillar_encoder.py:46-55)
-__device__ __forceinline__ void resblock(const float* __restrict__ Wb, const float (&x)[64], float (&out)[32]) {
-  const float* W0 = Wb;
-  const float* b0 = W0 + 64 * 32;
-  const float* W1 = b0 + 32;
-  const float* b1 = W1 + 32 * 32;
-  const float* Ws = b1 + 32;
-  float net[32];
-  dense<64, 32, true>(W0, b0, x, net);
-  float dx[32];
-  dense<32, 32, true>(W1, b1, net, dx);
-  dense<64, 32, false>(Ws, nullptr, x, out);
+template <int OUT>
+__device__ __forceinline__ void tile_store(float* __restrict__ Y, const float (&acc)[OUT / 8][8], int tr, int tc) {
 #pragma unroll
-  for (int o = 0; o < 32; ++o) out[o] += dx[o];
+  for (int o = 0; o < OUT / 8; ++o) {
+    float* y = Y + ((o >> 2) * 32 + 4 * tc + (o & 3)) * LD + tr * 8;
+    *reinterpret_cast<float4*>(y) = make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
+    *reinterpret_cast<float4*>(y + 4) = make_float4(acc[o][4], acc[o][5], acc[o][6], acc[o][7]);
+  }
 }
 
 struct PfnGeom {
@@ -62,106 +90,159 @@ struct PfnGeom {
   float scale, n_frames;
 };
 
-__global__ void __launch_bounds__(128) k_pfn_stage0(const float* __restrict__ xyz, const int* __restrict__ ptime,
-                                                    const int* __restrict__ order, const int* __restrict__ p2v,
-                                                    const int* __restrict__ coords, const float* __restrict__ pmean,
-                                                    const float* __restrict__ pack, int n, PfnGeom g,
-                                                    float* __restrict__ net_out) {
-  extern __shared__ float sw[];
-  for (int i = threadIdx.x; i < kBlk0 + kBlkSize; i += blockDim.x) sw[i] = pack[i];
-  __syncthreads();
-  int stride = gridDim.x * blockDim.x;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-    int i = order[j];
-    int m = p2v[i];
-    float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
-    float f[9];
-    f[0] = px, f[1] = py, f[2] = pz;
-    f[3] = __fsub_rn(px, pmean[3 * m]);
-    f[4] = __fsub_rn(py, pmean[3 * m + 1]);
-    f[5] = __fsub_rn(pz, pmean[3 * m + 2]);
-    int4 c = reinterpret_cast<const int4*>(coords)[m];  // z, y, x, t
-    f[6] = (float)((double)px - ((double)c.z * g.vx + g.x_off));
-    f[7] = (float)((double)py - ((double)c.y * g.vy + g.y_off));
+// STAGE 0: features -> fc_pos -> block 0;  STAGE 1: [net, pooled] -> block 1;  STAGE 2: [net, pooled] -> block 2 -> fc_c
+template <int STAGE>
+__global__ void __launch_bounds__(NTP, 2)
+k_pfn_tile(const float* __restrict__ xyz, const int* __restrict__ ptime, const int* __restrict__ order,
+           const int* __restrict__ p2v, const int* __restrict__ coords, const float* __restrict__ pmean,
+           const float* __restrict__ net_in, const float* __restrict__ pooled_in, const float* __restrict__ pack, int n,
+           PfnGeom g, float* __restrict__ net_out, float* __restrict__ pooled_out) {
+  extern __shared__ __align__(16) float sm[];
+  float* X = sm;                 // [64][LD]  block input; reused for the block output tile
+  float* NETs = X + 64 * LD;     // [32][LD]  relu(fc_0) ; stage 0: the 9 input features ; stage 2: fc_c output tile
+  float* Wb = NETs + 32 * LD;    // block weights (kBlkSize floats)
+  float* Wx = Wb + kBlkSize;     // stage 0: fc_pos W,b (640) ; stage 2: fc_c W,b (1056)
+  __shared__ int s_pil[PT];
+  const int tid = threadIdx.x, tr = tid >> 3, tc = tid & 7;
+  {
+    const float* src = pack + kBlk0 + STAGE * kBlkSize;
+    for (int i = tid; i < kBlkSize / 4; i += NTP) reinterpret_cast<float4*>(Wb)[i] = reinterpret_cast<const float4*>(src)[i];
+    if (STAGE == 0)
+      for (int i = tid; i < (9 * 64 + 64) / 4; i += NTP) reinterpret_cast<float4*>(Wx)[i] = reinterpret_cast<const float4*>(pack + kPosW)[i];
+    if (STAGE == 2)
+      for (int i = tid; i < (32 * 32 + 32) / 4; i += NTP) reinterpret_cast<float4*>(Wx)[i] = reinterpret_cast<const float4*>(pack + kFcC)[i];
+  }
+  const float* W0 = Wb;
+  const float* b0 = W0 + 64 * 32;
+  const float* W1 = b0 + 32;
+  const float* b1 = W1 + 32 * 32;
+  const float* Ws = b1 + 32;
+  const int ntiles = (n + PT - 1) / PT;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int j0 = tile * PT;
+    __syncthreads();  // previous tile fully consumed (and the weights are in place on the first pass)
+    {
+      const int j = j0 + tid;
+      const int i = j < n ? order[j] : -1;
+      const int m = i >= 0 ? p2v[i] : -1;
+      s_pil[tid] = m;
+      if (STAGE == 0) {
+        float f[9];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = __fdiv_rn(f[k], g.scale);
-    f[8] = __fdiv_rn((float)ptime[i], g.n_frames);
-    float x[64];
-    dense<9, 64, false>(sw + kPosW, sw + kPosB, f, x);
-    float out[32];
-    resblock(sw + kBlk0, x, out);
-    float4* dst = reinterpret_cast<float4*>(net_out + (size_t)j * 32);
+        for (int k = 0; k < 9; ++k) f[k] = 0.f;
+        if (i >= 0) {
+          const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+          f[0] = px, f[1] = py, f[2] = pz;
+          f[3] = __fsub_rn(px, pmean[3 * m]);
+          f[4] = __fsub_rn(py, pmean[3 * m + 1]);
+          f[5] = __fsub_rn(pz, pmean[3 * m + 2]);
+          const int4 c = reinterpret_cast<const int4*>(coords)[m];  // z, y, x, t
+          f[6] = (float)((double)px - ((double)c.z * g.vx + g.x_off));
+          f[7] = (float)((double)py - ((double)c.y * g.vy + g.y_off));
 #pragma unroll
-    for (int q = 0; q < 8; ++q) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+          for (int k = 0; k < 8; ++k) f[k] = __fdiv_rn(f[k], g.scale);
+          f[8] = __fdiv_rn((float)ptime[i], g.n_frames);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) NETs[k * LD + tid] = f[k];
+      } else {
+        // row tid of the tile: 32 channels of the previous block output, 32 channels of its pillar's pooled vector
+        const float4* a = reinterpret_cast<const float4*>(net_in + (size_t)(j < n ? j : 0) * 32);
+        const float4* b = reinterpret_cast<const float4*>(pooled_in + (size_t)(m >= 0 ? m : 0) * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 v = j < n ? a[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 u = j < n ? b[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+          X[(4 * q + 0) * LD + tid] = v.x, X[(4 * q + 1) * LD + tid] = v.y, X[(4 * q + 2) * LD + tid] = v.z, X[(4 * q + 3) * LD + tid] = v.w;
+          X[(32 + 4 * q + 0) * LD + tid] = u.x, X[(32 + 4 * q + 1) * LD + tid] = u.y, X[(32 + 4 * q + 2) * LD + tid] = u.z,
+                                X[(32 + 4 * q + 3) * LD + tid] = u.w;
+        }
+      }
+    }
+    __syncthreads();
+    if (STAGE == 0) {
+      float a64[8][8];
+      tile_dense<9, 64, false>(NETs, Wx, Wx + 9 * 64, a64, tr, tc);
+      tile_store<64>(X, a64, tr, tc);
+      __syncthreads();
+    }
+    float out[4][8];
+    {
+      float net[4][8];
+      tile_dense<64, 32, true>(X, W0, b0, net, tr, tc);
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) net[o][p] = fmaxf(net[o][p], 0.f);  // fc_1 consumes relu(net)
+      tile_store<32>(NETs, net, tr, tc);
+    }
+    tile_dense<64, 32, false>(X, Ws, nullptr, out, tr, tc);
+    __syncthreads();  // NETs complete; everyone is done reading X
+    {
+      float dx[4][8];
+      tile_dense<32, 32, false>(NETs, W1, b1, dx, tr, tc);
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) out[o][p] += dx[o][p];
+    }
+    float* R = X;  // result tile [32][LD]
+    if (STAGE == 2) {
+      tile_store<32>(X, out, tr, tc);
+      __syncthreads();
+      float y[4][8];
+      tile_dense<32, 32, false>(X, Wx, Wx + 32 * 32, y, tr, tc);
+      tile_store<32>(NETs, y, tr, tc);  // every thread finished reading NETs before the barrier above
+      R = NETs;
+    } else {
+      tile_store<32>(X, out, tr, tc);
+      // the next stage reads the block output row-major from HBM: 8 points x 16 B per thread, a 128 B row per 8 lanes
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int j = j0 + tr * 8 + p;
+        if (j < n) *reinterpret_cast<float4*>(net_out + (size_t)j * 32 + 4 * tc) = make_float4(out[0][p], out[1][p], out[2][p], out[3][p]);
+      }
+    }
+    __syncthreads();
+    // fused segment max: thread = channel c x quarter q of the tile's rows
+    {
+      const int c = tid & 31, r0 = (tid >> 5) * 32, r1 = r0 + 32;
+      const float* row = R + c * LD;
+      int cur = s_pil[r0], start = r0;
+      float v = -INFINITY;
+      for (int r = r0; r <= r1; ++r) {
+        const int pil = r < r1 ? s_pil[r] : -2;
+        if (pil != cur) {
+          if (cur >= 0) {
+            float* dst = pooled_out + (size_t)cur * 32 + c;
+            if (start > r0 && r < r1) *dst = v; else atomic_max_float(dst, v);
+          }
+          cur = pil, start = r, v = -INFINITY;
+        }
+        if (r < r1) v = fmaxf(v, row[r]);
+      }
+    }
   }
 }
 
-// pooled[m][c] = max over the pillar's points.  Eight lanes per pillar (one float4 of channels each), four pillars per
-// warp, rows of a pillar loaded two at a time: a pillar holds ~3 points, so the kernel is bound by the number of
-// independent loads in flight, not by arithmetic.
-__global__ void k_segmax32(const float* __restrict__ net, const int* __restrict__ pstart, int m,
-                           float* __restrict__ pooled, const int* __restrict__ cell_of_pillar,
-                           float* __restrict__ canvas) {
-  const int sub = threadIdx.x & 7;
-  const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  const int ngroup = (gridDim.x * blockDim.x) >> 3;
-  const float4* net4 = reinterpret_cast<const float4*>(net);
-  for (int p = group; p < m; p += ngroup) {
-    const int s = pstart[p], e = pstart[p + 1];
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // torch_scatter leaves empty segments at 0
-    if (s < e) {
-      v = net4[(size_t)s * 8 + sub];
-      int j = s + 1;
-      for (; j + 1 < e; j += 2) {
-        const float4 a = net4[(size_t)j * 8 + sub], b = net4[(size_t)(j + 1) * 8 + sub];
-        v.x = fmaxf(v.x, fmaxf(a.x, b.x)), v.y = fmaxf(v.y, fmaxf(a.y, b.y));
-        v.z = fmaxf(v.z, fmaxf(a.z, b.z)), v.w = fmaxf(v.w, fmaxf(a.w, b.w));
-      }
-      if (j < e) {
-        const float4 a = net4[(size_t)j * 8 + sub];
-        v.x = fmaxf(v.x, a.x), v.y = fmaxf(v.y, a.y), v.z = fmaxf(v.z, a.z), v.w = fmaxf(v.w, a.w);
-      }
-    }
-    reinterpret_cast<float4*>(pooled)[(size_t)p * 8 + sub] = v;
-    if (canvas) reinterpret_cast<float4*>(canvas)[(size_t)cell_of_pillar[p] * 8 + sub] = v;
-  }
+__global__ void k_fill_neg_inf(float4* __restrict__ a, long long n4) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  const float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) a[i] = v;
 }
 
-template <bool FINAL>
-__global__ void __launch_bounds__(128) k_pfn_block(const float* __restrict__ net_in, const float* __restrict__ pooled,
-                                                   const int* __restrict__ order, const int* __restrict__ p2v,
-                                                   const float* __restrict__ pack, int blk, int n,
-                                                   float* __restrict__ net_out) {
-  extern __shared__ float sw[];
-  const float* src = pack + kBlk0 + blk * kBlkSize;
-  for (int i = threadIdx.x; i < kBlkSize; i += blockDim.x) sw[i] = src[i];
-  if (FINAL)
-    for (int i = threadIdx.x; i < 32 * 32 + 32; i += blockDim.x) sw[kBlkSize + i] = pack[kFcC + i];
-  __syncthreads();
-  int stride = gridDim.x * blockDim.x;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-    int m = p2v[order[j]];
-    float x[64];
-    const float4* a = reinterpret_cast<const float4*>(net_in + (size_t)j * 32);
-    const float4* b = reinterpret_cast<const float4*>(pooled + (size_t)m * 32);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 v = a[q];
-      x[4 * q] = v.x, x[4 * q + 1] = v.y, x[4 * q + 2] = v.z, x[4 * q + 3] = v.w;
-      float4 u = b[q];
-      x[32 + 4 * q] = u.x, x[32 + 4 * q + 1] = u.y, x[32 + 4 * q + 2] = u.z, x[32 + 4 * q + 3] = u.w;
+// pillar features -> canvas cells (models/pillar_encoder.py:158-172); a pillar without points keeps 0 like torch_scatter
+__global__ void k_canvas_scatter(float4* __restrict__ feats, const int* __restrict__ cell_of_pillar, int m,
+                                 float4* __restrict__ canvas) {
+  long long total = (long long)m * 8, stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int p = (int)(e >> 3), q = (int)(e & 7);
+    float4 v = feats[e];
+    if (v.x == -INFINITY) {
+      v = make_float4(0.f, 0.f, 0.f, 0.f);
+      feats[e] = v;
     }
-    float out[32];
-    resblock(sw, x, out);
-    if (FINAL) {
-      float y[32];
-      dense<32, 32, false>(sw + kBlkSize, sw + kBlkSize + 32 * 32, out, y);
-#pragma unroll
-      for (int o = 0; o < 32; ++o) out[o] = y[o];
-    }
-    float4* dst = reinterpret_cast<float4*>(net_out + (size_t)j * 32);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+    canvas[(size_t)cell_of_pillar[p] * 8 + q] = v;
   }
 }
 
@@ -213,17 +294,30 @@ extern "C" int pcab_pillar_encode(const float* xyz, const int* point_time, const
   g.y_off = g.vy / 2 + (double)range6[1];
   g.scale = fabsf(range6[0]);
   g.n_frames = (float)n_sweeps;
-  const int B = 128;
-  int gp = grid_for(n_points, B, 8);
-  int gw = grid_for((long long)n_pillars * 8, 256, 8);
-  size_t sm0 = (size_t)(kBlk0 + kBlkSize) * 4, sm1 = (size_t)kBlkSize * 4, sm2 = (size_t)(kBlkSize + 32 * 32 + 32) * 4;
-  k_pfn_stage0<<<gp, B, sm0, stream>>>(xyz, point_time, order, p2v, coords_zyxt, pillar_mean, weight_pack, n_points, g,
-                                       net_a);
-  k_segmax32<<<gw, 256, 0, stream>>>(net_a, pstart, n_pillars, pooled, nullptr, nullptr);
-  k_pfn_block<false><<<gp, B, sm1, stream>>>(net_a, pooled, order, p2v, weight_pack, 1, n_points, net_b);
-  k_segmax32<<<gw, 256, 0, stream>>>(net_b, pstart, n_pillars, pooled, nullptr, nullptr);
-  k_pfn_block<true><<<gp, B, sm2, stream>>>(net_b, pooled, order, p2v, weight_pack, 2, n_points, net_a);
-  k_segmax32<<<gw, 256, 0, stream>>>(net_a, pstart, n_pillars, pillar_feats, pillar_cell, canvas_nhwc);
+  (void)pstart;  // the segment boundaries are recovered from the sorted pillar ids inside the tiles
+  const size_t smem = (size_t)(64 * LD + 32 * LD + kBlkSize + 1056) * sizeof(float);
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(k_pfn_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_pfn_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_pfn_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cfg = true;
+  }
+  const int ntiles = (n_points + PT - 1) / PT;
+  const int gp = ntiles < 2 * 148 ? ntiles : 2 * 148;  // persistent: two CTAs per SM
+  const long long pool4 = (long long)n_pillars * 8;
+  const int gf = grid_for(pool4, 256, 8);
+  // pooled vectors ping-pong between `pillar_feats` and the scratch array (each is re-filled with -inf before reuse)
+  k_fill_neg_inf<<<gf, 256, 0, stream>>>((float4*)pillar_feats, pool4);
+  k_pfn_tile<0><<<gp, NTP, smem, stream>>>(xyz, point_time, order, p2v, coords_zyxt, pillar_mean, nullptr, nullptr,
+                                           weight_pack, n_points, g, net_a, pillar_feats);
+  k_fill_neg_inf<<<gf, 256, 0, stream>>>((float4*)pooled, pool4);
+  k_pfn_tile<1><<<gp, NTP, smem, stream>>>(xyz, point_time, order, p2v, coords_zyxt, pillar_mean, net_a, pillar_feats,
+                                           weight_pack, n_points, g, net_b, pooled);
+  k_fill_neg_inf<<<gf, 256, 0, stream>>>((float4*)pillar_feats, pool4);
+  k_pfn_tile<2><<<gp, NTP, smem, stream>>>(xyz, point_time, order, p2v, coords_zyxt, pillar_mean, net_b, pooled,
+                                           weight_pack, n_points, g, nullptr, pillar_feats);
+  k_canvas_scatter<<<gf, 256, 0, stream>>>((float4*)pillar_feats, pillar_cell, n_pillars, (float4*)canvas_nhwc);
   PCAB_CHECK_LAUNCH("pcab_pillar_encode");
   return PCAB_OK;
 }

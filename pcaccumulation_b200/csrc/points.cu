@@ -76,6 +76,27 @@ __global__ void __launch_bounds__(mlp::NT, 2) k_stpn_head(const float* __restric
   const int base = blockIdx.x * PTS;
   if (threadIdx.x < PTS) s_idx[threadIdx.x] = (base + threadIdx.x < k) ? fg_idx[base + threadIdx.x] : -1;
   __syncthreads();
+  // bilinear pickup of the 64 motion-feature channels into E[64..127] - first, with four iterations (16 independent
+  // 128-bit loads per thread) in flight: these are scattered L2 reads and nothing else in the kernel hides their latency
+#pragma unroll 4
+  for (int e = threadIdx.x; e < PTS * 16; e += mlp::NT) {
+    int p = e / 16, q = e % 16;
+    const bool valid = s_idx[p] >= 0;
+    const int i = valid ? s_idx[p] : s_idx[0];  // padding rows read a real point so the loads stay branch-free
+    mlp::Bilinear bl = mlp::bilinear_border(tp[3 * i], tp[3 * i + 1], x_abs, y_abs, H, W);
+    const float4* b4 = reinterpret_cast<const float4*>(mos_feats + (size_t)pbatch[i] * H * W * 64) + q;
+    float4 a = b4[(size_t)bl.o00 * 16], b = b4[(size_t)bl.o01 * 16], c = b4[(size_t)bl.o10 * 16], d = b4[(size_t)bl.o11 * 16];
+    float4 v;
+    v.x = fmaf(d.x, bl.w11, fmaf(c.x, bl.w10, fmaf(b.x, bl.w01, a.x * bl.w00)));
+    v.y = fmaf(d.y, bl.w11, fmaf(c.y, bl.w10, fmaf(b.y, bl.w01, a.y * bl.w00)));
+    v.z = fmaf(d.z, bl.w11, fmaf(c.z, bl.w10, fmaf(b.z, bl.w01, a.z * bl.w00)));
+    v.w = fmaf(d.w, bl.w11, fmaf(c.w, bl.w10, fmaf(b.w, bl.w01, a.w * bl.w00)));
+    if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+    E[(64 + 4 * q + 0) * LDP + p] = v.x;
+    E[(64 + 4 * q + 1) * LDP + p] = v.y;
+    E[(64 + 4 * q + 2) * LDP + p] = v.z;
+    E[(64 + 4 * q + 3) * LDP + p] = v.w;
+  }
   // inputs: pos = p / |x_min| (all three by x scale, models/stpn.py:94), channel-major into G[0..2]
   for (int e = threadIdx.x; e < 3 * PTS; e += mlp::NT) {
     int c = e / PTS, p = e % PTS;
@@ -85,26 +106,6 @@ __global__ void __launch_bounds__(mlp::NT, 2) k_stpn_head(const float* __restric
   __syncthreads();
   mlp::block_dense<3, 32>(G, pk + S_PE0W, pk + S_PE0B, nullptr, nullptr, true, F, s_w);
   mlp::block_dense<32, 64>(F, pk + S_PE2W, pk + S_PE2B, nullptr, nullptr, true, E, s_w);
-  // bilinear pickup of the 64 motion-feature channels into E[64..127]
-  for (int e = threadIdx.x; e < PTS * 16; e += mlp::NT) {
-    int p = e / 16, q = e % 16;
-    int i = s_idx[p];
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i >= 0) {
-      mlp::Bilinear bl = mlp::bilinear_border(tp[3 * i], tp[3 * i + 1], x_abs, y_abs, H, W);
-      const float4* b4 = reinterpret_cast<const float4*>(mos_feats + (size_t)pbatch[i] * H * W * 64) + q;
-      float4 a = b4[(size_t)bl.o00 * 16], b = b4[(size_t)bl.o01 * 16], c = b4[(size_t)bl.o10 * 16], d = b4[(size_t)bl.o11 * 16];
-      v.x = fmaf(d.x, bl.w11, fmaf(c.x, bl.w10, fmaf(b.x, bl.w01, a.x * bl.w00)));
-      v.y = fmaf(d.y, bl.w11, fmaf(c.y, bl.w10, fmaf(b.y, bl.w01, a.y * bl.w00)));
-      v.z = fmaf(d.z, bl.w11, fmaf(c.z, bl.w10, fmaf(b.z, bl.w01, a.z * bl.w00)));
-      v.w = fmaf(d.w, bl.w11, fmaf(c.w, bl.w10, fmaf(b.w, bl.w01, a.w * bl.w00)));
-    }
-    E[(64 + 4 * q + 0) * LDP + p] = v.x;
-    E[(64 + 4 * q + 1) * LDP + p] = v.y;
-    E[(64 + 4 * q + 2) * LDP + p] = v.z;
-    E[(64 + 4 * q + 3) * LDP + p] = v.w;
-  }
-  __syncthreads();
   mlp::block_dense<128, 128>(E, pk + S_FPW, pk + S_FPB, nullptr, nullptr, true, F, s_w);
   mlp::block_dense<128, 128>(F, pk + S_M0W, pk + S_M0B, pk + S_M0S, pk + S_M0T, true, G, s_w);
   mlp::block_dense_small<128, 2>(G, pk + S_M3W, pk + S_M3B, s_o);
