@@ -121,6 +121,15 @@ int pcab_init_point_outputs(int n_points, float* mos, float* offset, pcab_stream
 int pcab_stpn_head(const float* mos_feats_nhwc /* [B,H,W,64] */, int H, int W, const float* transformed_points,
                    const int* point_batch, const int* fg_idx, int n_fg, const float* weight_pack, float x_abs,
                    float y_abs, float* mos_out /* [N,2] */, float* offset_out /* [N,2] */, pcab_stream_t stream);
+/* the same head on the tensor cores (tcgen05, 3xTF32; csrc/mlp_tc.cu).  which = 0: floats of w1_tc = positional_encoding[2]
+ * as [hi 64 rows; lo 64 rows][32]; which = 1: floats of w_tc = [final_proj; mos_seg[0]; offset_head[0]] x [hi 128 rows; lo 128
+ * rows][128] (rows = output channels, K-major, hi = weight rounded to tf32, lo = weight - hi). */
+size_t pcab_stpn_head_tc_pack_floats(int which);
+int pcab_stpn_head_tc_set_stats(long long* device_counters /* 148*2*8 int64, or NULL */);
+int pcab_stpn_head_tc(const float* mos_feats_nhwc, int H, int W, const float* transformed_points, const int* point_batch,
+                      const int* fg_idx, int n_fg, const float* weight_pack_host /* HOST copy of the pcab_stpn_head pack */,
+                      const float* w1_tc, const float* w_tc,
+                      float x_abs, float y_abs, float* mos_out, float* offset_out, pcab_stream_t stream);
 
 /* ---- clustering: models/cluster.py:9-110 (sparse_quantize + sklearn DBSCAN + canonicalise) ---------------- */
 int pcab_dynamic_flags(const float* mos, int n0, int n, int* flags, pcab_stream_t stream);

@@ -1,0 +1,477 @@
+// Per-point MLPs on the 5th-generation tensor cores (tcgen05.mma kind::tf32, FP32 accumulators in TMEM, 3xTF32 error
+// compensation as in conv_tc.cu): the STPN point head of models/stpn.py:91-103 (positional encoding, bilinear pickup,
+// final_proj, mos_seg and offset_head).
+//
+// A CTA (one per SM, persistent) owns tiles of 128 foreground points = the 128 rows (M) of every MMA.  The activations
+// of a tile live in shared memory as the K-major, 128B-swizzled A operand: 4 "atoms" of [128 rows x 32 channels] per
+// plane, one plane with the FP32 values (the tensor core reads their upper 19 bits = a_hi) and one with the residuals
+// a_lo.  A layer y = act(W x + b) is
+//     D[:, 0:2N] = a_hi . [w_hi | w_lo]^T        (one N = 2*out MMA per 8 input channels)
+//     D[:, N:2N] += a_lo . w_hi^T                 (one N = out MMA)
+// and y = D[:, 0:N] + D[:, N:2N] (+ bias, BN, ReLU) is formed by the epilogue warps, which write it back IN PLACE as the
+// A operand of the next layer (the MMAs of the producing layer have completed by then).  Weights ([w_hi; w_lo] rows,
+// K-major, pre-split on the host) stream through a 3-stage TMA ring in 32-input-channel chunks.  mos_seg and offset_head
+// share their input, use the two halves of TMEM and are drained by different warps, so their 128 -> 2 projections are
+// register dot products in the epilogue and their hidden layers never exist in memory.
+//
+// Warp roles: 0-7 gather / positional encoding / epilogues (thread = one point x one half of the channels; TMEM lane
+// quadrant = warp % 4), 8 = weight producer (TMA), 9 = TMEM allocator + MMA issuer.
+#include <cuda.h>
+#include <cstring>
+#include <type_traits>
+#include "common.cuh"
+#include "mlp.cuh"
+#include "pcab200.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace pcab_tc;
+using namespace mlp::stpn_pack;
+
+constexpr int kNT = 320;
+constexpr uint32_t kAtom = 128 * 128;     // [128 rows][32 ch] fp32 = 16 KB
+constexpr uint32_t kPlane = 4 * kAtom;    // 128 channels
+constexpr uint32_t kWStage = 256 * 128;   // [w_hi 128 rows | w_lo 128 rows] x 32 input channels
+constexpr int kStages = 3;
+constexpr int kChunksPerTile = 13;        // pe2: 1, final_proj / mos0 / off0: 4 each
+constexpr size_t kSmemBytes = 1024 + 2 * (size_t)kPlane + kStages * (size_t)kWStage + 128 + 3 * 128 * 4;
+
+struct HeadArgs {
+  const float* mos_feats;
+  int H, W;
+  const float* tp;
+  const int* pbatch;
+  const int* fg_idx;
+  int n_fg;
+  float x_abs, y_abs;
+  float* mos_out;
+  float* off_out;
+  int n_tiles;
+  long long* stats;  // debug: per-CTA phase cycle counters (null = off)
+};
+
+// Small per-layer vectors (biases, BN affine, pe0, the two 128 -> 2 projections) travel as a kernel parameter: parameters
+// live in the constant bank, so with the fully unrolled epilogues they become c[0x0][..] operands of the FMAs - no loads at
+// all.  (The CTA's shared memory is full and with a 227 KB carve-out there is no L1 left to cache global loads.)
+struct HeadConsts {
+  float pe0w[96], pe0b[32], pe2b[64], fpb[128];
+  float hb[2][128], hs[2][128], ht[2][128], h3w[2][256], h3b[2][2];  // [0] = mos_seg, [1] = offset_head
+};
+
+__device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar, uint32_t cnt) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+// channels c..c+3 (c % 4 == 0) of row r, as the A operand expects them: value plane and residual plane
+__device__ __forceinline__ void put4(uint32_t a_hi, uint32_t a_lo, int r, int c, float x, float y, float z, float w) {
+  const uint32_t off = (uint32_t)(c >> 5) * kAtom + (uint32_t)r * 128u + (uint32_t)((((c & 31) >> 2) ^ (r & 7)) << 4);
+  sts128(a_hi + off, x, y, z, w);
+  sts128(a_lo + off, split_lo(x), split_lo(y), split_lo(z), split_lo(w));
+}
+
+__global__ void __launch_bounds__(kNT, 1)
+k_stpn_head_tc(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w, const HeadArgs a,
+               const __grid_constant__ HeadConsts k) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_hi = sbase, a_lo = sbase + kPlane, w0 = sbase + 2 * kPlane;
+  const uint32_t bars = w0 + kStages * kWStage;
+  const uint32_t bar_w_full = bars, bar_w_free = bars + 24, bar_a_ready = bars + 48, bar_acc_full = bars + 56,
+                 bar_acc_empty = bars + 72, tmem_slot = bars + 88;
+  const uint32_t s_px = bars + 128, s_py = s_px + 512, s_pb = s_py + 512;  // per-point x, y, batch of the tile being gathered
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) mbar_init(bar_w_full + 8 * i, 1), mbar_init(bar_w_free + 8 * i, 1);
+    mbar_init(bar_a_ready, 256);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_acc_full + 8 * i, 1), mbar_init(bar_acc_empty + 8 * i, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 8 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w1)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  if (warp == 8) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      int wg = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        for (int c = 0; c < kChunksPerTile; ++c, ++wg) {
+          const int ws = wg % kStages;
+          if (wg >= kStages) mbar_wait(bar_w_free + 8 * ws, ((wg / kStages) - 1) & 1);
+          const uint32_t dst = w0 + ws * kWStage, bar = bar_w_full + 8 * ws;
+          if (c == 0) {
+            mbar_expect_tx(bar, 128u * 128u);
+            tma_load_2d(&map_w1, dst, bar, 0, 0);  // pe2: [w_hi 64 rows; w_lo 64 rows] x 32
+          } else {
+            mbar_expect_tx(bar, kWStage);
+            tma_load_2d(&map_w, dst, bar, ((c - 1) & 3) * 32, ((c - 1) >> 2) * 256);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
+    const uint64_t desc_hi = (uint64_t)(64u | (1u << 14) | (2u << 29)) << 32;  // SBO 1024 B, version 1, SWIZZLE_128B
+    const uint32_t lbo = 1u << 16;
+    const uint32_t ah_base = lbo | ((a_hi & 0x3FFFF) >> 4), al_base = lbo | ((a_lo & 0x3FFFF) >> 4);
+    const uint32_t b_base = lbo | ((w0 & 0x3FFFF) >> 4);
+    int wg = 0, job = 0, ar = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      for (int j = 0; j < 4; ++j, ++job) {
+        const int buf = job & 1;
+        const int n = j == 0 ? 64 : 128, nchunks = j == 0 ? 1 : 4;
+        if (j < 3) {
+          mbar_wait(bar_a_ready, ar & 1);
+          ++ar;
+        }
+        if (job >= 2) mbar_wait(bar_acc_empty + 8 * buf, ((job >> 1) - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
+          const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * n) >> 3) << 17), idesc1 = idesc_base | ((uint32_t)(n >> 3) << 17);
+          for (int c = 0; c < nchunks; ++c) {
+            const int ws = (wg + c) % kStages;
+            mbar_wait(bar_w_full + 8 * ws, ((wg + c) / kStages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ah = ah_base + (uint32_t)c * (kAtom >> 4), al = al_base + (uint32_t)c * (kAtom >> 4);
+            const uint32_t b16 = b_base + (uint32_t)ws * (kWStage >> 4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t dah = desc_hi | (ah + 2u * kk), dal = desc_hi | (al + 2u * kk), db = desc_hi | (b16 + 2u * kk);
+              umma_tf32(tmem_d, dah, db, idesc2, (c | kk) ? 1u : 0u);  // [a_hi*w_hi | a_hi*w_lo]
+              umma_tf32(tmem_d + (uint32_t)n, dal, db, idesc1, 1u);    // += a_lo*w_hi into the second half
+            }
+            umma_commit(bar_w_free + 8 * ws);
+          }
+          umma_commit(bar_acc_full + 8 * buf);
+        }
+        __syncwarp();
+        wg += nchunks;
+      }
+    }
+  } else {
+    // ===================== gather, positional encoding, epilogues =====================
+    const int r = (warp & 3) * 32 + lane, h = warp >> 2;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const bool st_on = a.stats != nullptr && (threadIdx.x == 0 || threadIdx.x == 128);
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = st_on ? clock64() : 0;
+#define PCAB_PHASE(k)                      \
+  if (st_on) {                             \
+    const long long tnow = clock64();      \
+    ph[k] += tnow - tprev, tprev = tnow;   \
+  }
+    // Per-tile inputs are fetched one tile ahead: the point metadata goes through a small shared table, the bilinear
+    // pickup (work item = (point, 16-byte chunk): the 16 lanes of a point read whole 256 B pixel rows of the four taps,
+    // coalesced - a thread-per-point gather would send 16 B requests to 32 different lines per instruction and there is no
+    // L1 left to merge them) is combined into registers while the head MMAs of the previous tile run, and is written into
+    // the A planes once those MMAs have released them.
+    int i_cur = 0;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    bool valid = false;
+    float4 g[8];
+    auto prefetch = [&](int tile) {
+      const int base = tile * 128;
+      valid = base + r < a.n_fg;
+      i_cur = a.fg_idx[valid ? base + r : base];  // padding rows recompute the tile's first point (never stored)
+      px = a.tp[3 * i_cur], py = a.tp[3 * i_cur + 1], pz = a.tp[3 * i_cur + 2];
+      if (h == 0) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_px + 4u * r), "f"(px) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_py + 4u * r), "f"(py) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_pb + 4u * r), "r"(a.pbatch[i_cur]) : "memory");
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int ctid = (int)threadIdx.x;  // 0..255
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int e = it * 256 + ctid, p = e >> 4, q = e & 15;
+        float qx, qy;
+        int qb;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qx) : "r"(s_px + 4u * p));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qy) : "r"(s_py + 4u * p));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qb) : "r"(s_pb + 4u * p));
+        const mlp::Bilinear bl = mlp::bilinear_border(qx, qy, a.x_abs, a.y_abs, a.H, a.W);
+        const float4* b4 = reinterpret_cast<const float4*>(a.mos_feats + (size_t)qb * a.H * a.W * 64) + q;
+        const float4 t00 = b4[(size_t)bl.o00 * 16], t01 = b4[(size_t)bl.o01 * 16], t10 = b4[(size_t)bl.o10 * 16],
+                     t11 = b4[(size_t)bl.o11 * 16];
+        g[it].x = fmaf(t11.x, bl.w11, fmaf(t10.x, bl.w10, fmaf(t01.x, bl.w01, t00.x * bl.w00)));
+        g[it].y = fmaf(t11.y, bl.w11, fmaf(t10.y, bl.w10, fmaf(t01.y, bl.w01, t00.y * bl.w00)));
+        g[it].z = fmaf(t11.z, bl.w11, fmaf(t10.z, bl.w10, fmaf(t01.z, bl.w01, t00.z * bl.w00)));
+        g[it].w = fmaf(t11.w, bl.w11, fmaf(t10.w, bl.w10, fmaf(t01.w, bl.w01, t00.w * bl.w00)));
+      }
+    };
+    if ((int)blockIdx.x < a.n_tiles) prefetch(blockIdx.x);
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const int i = i_cur;
+      const bool valid_cur = valid;
+      // ---- gathered motion features of this tile -> A channels 64..127
+      {
+        const int ctid = (int)threadIdx.x;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int e = it * 256 + ctid, p = e >> 4, q = e & 15;
+          put4(a_hi, a_lo, p, 64 + 4 * q, g[it].x, g[it].y, g[it].z, g[it].w);
+        }
+      }
+      // ---- positional encoding layer 0 (3 -> 32, ReLU) on the CUDA cores: this thread's 16 hidden channels -> A channels 16h ..
+      {
+        const float p0 = px / a.x_abs, p1 = py / a.x_abs, p2 = pz / a.x_abs;  // all three by the x scale (models/stpn.py:94)
+        auto pe0 = [&](auto hc) {
+          constexpr int HH = decltype(hc)::value;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int c = HH * 16 + 4 * q + u;
+              float t = fmaf(p0, k.pe0w[c], 0.f);
+              t = fmaf(p1, k.pe0w[32 + c], t);
+              t = fmaf(p2, k.pe0w[64 + c], t);
+              v[u] = fmaxf(t + k.pe0b[c], 0.f);
+            }
+            put4(a_hi, a_lo, r, HH * 16 + 4 * q, v[0], v[1], v[2], v[3]);
+          }
+        };
+        if (h == 0) pe0(std::integral_constant<int, 0>{}); else pe0(std::integral_constant<int, 1>{});
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_a_ready);
+      PCAB_PHASE(0)
+
+      // ---- epilogue of pe2 (32 -> 64, ReLU): this thread's 32 outputs -> A channels 32h ..   (job 0: buffer 0, phase 0)
+      mbar_wait(bar_acc_full + 0, 0);
+      PCAB_PHASE(1)
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      {
+        const uint32_t tm = tmem_base + lane_addr;
+        auto epi = [&](auto hc) {
+          constexpr int HH = decltype(hc)::value;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            uint32_t vm[16], vc[16];
+            const int c0 = HH * 32 + b * 16;
+            tmem_ld16(tm + (uint32_t)c0, vm);
+            tmem_ld16(tm + (uint32_t)(64 + c0), vc);
+            tmem_ld_wait16(vm, vc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                v[u] = fmaxf((__uint_as_float(vm[4 * q + u]) + __uint_as_float(vc[4 * q + u])) + k.pe2b[c0 + 4 * q + u], 0.f);
+              put4(a_hi, a_lo, r, c0 + 4 * q, v[0], v[1], v[2], v[3]);
+            }
+          }
+        };
+        if (h == 0) epi(std::integral_constant<int, 0>{}); else epi(std::integral_constant<int, 1>{});
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 0);
+      mbar_arrive(bar_a_ready);
+      PCAB_PHASE(2)
+
+      // ---- epilogue of final_proj (128 -> 128, ReLU): this thread's 64 outputs -> A channels 64h ..  (job 1: buffer 1, phase 0)
+      mbar_wait(bar_acc_full + 8, 0);
+      PCAB_PHASE(3)
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      {
+        const uint32_t tm = tmem_base + lane_addr + 256u;
+        auto epi = [&](auto hc) {
+          constexpr int HH = decltype(hc)::value;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            uint32_t vm[16], vc[16];
+            const int c0 = HH * 64 + b * 16;
+            tmem_ld16(tm + (uint32_t)c0, vm);
+            tmem_ld16(tm + (uint32_t)(128 + c0), vc);
+            tmem_ld_wait16(vm, vc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                v[u] = fmaxf((__uint_as_float(vm[4 * q + u]) + __uint_as_float(vc[4 * q + u])) + k.fpb[c0 + 4 * q + u], 0.f);
+              put4(a_hi, a_lo, r, c0 + 4 * q, v[0], v[1], v[2], v[3]);
+            }
+          }
+        };
+        if (h == 0) epi(std::integral_constant<int, 0>{}); else epi(std::integral_constant<int, 1>{});
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8);
+      mbar_arrive(bar_a_ready);
+      PCAB_PHASE(4)
+      if (tile + (int)gridDim.x < a.n_tiles) prefetch(tile + gridDim.x);  // flies while the head MMAs run
+
+      // ---- heads: warps 0-3 drain mos0 (job 2: buffer 0, phase 1), warps 4-7 drain off0 (job 3: buffer 1, phase 1).
+      // hidden = ReLU(BN(W x + b)); out = W3 hidden + b3 as a register dot product over the 128 hidden channels.
+      {
+        mbar_wait(bar_acc_full + 8 * h, 1);
+        PCAB_PHASE(5)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tm = tmem_base + lane_addr + (uint32_t)(h * 256);
+        float o0 = 0.f, o1 = 0.f;
+        auto epi = [&](auto hc) {
+          constexpr int HH = decltype(hc)::value;
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            uint32_t vm[16], vc[16];
+            const int c0 = b * 16;
+            tmem_ld16(tm + (uint32_t)c0, vm);
+            tmem_ld16(tm + (uint32_t)(128 + c0), vc);
+            tmem_ld_wait16(vm, vc);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int c = c0 + u;
+              const float g = fmaxf(fmaf((__uint_as_float(vm[u]) + __uint_as_float(vc[u])) + k.hb[HH][c], k.hs[HH][c], k.ht[HH][c]), 0.f);
+              o0 = fmaf(g, k.h3w[HH][2 * c], o0), o1 = fmaf(g, k.h3w[HH][2 * c + 1], o1);
+            }
+          }
+          o0 += k.h3b[HH][0], o1 += k.h3b[HH][1];
+        };
+        if (h == 0) epi(std::integral_constant<int, 0>{}); else epi(std::integral_constant<int, 1>{});
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cnt(bar_acc_empty + 8 * h, 2);
+        if (valid_cur) {
+          if (h == 0) {
+            *reinterpret_cast<float2*>(a.mos_out + 2 * (size_t)i) = make_float2(o0, o1);
+          } else {
+            if (isnan(o0) || isinf(o0)) o0 = 0.f;  // safe_guard_offset (models/stpn.py:61-65)
+            if (isnan(o1) || isinf(o1)) o1 = 0.f;
+            *reinterpret_cast<float2*>(a.off_out + 2 * (size_t)i) =
+                make_float2(fminf(fmaxf(o0, -20.f), 20.f), fminf(fmaxf(o1, -20.f), 20.f));
+          }
+        }
+        // the next tile overwrites the A planes: off0's MMAs (job 3) must have finished reading them
+        PCAB_PHASE(6)
+        if (h == 0) mbar_wait(bar_acc_full + 8, 1);
+        PCAB_PHASE(7)
+      }
+    }
+    if (st_on) {
+      long long* sp = a.stats + (blockIdx.x * 2 + h) * 8;
+      for (int k = 0; k < 8; ++k) sp[k] += ph[k];
+    }
+#undef PCAB_PHASE
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 9) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int encode_weights(EncodeTiledFn enc, CUtensorMap* map, const float* w, int rows, int K, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    pcab_set_error("mlp_tc: cuTensorMapEncodeTiled failed: %d", (int)r);
+    return PCAB_ERR_CUDA;
+  }
+  return PCAB_OK;
+}
+
+long long* g_head_stats = nullptr;
+
+}  // namespace
+
+// debug: device buffer of 148*2*8 int64 phase-cycle counters filled by k_stpn_head_tc (null = off).  Per CTA and head half:
+// gather+pe0, wait pe2, pe2 epilogue, wait final_proj, its epilogue, wait head MMA, head epilogue, wait for the last MMA.
+extern "C" int pcab_stpn_head_tc_set_stats(long long* device_counters) {
+  g_head_stats = device_counters;
+  return 0;
+}
+
+// floats in the tensor-core weight packs of the STPN head: pe2 [hi 64 rows; lo 64 rows][32] and
+// [final_proj, mos0, off0] x [hi 128 rows; lo 128 rows][128]   (rows = output channels, K-major)
+extern "C" size_t pcab_stpn_head_tc_pack_floats(int which) { return which == 0 ? (size_t)128 * 32 : (size_t)3 * 256 * 128; }
+
+// Same contract as pcab_stpn_head (points.cu), except that the FP32 pack of that entry point is passed as a HOST pointer
+// (biases, BN, pe0 and the two 128 -> 2 projections are copied from it into the kernel's parameter block); `w1_tc` / `w_tc`
+// are the pre-split K-major device matrices described above.
+extern "C" int pcab_stpn_head_tc(const float* mos_feats_nhwc, int H, int W, const float* transformed_points,
+                                 const int* point_batch, const int* fg_idx, int n_fg, const float* weight_pack_host,
+                                 const float* w1_tc, const float* w_tc, float x_abs, float y_abs, float* mos_out,
+                                 float* offset_out, cudaStream_t stream) {
+  if (n_fg <= 0) return PCAB_OK;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    pcab_set_error("pcab_stpn_head_tc: cuTensorMapEncodeTiled unavailable");
+    return PCAB_ERR_CUDA;
+  }
+  PCAB_REQUIRE(weight_pack_host != nullptr && ((uintptr_t)w1_tc & 15) == 0 && ((uintptr_t)w_tc & 15) == 0 &&
+                   ((uintptr_t)mos_feats_nhwc & 15) == 0 && ((uintptr_t)mos_out & 7) == 0 && ((uintptr_t)offset_out & 7) == 0,
+               "alignment of the weight packs / feature map / outputs");
+  CUtensorMap m1, m2;
+  int rc = encode_weights(enc, &m1, w1_tc, 128, 32, 128);
+  if (rc != PCAB_OK) return rc;
+  rc = encode_weights(enc, &m2, w_tc, 3 * 256, 128, 256);
+  if (rc != PCAB_OK) return rc;
+  HeadArgs a;
+  a.mos_feats = mos_feats_nhwc, a.H = H, a.W = W, a.tp = transformed_points, a.pbatch = point_batch, a.fg_idx = fg_idx;
+  a.n_fg = n_fg, a.x_abs = x_abs, a.y_abs = y_abs, a.mos_out = mos_out, a.off_out = offset_out;
+  a.n_tiles = cdiv(n_fg, 128);
+  a.stats = g_head_stats;
+  static bool configured = false;
+  if (!configured) {
+    PCAB_CUDA(cudaFuncSetAttribute(k_stpn_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    configured = true;
+  }
+  HeadConsts k;
+  const float* pk = weight_pack_host;
+  memcpy(k.pe0w, pk + S_PE0W, sizeof(k.pe0w)), memcpy(k.pe0b, pk + S_PE0B, sizeof(k.pe0b));
+  memcpy(k.pe2b, pk + S_PE2B, sizeof(k.pe2b)), memcpy(k.fpb, pk + S_FPB, sizeof(k.fpb));
+  const int hb[2] = {S_M0B, S_O0B}, hs[2] = {S_M0S, S_O0S}, ht[2] = {S_M0T, S_O0T}, h3w[2] = {S_M3W, S_O3W}, h3b[2] = {S_M3B, S_O3B};
+  for (int i = 0; i < 2; ++i) {
+    memcpy(k.hb[i], pk + hb[i], sizeof(k.hb[i])), memcpy(k.hs[i], pk + hs[i], sizeof(k.hs[i]));
+    memcpy(k.ht[i], pk + ht[i], sizeof(k.ht[i])), memcpy(k.h3w[i], pk + h3w[i], sizeof(k.h3w[i]));
+    memcpy(k.h3b[i], pk + h3b[i], sizeof(k.h3b[i]));
+  }
+  const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
+  k_stpn_head_tc<<<grid, kNT, kSmemBytes, stream>>>(m1, m2, a, k);
+  PCAB_CHECK_LAUNCH("pcab_stpn_head_tc");
+  return PCAB_OK;
+}

@@ -53,13 +53,7 @@ __global__ void k_ungrid(const float* __restrict__ feats, int C, int H, int W, c
 //   pe0 W[3][32] b[32] | pe2 W[32][64] b[64] | fp W[128][128] b[128] |
 //   mos0 W[128][128] b[128] s[128] t[128] | mos3 W[128][2] b[2] | off0 W,b,s,t | off3 W[128][2] b[2]
 // ---------------------------------------------------------------------------------------------
-constexpr int S_PE0W = 0, S_PE0B = S_PE0W + 3 * 32, S_PE2W = S_PE0B + 32, S_PE2B = S_PE2W + 32 * 64;
-constexpr int S_FPW = S_PE2B + 64, S_FPB = S_FPW + 128 * 128;
-constexpr int S_M0W = S_FPB + 128, S_M0B = S_M0W + 128 * 128, S_M0S = S_M0B + 128, S_M0T = S_M0S + 128;
-constexpr int S_M3W = S_M0T + 128, S_M3B = S_M3W + 128 * 2;
-constexpr int S_O0W = S_M3B + 2 + 2 /*pad to 4*/, S_O0B = S_O0W + 128 * 128, S_O0S = S_O0B + 128, S_O0T = S_O0S + 128;
-constexpr int S_O3W = S_O0T + 128, S_O3B = S_O3W + 128 * 2;
-constexpr int S_PACK = S_O3B + 2 + 2;
+using namespace mlp::stpn_pack;
 
 __global__ void __launch_bounds__(mlp::NT, 2) k_stpn_head(const float* __restrict__ mos_feats /* [B,H,W,64] */, int H, int W,
                                                    const float* __restrict__ tp, const int* __restrict__ pbatch,

@@ -284,6 +284,9 @@ class MotionNet(nn.Module):
             _t(ms[0].weight), _v(ms[0].bias), s_m, t_m, _t(ms[3].weight), _v(ms[3].bias), pad2,
             _t(os_[0].weight), _v(os_[0].bias), s_o, t_o, _t(os_[3].weight), _v(os_[3].bias), pad2]).contiguous()
         assert W["stpn_head"].numel() == L.lib().pcab_stpn_head_pack_size()
+        from .tc_pack import pack_stpn_head_tc
+        W["stpn_head_tc1"], W["stpn_head_tc"] = pack_stpn_head_tc(mh)
+        W["stpn_head_host"] = W["stpn_head"].cpu().contiguous()  # small vectors go into the kernel parameter block
         al = self.reconstructor.alignment
 
         def mlp_pack(seq):
@@ -517,8 +520,12 @@ class MotionNet(nn.Module):
             call("pcab_temporal_max", P(x), P(xm), I(B), I(T), I(Ny), I(Nx), I(32), stream())
             del x
             mos_feats = self._unet(W, "stpn.", xm, B, Ny, Nx, 5, False)
-            call("pcab_stpn_head", P(mos_feats), I(Ny), I(Nx), P(tp), P(pbatch), P(fg_idx), I(n_fg), P(W["stpn_head"]),
-                 F(x_abs), F(y_abs), P(full_mos), P(full_off), stream())
+            if self.use_tensor_cores:
+                call("pcab_stpn_head_tc", P(mos_feats), I(Ny), I(Nx), P(tp), P(pbatch), P(fg_idx), I(n_fg), P(W["stpn_head_host"]),
+                     P(W["stpn_head_tc1"]), P(W["stpn_head_tc"]), F(x_abs), F(y_abs), P(full_mos), P(full_off), stream())
+            else:
+                call("pcab_stpn_head", P(mos_feats), I(Ny), I(Nx), P(tp), P(pbatch), P(fg_idx), I(n_fg), P(W["stpn_head"]),
+                     F(x_abs), F(y_abs), P(full_mos), P(full_off), stream())
         if self.keep_stages:
             st.update(warped=warped, mos_feats=mos_feats)
         results["mos_est"], results["offset_est"] = full_mos, full_off

@@ -10,3 +10,19 @@ def pack_conv_tc(layer):
     hi = ((w.view(torch.int32) + 0x1000) & -8192).view(torch.float32)  # round the magnitude to the nearest tf32
     lo = w - hi
     return torch.cat((hi, lo), 0).contiguous()
+
+
+def split_tf32(w):
+    """w [rows, K] (K-major) -> [hi rows; lo rows]: hi = w rounded to the nearest tf32, lo = w - hi (exact in FP32)."""
+    w = w.detach().float().contiguous()
+    hi = ((w.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    return torch.cat((hi, w - hi), 0).contiguous()
+
+
+def pack_stpn_head_tc(mh):
+    """Tensor-core packs of the STPN point head (csrc/mlp_tc.cu): nn.Linear weights are [out, in] = K-major rows already.
+    Returns (pe2 [128, 32], [final_proj; mos0; off0] [768, 128])."""
+    w1 = split_tf32(mh.positional_encoding[2].weight)
+    w = torch.cat([split_tf32(mh.final_proj[0].weight), split_tf32(mh.mos_seg.seg_head[0].weight),
+                   split_tf32(mh.offset_head.seg_head[0].weight)], 0).contiguous()
+    return w1, w
