@@ -203,9 +203,11 @@ def main():
     sd = fixture.fixture_state_dict(model.state_dict(), 42)
     model.load_state_dict(sd)
     model.use_tensor_cores = not args.no_tc
-    pipe = ScenePipeline(cfg, sd, depth=max(1, args.in_flight), device=dev)
+    runner.warmup()
+    pipe = ScenePipeline(cfg, depth=max(1, args.in_flight), device=dev)
     for r in pipe.runners:
         r.model.use_tensor_cores = not args.no_tc
+    pipe.load_state_dict(sd)
     scenes = make_scenes(args.workload, rank, N_SCENES)
     host_pts = [torch.from_numpy(scene_to_points4(s)).pin_memory() for s in scenes]
     host_ego = [torch.from_numpy(s["ego_motion_gt"])[None].contiguous().pin_memory() for s in scenes]

@@ -197,6 +197,7 @@ class _ConvLayer:
         self.bn = _bn_affine(bn) if bn is not None else (None, None)
         self.weight = w  # for the tensor-core pack (built lazily)
         self.tc_pack = None
+        self.tc_ok = {}  # (H, W) -> does the tensor-core kernel take this layer at that map size
 
 
 class MotionNet(nn.Module):
@@ -222,6 +223,7 @@ class MotionNet(nn.Module):
         self.n_sweeps = cfg["voxel_generator"]["n_sweeps"]
         self._packed = None
         self._packed_key = None
+        self._plist = None
         self.use_tensor_cores = True
         self.stages = {}  # stage-boundary tensors of the last forward (for stage-wise parity tests)
         self.keep_stages = False
@@ -232,10 +234,23 @@ class MotionNet(nn.Module):
         self.stage_marks = None  # when a list: (name, cuda event) at stage boundaries (profiling aid)
         self.rng = None  # torch.Generator for the keypoint permutations (None = the global CPU generator, as upstream)
         self.conv_events = None  # when a list: (start_event, end_event, flops, path) per conv launch (bench roofline)
+        # The two convolution stacks (backbone UNet + FG/BG trunk; Conv3d + STPN UNet) are fixed launch sequences over fixed
+        # shapes: after one eager pass they are captured into CUDA graphs and replayed (2 graph launches instead of ~50 kernel
+        # launches from Python per scene).  Their inputs are persistent buffers; their outputs are rewritten by the next forward.
+        self.use_graphs = True
+        self._graphs = {}
 
     # ------------------------------------------------------------------------------------------
     def _pack_key(self):
-        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        # (storage, in-place version) of every parameter / buffer; the tensor list is cached (walking the module tree costs
+        # ~1 ms per forward) and rebuilt whenever the module is moved / cast (``_apply`` replaces the tensors)
+        if self._plist is None:
+            self._plist = list(self.parameters()) + list(self.buffers())
+        return tuple((p.data_ptr(), p._version) for p in self._plist)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._plist = None
+        return super()._apply(fn, *args, **kwargs)
 
     def _weights(self):
         key = self._pack_key()
@@ -305,6 +320,76 @@ class MotionNet(nn.Module):
         return W
 
     # ------------------------------------------------------------------------------------------
+    # CUDA-graph replay of fixed launch sequences
+    # ------------------------------------------------------------------------------------------
+    def _graph_input(self, key, shape, dev):
+        """Persistent input buffer of the graphed stack ``key`` (the producer writes into it every forward)."""
+        slot = self._graphs.get(key)
+        if slot is None:
+            slot = self._graphs[key] = {"in": torch.empty(*shape, device=dev, dtype=torch.float32), "graph": None, "out": None}
+        return slot["in"]
+
+    def _run_stack(self, key, fn, capture=False):
+        """outputs = fn(static_input): replay of the captured graph when there is one for the current weights, eager
+        otherwise.  Graphs are only captured by ``warmup()`` (stream capture while other host threads drive the same GPU
+        is fragile), never implicitly."""
+        slot = self._graphs[key]
+        if slot.get("key") is not self._packed_key:  # first use, or a new weight pack drops the capture
+            slot.update(graph=None, out=None, key=self._packed_key)
+        if not (self.use_graphs and self.conv_events is None):
+            return fn(slot["in"])
+        if slot["graph"] is not None:
+            slot["graph"].replay()
+            return slot["out"]
+        if not capture:
+            return fn(slot["in"])
+        fn(slot["in"])  # eager pass first: lazy weight packs, kernel attributes, allocator warm-up
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            with L.pinned_stream():  # the capture runs on a side stream
+                out = fn(slot["in"])
+        slot["graph"], slot["out"] = g, out
+        return out
+
+    def _backbone_stack(self, W, B, T, Ny, Nx):
+        def backbone(x):
+            feats = self._unet(W, "unet.", x, B * T, Ny, Nx, self.cfg["unet"]["depth"], True)
+            return feats, self._conv(W["sem0"], [feats], B * T, Ny, Nx, True)
+        return backbone
+
+    def _stpn_stack(self, W, B, T, Ny, Nx, dev):
+        def stpn_stack(x):
+            for j in range(4):
+                x = self._conv(W[f"stpn.c3d{j}"], [x], B * T, Ny, Nx, True, T=T)
+            xm = torch.empty(B, Ny, Nx, 32, device=dev)
+            call("pcab_temporal_max", P(x), P(xm), I(B), I(T), I(Ny), I(Nx), I(32), stream())
+            del x
+            return self._unet(W, "stpn.", xm, B, Ny, Nx, 5, False)
+        return stpn_stack
+
+    @torch.no_grad()
+    def warmup(self, batch_size=1):
+        """Capture the CUDA graphs of the two convolution stacks for ``batch_size`` scenes per forward (grid and sweep
+        count come from the config).  Call it from the thread that owns the model while no other thread is using the GPU
+        (``SceneRunner`` / ``ScenePipeline`` do); without it every forward launches the stacks kernel by kernel."""
+        if not self.use_graphs:
+            return
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise L.PcabError("warmup() needs the model on a CUDA device")
+        vg = self.cfg["voxel_generator"]
+        Nx = int(round((vg["range"][3] - vg["range"][0]) / vg["voxel_size"][0]))
+        Ny = int(round((vg["range"][4] - vg["range"][1]) / vg["voxel_size"][1]))
+        B, T, tc = int(batch_size), self.n_sweeps, self.use_tensor_cores
+        with L.pinned_stream():
+            W = self._weights()
+            for name, fn in (("backbone", self._backbone_stack(W, B, T, Ny, Nx)), ("stpn", self._stpn_stack(W, B, T, Ny, Nx, dev))):
+                key = (name, B, T, Ny, Nx, tc)
+                self._graph_input(key, (B * T, Ny, Nx, 32), dev).zero_()
+                self._run_stack(key, fn, capture=True)
+        torch.cuda.current_stream().synchronize()
+
+    # ------------------------------------------------------------------------------------------
     # convolution dispatch
     # ------------------------------------------------------------------------------------------
     def _conv(self, layer, srcs, n_img, H, W_, relu, out=None, T=1):
@@ -321,7 +406,13 @@ class MotionNet(nn.Module):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         path = "f32"
-        if self.use_tensor_cores and L.lib().pcab_conv3x3_tc_supported(I(len(layer.splits)), I(c[0]), I(c[1]), I(c[2]), I(layer.cout), I(H), I(W_)):
+        tc_ok = False
+        if self.use_tensor_cores:
+            tc_ok = layer.tc_ok.get((H, W_))
+            if tc_ok is None:
+                tc_ok = layer.tc_ok[(H, W_)] = bool(L.lib().pcab_conv3x3_tc_supported(
+                    I(len(layer.splits)), I(c[0]), I(c[1]), I(c[2]), I(layer.cout), I(H), I(W_)))
+        if tc_ok:
             if layer.tc_pack is None:
                 layer.tc_pack = self._pack_tc(layer)
             call("pcab_conv3x3_tc", P(s[0]), I(c[0]), P(s[1]), I(c[1]), P(s[2]), I(c[2]), I(T if layer.temporal else 1),
@@ -393,6 +484,10 @@ class MotionNet(nn.Module):
     @torch.no_grad()
     def forward(self, input_dict):
         """Same contract as ``models/motionnet.py:137-262`` (inference; gradients are round-2 work)."""
+        with L.pinned_stream():
+            return self._forward(input_dict)
+
+    def _forward(self, input_dict):
         W = self._weights()
         st = self.stages = {}
         self._deferred = []  # (keys, device tensor): python floats of the API are fetched with ONE sync at the end
@@ -453,7 +548,9 @@ class MotionNet(nn.Module):
 
         self._mark("index+stats")
         # 1. pillar encoder -> BEV canvas
-        canvas = torch.zeros(B * T, Ny, Nx, 32, device=dev)
+        tc = self.use_tensor_cores
+        canvas = self._graph_input(("backbone", B, T, Ny, Nx, tc), (B * T, Ny, Nx, 32), dev)
+        canvas.zero_()
         pillar_feats = torch.empty(M, 32, device=dev)
         ws = scratch(size("pcab_pillar_encode_workspace", I(N), I(M)), dev)
         call("pcab_pillar_encode", P(pts), P(ptime), P(order), P(p2v), P(pstart), P(coords_zyxt), P(pillar_cell),
@@ -463,11 +560,10 @@ class MotionNet(nn.Module):
 
         self._mark("pillar_encoder")
         # 2. UNet backbone
-        bev_feats = self._unet(W, "unet.", canvas, B * T, Ny, Nx, cfg["unet"]["depth"], True)
+        bev_feats, h = self._run_stack(("backbone", B, T, Ny, Nx, tc), self._backbone_stack(W, B, T, Ny, Nx))
 
         self._mark("unet")
         # 3. FG/BG head
-        h = self._conv(W["sem0"], [bev_feats], B * T, Ny, Nx, True)
         fb_seg = torch.empty(B, T, 2, Ny, Nx, device=dev)
         fb_est = torch.empty(B * T * HW, dtype=torch.int32, device=dev)
         call("pcab_head2_conv", P(h), I(32), P(W["sem3"][0]), P(W["sem3"][1]), I(B * T), I(Ny), I(Nx), P(fb_seg),
@@ -496,7 +592,7 @@ class MotionNet(nn.Module):
         pose_est = results["ego_motion_est"].float().contiguous()
         if "ego_motion_est" in self.inject:
             pose_est = self.inject["ego_motion_est"].to(dev).float().contiguous()
-        warped = torch.empty(B * T, Ny, Nx, 32, device=dev)
+        warped = self._graph_input(("stpn", B, T, Ny, Nx, tc), (B * T, Ny, Nx, 32), dev)
         call("pcab_warp_bev", P(bev_feats), P(pose_est), I(B), I(T), I(Ny), I(Nx), I(32), F(self.resolution[0]),
              F(self.resolution[1]), F(self.pc_range[0]), F(self.pc_range[1]), P(warped), stream())
         tp = torch.empty(N, 3, device=dev)
@@ -513,13 +609,7 @@ class MotionNet(nn.Module):
         call("pcab_init_point_outputs", I(N), P(full_mos), P(full_off), stream())
         mos_feats = None
         if n_fg > MIN_POINTS:
-            x = warped
-            for j in range(4):
-                x = self._conv(W[f"stpn.c3d{j}"], [x], B * T, Ny, Nx, True, T=T)
-            xm = torch.empty(B, Ny, Nx, 32, device=dev)
-            call("pcab_temporal_max", P(x), P(xm), I(B), I(T), I(Ny), I(Nx), I(32), stream())
-            del x
-            mos_feats = self._unet(W, "stpn.", xm, B, Ny, Nx, 5, False)
+            mos_feats = self._run_stack(("stpn", B, T, Ny, Nx, tc), self._stpn_stack(W, B, T, Ny, Nx, dev))
             if self.use_tensor_cores:
                 call("pcab_stpn_head_tc", P(mos_feats), I(Ny), I(Nx), P(tp), P(pbatch), P(fg_idx), I(n_fg), P(W["stpn_head_host"]),
                      P(W["stpn_head_tc1"]), P(W["stpn_head_tc"]), F(x_abs), F(y_abs), P(full_mos), P(full_off), stream())

@@ -68,6 +68,10 @@ class SceneRunner:
             d["point_to_voxel_map"] = v["point_to_voxel_map"].to(torch.int64)[:, None]
         return d
 
+    def warmup(self, batch_size=1):
+        """Capture the model's CUDA graphs (see ``MotionNet.warmup``); call after loading weights, before serving."""
+        self.model.warmup(batch_size)
+
     @torch.no_grad()
     def run_device(self, points4, num_points, **kw):
         return self.model(self.build_input(points4, num_points, **kw))
@@ -115,9 +119,11 @@ class ScenePipeline:
         self.depth = int(depth)
         self.runners = [SceneRunner(cfg, device=self.device) for _ in range(self.depth)]
         self._free = queue.SimpleQueue()
+        self._slots = []
         for r in self.runners:
             r.model.rng = torch.Generator()  # per-slot CPU generator: the global one would interleave between threads
-            self._free.put((r, torch.cuda.Stream(device=self.device)))
+            self._slots.append((r, torch.cuda.Stream(device=self.device)))
+            self._free.put(self._slots[-1])
         if state_dict is not None:
             self.load_state_dict(state_dict)
         # torch initialises its linear-algebra backend lazily and not thread-safely: touch it once from this thread
@@ -128,8 +134,11 @@ class ScenePipeline:
         self._pool = ThreadPoolExecutor(max_workers=self.depth, thread_name_prefix="pcab-scene")
 
     def load_state_dict(self, state_dict):
-        for r in self.runners:
+        """Load the weights into every slot and capture its CUDA graphs (single-threaded: the workers are idle)."""
+        for r, stream in self._slots:
             r.model.load_state_dict(state_dict)
+            with torch.cuda.stream(stream):
+                r.warmup()
 
     def _work(self, points4, num_points, ego, seed, out, host):
         runner, stream = self._free.get()

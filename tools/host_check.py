@@ -10,6 +10,7 @@ torch.set_num_threads(1)
 cfg = config.workload_config(name)
 runner = SceneRunner(cfg)
 runner.model.load_state_dict(fixture.fixture_state_dict(runner.model.state_dict(), 42))
+runner.warmup()
 s = synth.make_workload_scene(name, 0)
 p4 = torch.tensor(scene_to_points4(s)).cuda()
 for i in range(4):
