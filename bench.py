@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 from pcaccumulation_b200 import config, fixture, synth  # noqa: E402
 
 N_SCENES = 4  # distinct synthetic scenes cycled through the steps
+CONV_DRAM_BYTES_PER_LAUNCH = {"C2": 32.81e6}  # measured with ncu (profiles/r1_conv_dram.csv), see the roofline block below
 
 
 def env_int(name, default):
@@ -311,9 +312,10 @@ def main():
 
 
     # roofline of the convolution kernels (dominant): algorithmic FLOPs / event time
-    tot_flops = sum(f for _, _, f, _ in events)
-    tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in events)
-    paths = sorted(set(p for _, _, _, p in events))
+    tot_flops = sum(e[2] for e in events)
+    tot_ms = sum(e[0].elapsed_time(e[1]) for e in events)
+    tot_bytes = sum(e[4] for e in events)
+    paths = sorted(set(e[3] for e in events))
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -381,7 +383,13 @@ def main():
             "gpu_launches": (launches_per_step or 0) * args.steps,
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "kernel": "conv3x3 (all launches, %.0f per step)" % n_conv, "achieved": achieved,
-                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         # DRAM bytes per conv launch from profiles/r1_conv_dram.csv (ncu dram__bytes_read+write summed over
+                         # the 44 conv launches of one C2 step / 44; cold-cache replay, so an upper bound on the warm traffic)
+                         "traffic": CONV_DRAM_BYTES_PER_LAUNCH.get(args.workload),
+                         "algorithmic_bytes_per_launch": tot_bytes / max(len(events), 1),
+                         "algorithmic_flops_per_launch": tot_flops / max(len(events), 1),
+                         "peak_source": peak_src,
                          "conv_ms_per_step": tot_ms / max(args.steps, 1), "conv_share_of_step": tot_ms / ms_serial},
             "cpu_baseline": cpu_base,
             "parity_vs_oracle": epe,

@@ -429,7 +429,9 @@ class MotionNet(nn.Module):
                 taps = 9 * layer.splits[0] * (3 * T - 2) * (n_img // T)
             else:
                 taps = 9 * sum(layer.splits) * n_img
-            ev.append((e0, e1, 2.0 * taps * layer.cout * H * W_, path))
+            cin_read = (sum(layer.splits) if not layer.temporal else layer.splits[0]) * n_img
+            nbytes = 4.0 * H * W_ * (cin_read + layer.cout * n_img) + 4.0 * 9 * sum(layer.splits) * layer.cout
+            ev.append((e0, e1, 2.0 * taps * layer.cout * H * W_, path, nbytes))
         return out
 
     def _pack_tc(self, layer):

@@ -13,6 +13,7 @@ cfg = config.workload_config(name)
 runner = SceneRunner(cfg)
 runner.model.load_state_dict(fixture.fixture_state_dict(runner.model.state_dict(), 42))
 runner.model.use_tensor_cores = not no_tc
+runner.warmup()
 s = synth.make_workload_scene(name, 0)
 p4 = torch.tensor(scene_to_points4(s)).cuda()
 for i in range(2):
