@@ -34,7 +34,8 @@ constexpr int kPackSize = kFcC + 32 * 32 + 32;
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int PT = 128;       // points per tile
 constexpr int LD = PT + 4;    // channel-major row stride
-constexpr int NTP = 128;      // threads per CTA
+constexpr int NTP = 256;      // threads per CTA
+constexpr int RPT = PT * 8 / NTP;  // points per thread tile (4): 16 resident warps per SM hide the shared-memory latency
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   if (v >= 0.f)
@@ -43,25 +44,25 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
     atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-// acc[o][p]: thread (tr = tid>>3, tc = tid&7) owns points tr*8+p and outputs g*32 + 4*tc + u  (o = 4*g + u)
+// acc[o][p]: thread (tr = tid>>3, tc = tid&7) owns points tr*RPT+p and outputs g*32 + 4*tc + u  (o = 4*g + u)
 template <int IN, int OUT, bool RELU_IN>
 __device__ __forceinline__ void tile_dense(const float* __restrict__ X, const float* __restrict__ W,
-                                           const float* __restrict__ b, float (&acc)[OUT / 8][8], int tr, int tc) {
+                                           const float* __restrict__ b, float (&acc)[OUT / 8][RPT], int tr, int tc) {
   constexpr int NG = OUT / 32;
+  static_assert(RPT == 4, "one 128-bit activation load per k");
 #pragma unroll
   for (int o = 0; o < OUT / 8; ++o) {
     const float bb = b ? b[(o >> 2) * 32 + 4 * tc + (o & 3)] : 0.f;
 #pragma unroll
-    for (int p = 0; p < 8; ++p) acc[o][p] = bb;
+    for (int p = 0; p < RPT; ++p) acc[o][p] = bb;
   }
-#pragma unroll 4
+#pragma unroll 8
   for (int k = 0; k < IN; ++k) {
-    const float4 xa = *reinterpret_cast<const float4*>(X + k * LD + tr * 8);
-    const float4 xb = *reinterpret_cast<const float4*>(X + k * LD + tr * 8 + 4);
-    float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    const float4 xa = *reinterpret_cast<const float4*>(X + k * LD + tr * RPT);
+    float xv[RPT] = {xa.x, xa.y, xa.z, xa.w};
     if (RELU_IN) {
 #pragma unroll
-      for (int p = 0; p < 8; ++p) xv[p] = fmaxf(xv[p], 0.f);
+      for (int p = 0; p < RPT; ++p) xv[p] = fmaxf(xv[p], 0.f);
     }
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
@@ -70,18 +71,17 @@ __device__ __forceinline__ void tile_dense(const float* __restrict__ X, const fl
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int p = 0; p < 8; ++p) acc[4 * g + u][p] = fmaf(xv[p], wv[u], acc[4 * g + u][p]);
+        for (int p = 0; p < RPT; ++p) acc[4 * g + u][p] = fmaf(xv[p], wv[u], acc[4 * g + u][p]);
     }
   }
 }
 
 template <int OUT>
-__device__ __forceinline__ void tile_store(float* __restrict__ Y, const float (&acc)[OUT / 8][8], int tr, int tc) {
+__device__ __forceinline__ void tile_store(float* __restrict__ Y, const float (&acc)[OUT / 8][RPT], int tr, int tc) {
 #pragma unroll
   for (int o = 0; o < OUT / 8; ++o) {
-    float* y = Y + ((o >> 2) * 32 + 4 * tc + (o & 3)) * LD + tr * 8;
+    float* y = Y + ((o >> 2) * 32 + 4 * tc + (o & 3)) * LD + tr * RPT;
     *reinterpret_cast<float4*>(y) = make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
-    *reinterpret_cast<float4*>(y + 4) = make_float4(acc[o][4], acc[o][5], acc[o][6], acc[o][7]);
   }
 }
 
@@ -122,75 +122,77 @@ k_pfn_tile(const float* __restrict__ xyz, const int* __restrict__ ptime, const i
     const int j0 = tile * PT;
     __syncthreads();  // previous tile fully consumed (and the weights are in place on the first pass)
     {
-      const int j = j0 + tid;
+      // two threads per row: half 0 / 1 load the first / second 32 input channels of row `row`
+      const int row = tid & (PT - 1), half = tid >> 7;
+      const int j = j0 + row;
       const int i = j < n ? order[j] : -1;
       const int m = i >= 0 ? p2v[i] : -1;
-      s_pil[tid] = m;
+      if (half == 0) s_pil[row] = m;
       if (STAGE == 0) {
-        float f[9];
+        if (half == 0) {
+          float f[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) f[k] = 0.f;
-        if (i >= 0) {
-          const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
-          f[0] = px, f[1] = py, f[2] = pz;
-          f[3] = __fsub_rn(px, pmean[3 * m]);
-          f[4] = __fsub_rn(py, pmean[3 * m + 1]);
-          f[5] = __fsub_rn(pz, pmean[3 * m + 2]);
-          const int4 c = reinterpret_cast<const int4*>(coords)[m];  // z, y, x, t
-          f[6] = (float)((double)px - ((double)c.z * g.vx + g.x_off));
-          f[7] = (float)((double)py - ((double)c.y * g.vy + g.y_off));
+          for (int k = 0; k < 9; ++k) f[k] = 0.f;
+          if (i >= 0) {
+            const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+            f[0] = px, f[1] = py, f[2] = pz;
+            f[3] = __fsub_rn(px, pmean[3 * m]);
+            f[4] = __fsub_rn(py, pmean[3 * m + 1]);
+            f[5] = __fsub_rn(pz, pmean[3 * m + 2]);
+            const int4 c = reinterpret_cast<const int4*>(coords)[m];  // z, y, x, t
+            f[6] = (float)((double)px - ((double)c.z * g.vx + g.x_off));
+            f[7] = (float)((double)py - ((double)c.y * g.vy + g.y_off));
 #pragma unroll
-          for (int k = 0; k < 8; ++k) f[k] = __fdiv_rn(f[k], g.scale);
-          f[8] = __fdiv_rn((float)ptime[i], g.n_frames);
+            for (int k = 0; k < 8; ++k) f[k] = __fdiv_rn(f[k], g.scale);
+            f[8] = __fdiv_rn((float)ptime[i], g.n_frames);
+          }
+#pragma unroll
+          for (int k = 0; k < 9; ++k) NETs[k * LD + row] = f[k];
         }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) NETs[k * LD + tid] = f[k];
       } else {
-        // row tid of the tile: 32 channels of the previous block output, 32 channels of its pillar's pooled vector
-        const float4* a = reinterpret_cast<const float4*>(net_in + (size_t)(j < n ? j : 0) * 32);
-        const float4* b = reinterpret_cast<const float4*>(pooled_in + (size_t)(m >= 0 ? m : 0) * 32);
+        // half 0: the 32 channels of the previous block output; half 1: the 32 channels of the pillar's pooled vector
+        const float4* a = half == 0 ? reinterpret_cast<const float4*>(net_in + (size_t)(j < n ? j : 0) * 32)
+                                    : reinterpret_cast<const float4*>(pooled_in + (size_t)(m >= 0 ? m : 0) * 32);
+        float* dst = X + half * 32 * LD + row;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          float4 v = j < n ? a[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 u = j < n ? b[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-          X[(4 * q + 0) * LD + tid] = v.x, X[(4 * q + 1) * LD + tid] = v.y, X[(4 * q + 2) * LD + tid] = v.z, X[(4 * q + 3) * LD + tid] = v.w;
-          X[(32 + 4 * q + 0) * LD + tid] = u.x, X[(32 + 4 * q + 1) * LD + tid] = u.y, X[(32 + 4 * q + 2) * LD + tid] = u.z,
-                                X[(32 + 4 * q + 3) * LD + tid] = u.w;
+          const float4 v = j < n ? a[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+          dst[(4 * q + 0) * LD] = v.x, dst[(4 * q + 1) * LD] = v.y, dst[(4 * q + 2) * LD] = v.z, dst[(4 * q + 3) * LD] = v.w;
         }
       }
     }
     __syncthreads();
     if (STAGE == 0) {
-      float a64[8][8];
+      float a64[8][RPT];
       tile_dense<9, 64, false>(NETs, Wx, Wx + 9 * 64, a64, tr, tc);
       tile_store<64>(X, a64, tr, tc);
       __syncthreads();
     }
-    float out[4][8];
+    float out[4][RPT];
     {
-      float net[4][8];
+      float net[4][RPT];
       tile_dense<64, 32, true>(X, W0, b0, net, tr, tc);
 #pragma unroll
       for (int o = 0; o < 4; ++o)
 #pragma unroll
-        for (int p = 0; p < 8; ++p) net[o][p] = fmaxf(net[o][p], 0.f);  // fc_1 consumes relu(net)
+        for (int p = 0; p < RPT; ++p) net[o][p] = fmaxf(net[o][p], 0.f);  // fc_1 consumes relu(net)
       tile_store<32>(NETs, net, tr, tc);
     }
     tile_dense<64, 32, false>(X, Ws, nullptr, out, tr, tc);
     __syncthreads();  // NETs complete; everyone is done reading X
     {
-      float dx[4][8];
+      float dx[4][RPT];
       tile_dense<32, 32, false>(NETs, W1, b1, dx, tr, tc);
 #pragma unroll
       for (int o = 0; o < 4; ++o)
 #pragma unroll
-        for (int p = 0; p < 8; ++p) out[o][p] += dx[o][p];
+        for (int p = 0; p < RPT; ++p) out[o][p] += dx[o][p];
     }
     float* R = X;  // result tile [32][LD]
     if (STAGE == 2) {
       tile_store<32>(X, out, tr, tc);
       __syncthreads();
-      float y[4][8];
+      float y[4][RPT];
       tile_dense<32, 32, false>(X, Wx, Wx + 32 * 32, y, tr, tc);
       tile_store<32>(NETs, y, tr, tc);  // every thread finished reading NETs before the barrier above
       R = NETs;
@@ -198,15 +200,15 @@ k_pfn_tile(const float* __restrict__ xyz, const int* __restrict__ ptime, const i
       tile_store<32>(X, out, tr, tc);
       // the next stage reads the block output row-major from HBM: 8 points x 16 B per thread, a 128 B row per 8 lanes
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int j = j0 + tr * 8 + p;
+      for (int p = 0; p < RPT; ++p) {
+        const int j = j0 + tr * RPT + p;
         if (j < n) *reinterpret_cast<float4*>(net_out + (size_t)j * 32 + 4 * tc) = make_float4(out[0][p], out[1][p], out[2][p], out[3][p]);
       }
     }
     __syncthreads();
-    // fused segment max: thread = channel c x quarter q of the tile's rows
+    // fused segment max: thread = channel c x one slice of the tile's rows
     {
-      const int c = tid & 31, r0 = (tid >> 5) * 32, r1 = r0 + 32;
+      const int c = tid & 31, r0 = (tid >> 5) * (PT * 32 / NTP), r1 = r0 + PT * 32 / NTP;
       const float* row = R + c * LD;
       int cur = s_pil[r0], start = r0;
       float v = -INFINITY;
@@ -304,7 +306,7 @@ extern "C" int pcab_pillar_encode(const float* xyz, const int* point_time, const
     cfg = true;
   }
   const int ntiles = (n_points + PT - 1) / PT;
-  const int gp = ntiles < 2 * 148 ? ntiles : 2 * 148;  // persistent: two CTAs per SM
+  const int gp = ntiles < 2 * 148 ? ntiles : 2 * 148;  // persistent: two CTAs (16 warps) per SM
   const long long pool4 = (long long)n_pillars * 8;
   const int gf = grid_for(pool4, 256, 8);
   // pooled vectors ping-pong between `pillar_feats` and the scratch array (each is re-filled with -inf before reuse)

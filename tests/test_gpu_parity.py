@@ -615,3 +615,87 @@ def test_other_baseline_configs_run_at_full_size(fixture_weights, name):
     assert_close_rel(res2["fb_seg_est"], res["fb_seg_est"].cpu(), 2e-4, "fb_seg_est tc vs fp32")
     flips = int((res2["fb_est_per_points"] != res["fb_est_per_points"]).sum())
     assert flips <= 40, flips
+
+
+# -------------------------------------------------------------------------------------------------------------
+# kernels added after the first full pipeline: tiled pillar encoder with fused segment max, tensor-core point head
+# -------------------------------------------------------------------------------------------------------------
+def test_pillar_encoder_long_runs_and_tile_boundaries(fixture_weights):
+    """Pillars of 1..700 points: runs that sit inside one scan range (plain stores), straddle thread / tile boundaries or
+    span several 128-point tiles (atomic max) - against the oracle's pillar encoder (models/pillar_encoder.py:97-122)."""
+    from oracle import oracle
+    from pcaccumulation_b200 import config, synth
+
+    cfg = config.workload_config("C1")
+    sd = fixture_weights(cfg)
+    rng = np.random.default_rng(5)
+    vg = cfg["voxel_generator"]
+    T = vg["n_sweeps"]
+    chunks = []
+    for t in range(T):
+        # dense cells: 700, 300, 129, 128, 127 points inside single 0.25 m cells, then sparse clutter
+        for k, n_pts in enumerate((700, 300, 129, 128, 127, 64, 33)):
+            c = np.array([-20.0 + 3.1 * k + 0.125, 5.0 * t - 10.0 + 0.125])
+            xy = c + rng.uniform(-0.12, 0.12, (n_pts, 2))
+            chunks.append(np.concatenate([xy, rng.uniform(0.0, 2.0, (n_pts, 1)), np.full((n_pts, 1), t)], 1))
+        n_pts = 3000
+        chunks.append(np.concatenate([rng.uniform(-30, 30, (n_pts, 2)), rng.uniform(0.0, 2.0, (n_pts, 1)), np.full((n_pts, 1), t)], 1))
+    p4 = np.concatenate(chunks).astype(np.float32)
+    p4 = p4[rng.permutation(p4.shape[0])]
+    p4 = p4[np.argsort(p4[:, 3], kind="stable")]  # frames ascending, shuffled inside a frame
+    v = oracle.voxelize(p4, vg["voxel_size"], vg["range"], T)
+    n = p4.shape[0]
+    sample = {"input_points": p4[:, :3], "time_indice": p4[:, 3:4].astype(np.float64), "sd_labels": np.zeros((n, 1), np.int64),
+              "fb_labels": np.zeros((n, 1), np.int64), "inst_labels": np.zeros((n, 1), np.int64),
+              "ego_motion_gt": np.tile(np.eye(4, dtype=np.float32), (T, 1, 1)), "inst_motion_gt": np.tile(np.eye(4, dtype=np.float32), (1, T, 1, 1)),
+              "num_points": np.array([n], dtype=np.int64)}
+    sample.update(v)
+    inp = synth.collate([sample])
+    orc = oracle.OracleMotionNet(cfg, sd)
+    torch.manual_seed(0)
+    orc.forward(inp)
+    ref = orc.stages["pillar_feats"]
+    p2v = inp["point_to_voxel_map"][:, 0].long()
+    M = int(inp["num_voxels"].sum())
+    counts = torch.bincount(p2v, minlength=M)
+    assert int(counts.max()) >= 700 and int((counts == 1).sum()) > 1000
+    model = make_model(cfg, sd, False)
+    torch.manual_seed(0)
+    model(cuda_dict(inp))
+    assert_close_rel(model.stages["pillar_feats"], ref, 1e-5, "pillar_feats")
+
+
+@pytest.mark.parametrize("n_fg", [1, 127, 129, 40001])
+def test_stpn_head_tensor_core_matches_fp32_head(fixture_weights, n_fg):
+    """pcab_stpn_head_tc (tcgen05, 3xTF32) against pcab_stpn_head (FP32 CUDA cores) on the same random inputs."""
+    from pcaccumulation_b200 import config
+    from pcaccumulation_b200._lib import F, I, P, call, stream
+
+    cfg = config.workload_config("C1")
+    model = make_model(cfg, fixture_weights(cfg), True)
+    W = model._weights()
+    g = torch.Generator(device="cuda").manual_seed(n_fg)
+    H = Wd = 96
+    N = max(2 * n_fg, 300)
+    feats = torch.randn(2, H, Wd, 64, device="cuda", generator=g)
+    tp = (torch.rand(N, 3, device="cuda", generator=g) * 2 - 1) * torch.tensor([12.5, 12.5, 3.0], device="cuda")  # incl. out-of-map
+    pbatch = (torch.rand(N, device="cuda", generator=g) < 0.5).to(torch.int32)
+    fg_idx = torch.randperm(N, device="cuda", generator=g)[:n_fg].sort().values.to(torch.int32)
+    outs = []
+    for tc in (False, True):
+        mos = torch.full((N, 2), 7.0, device="cuda")
+        off = torch.full((N, 2), 7.0, device="cuda")
+        if tc:
+            call("pcab_stpn_head_tc", P(feats), I(H), I(Wd), P(tp), P(pbatch), P(fg_idx), I(n_fg), P(W["stpn_head_host"]),
+                 P(W["stpn_head_tc1"]), P(W["stpn_head_tc"]), F(12.0), F(12.0), P(mos), P(off), stream())
+        else:
+            call("pcab_stpn_head", P(feats), I(H), I(Wd), P(tp), P(pbatch), P(fg_idx), I(n_fg), P(W["stpn_head"]), F(12.0), F(12.0),
+                 P(mos), P(off), stream())
+        torch.cuda.synchronize()
+        outs.append((mos, off))
+    sel = fg_idx.long()
+    rest = torch.ones(N, dtype=torch.bool, device="cuda")
+    rest[sel] = False
+    for a, b in zip(outs[0], outs[1]):
+        assert_close_rel(b[sel], a[sel], 2e-5, "tensor-core head")
+        assert bool((b[rest] == 7.0).all()), "rows outside fg_idx must not be written"
