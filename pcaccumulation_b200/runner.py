@@ -77,11 +77,13 @@ class SceneRunner:
         return self.model(self.build_input(points4, num_points, **kw))
 
     @torch.no_grad()
-    def run_host(self, points4_pinned, num_points, ego_motion_gt_host=None, out=None):
+    def run_host(self, points4_pinned, num_points, ego_motion_gt_host=None, out=None, copy_stream=None):
         """End to end with HOST buffers: H2D of the raw points, forward, D2H of the per-point results.
 
         ``out``: optional dict of pinned host tensors (rec_est f32[N,3], fb i64[N], mos f32[N,2], inst i64[N],
-        ego f32[B,T,4,4]) to receive the results.  Returns (results_on_device, bytes_h2d, bytes_d2h).
+        ego f32[B,T,4,4]) to receive the results.  ``copy_stream``: when given, the D2H copies are queued there (after an
+        event on the current stream), so the next forward on the current stream does not wait for them; the caller then
+        synchronises with ``copy_stream`` before reading ``out``.  Returns (results_on_device, bytes_h2d, bytes_d2h).
         """
         dev = self.device
         pts = points4_pinned.to(dev, non_blocking=True)
@@ -93,12 +95,18 @@ class SceneRunner:
         res = self.run_device(pts, num_points, ego_motion_gt=ego)
         d2h = 0
         if out is not None:
-            for key, src in (("rec_est", res["rec_est"]), ("fb", res["fb_est_per_points"][:, 0]), ("mos", res["mos_est"]),
-                             ("inst", res.get("inst_labels_est")), ("ego", res["ego_motion_est"])):
-                if src is None or key not in out:
-                    continue
-                out[key].copy_(src, non_blocking=True)
-                d2h += src.numel() * src.element_size()
+            srcs = [(key, src) for key, src in (("rec_est", res["rec_est"]), ("fb", res["fb_est_per_points"][:, 0]),
+                                                ("mos", res["mos_est"]), ("inst", res.get("inst_labels_est")),
+                                                ("ego", res["ego_motion_est"])) if src is not None and key in out]
+            cur = torch.cuda.current_stream()
+            if copy_stream is not None:
+                copy_stream.wait_stream(cur)
+            with torch.cuda.stream(copy_stream if copy_stream is not None else cur):
+                for key, src in srcs:
+                    out[key].copy_(src, non_blocking=True)
+                    if copy_stream is not None:
+                        src.record_stream(copy_stream)
+                    d2h += src.numel() * src.element_size()
         return res, h2d, d2h
 
 
@@ -124,6 +132,7 @@ class ScenePipeline:
             r.model.rng = torch.Generator()  # per-slot CPU generator: the global one would interleave between threads
             self._slots.append((r, torch.cuda.Stream(device=self.device)))
             self._free.put(self._slots[-1])
+            r.copy_stream = torch.cuda.Stream(device=self.device)  # D2H of a finished scene overlaps the slot's next forward
         if state_dict is not None:
             self.load_state_dict(state_dict)
         # torch initialises its linear-algebra backend lazily and not thread-safely: touch it once from this thread
@@ -147,12 +156,13 @@ class ScenePipeline:
             with torch.cuda.stream(stream):
                 if seed is not None:
                     runner.model.rng.manual_seed(int(seed))
+                done = torch.cuda.Event()
                 if host:
-                    res = runner.run_host(points4, num_points, ego_motion_gt_host=ego, out=out)[0]
+                    res = runner.run_host(points4, num_points, ego_motion_gt_host=ego, out=out, copy_stream=runner.copy_stream)[0]
+                    done.record(runner.copy_stream)
                 else:
                     res = runner.run_device(points4, num_points, ego_motion_gt=ego)
-                done = torch.cuda.Event()
-                done.record(stream)
+                    done.record(stream)
             return res, done
         finally:
             self._free.put((runner, stream))
