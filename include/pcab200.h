@@ -156,7 +156,17 @@ int pcab_tpn_iteration(const float* points, const int* inst, const int* tidx, in
                        const float* geo_emb, const float* pack_pos, const float* pack_regressor,
                        float* pose_out /* [K*T,4,4] */, float* pose_centered_out /* or NULL */,
                        float* rep_out /* [K*T,7] or NULL */, void* workspace, size_t workspace_bytes,
-                       pcab_stream_t stream);
+                       const float* pos_w0_tc /* NULL = FP32 positional embedding; else the tensor-core packs of its layers */,
+                       const float* pos_w1_tc, const float* pos_bias_host /* HOST: b1[64] b2[128] */,
+                       void* pos_scratch /* n * (32 floats + 1 int) */, pcab_stream_t stream);
+/* TubeNet embeddings on the tensor cores (csrc/mlp_tc.cu): MLP + max over the rows of each segment.  which: 0 = motion_embed
+ * (64-64-128-128), 1 = geo_embed (32-32-64-128), 2 = layers 1-2 of pos_embed (32-64-128) over the rows of pcab_tpn_pos_l0.
+ * w*_tc: per layer [hi rows; lo rows] K-major; bias_host: the layers' biases back to back (HOST memory); seg ascending. */
+int pcab_embed_segmax_tc(int which, const float* feat, const int* src_idx /* or NULL */, const int* seg, int n, int n_seg,
+                         const float* w0_tc, const float* w1_tc, const float* w2_tc, const float* bias_host,
+                         float* out /* [n_seg,128] */, pcab_stream_t stream);
+int pcab_tpn_pos_l0(const float* points, const int* inst, const int* tidx, int n, int T, const double* frame_sums,
+                    const float* pack_pos, float* rows /* [n,32] */, int* seg /* [n] */, pcab_stream_t stream);
 int pcab_apply_seg_pose(const float* points, const int* seg, const float* pose, int n, float* out,
                         pcab_stream_t stream);
 int pcab_scatter_rows3(const float* src, const int* idx, int k, float* dst, pcab_stream_t stream);

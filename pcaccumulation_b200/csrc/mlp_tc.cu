@@ -37,6 +37,8 @@ constexpr int kStages = 3;
 constexpr int kChunksPerTile = 13;        // pe2: 1, final_proj / mos0 / off0: 4 each
 constexpr size_t kSmemBytes = 1024 + 2 * (size_t)kPlane + kStages * (size_t)kWStage + 128 + 3 * 128 * 4;
 
+long long* g_head_stats = nullptr;  // debug counters of the kernels in this file (pcab_stpn_head_tc_set_stats)
+
 struct HeadArgs {
   const float* mos_feats;
   int H, W;
@@ -384,6 +386,293 @@ k_stpn_head_tc(const __grid_constant__ CUtensorMap map_w1, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// TubeNet embeddings (models/tpointnet.py:171-205, 240-262): a 2- or 3-layer point MLP (ReLU between layers, none after
+// the last) followed by a max over the rows of each segment (instance, or instance x frame).  Same machinery as the head
+// above: 128 rows per tile, activations as in-place A planes, weights through the TMA ring, two TMEM buffers.  Rows arrive
+// sorted by segment, so the last epilogue reduces the runs inside a warp with a segmented shuffle scan and issues one
+// atomic max per (run, channel); the destination is pre-filled with -inf.
+// ---------------------------------------------------------------------------------------------------------------------
+struct EmbedArgs {
+  const float* feat;   // [n_src][K0] input rows
+  const int* src_idx;  // [n] row of `feat` for each point, or null = identity
+  const int* seg;      // [n] segment of each point (ascending)
+  int n;
+  float* out;          // [n_seg][128]
+  int n_tiles;
+  long long* stats;    // debug: per-CTA phase cycle counters (null = off)
+};
+struct EmbedConsts {
+  float b[3][128];
+};
+
+template <int K0, int N1, int N2>
+__global__ void __launch_bounds__(kNT, 1)
+k_embed_tc(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
+           const __grid_constant__ CUtensorMap map_w2, const EmbedArgs a, const __grid_constant__ EmbedConsts k) {
+  constexpr int NL = N2 ? 3 : 2;
+  constexpr int KL[3] = {K0, N1, N2};
+  constexpr int NO[3] = {N1, N2 ? N2 : 128, 128};
+  constexpr int QPR = K0 / 4;            // 16-byte chunks per input row
+  constexpr int ITEMS = 128 * QPR / 256;  // (row, chunk) items per thread
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_hi = sbase, a_lo = sbase + kPlane, w0 = sbase + 2 * kPlane;
+  const uint32_t bars = w0 + kStages * kWStage;
+  const uint32_t bar_w_full = bars, bar_w_free = bars + 24, bar_a_ready = bars + 48, bar_acc_full = bars + 56,
+                 bar_acc_empty = bars + 72, tmem_slot = bars + 88;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) mbar_init(bar_w_full + 8 * i, 1), mbar_init(bar_w_free + 8 * i, 1);
+    mbar_init(bar_a_ready, 256);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_acc_full + 8 * i, 1), mbar_init(bar_acc_empty + 8 * i, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  if (warp == 8) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      int wg = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+          const CUtensorMap* m = l == 0 ? &map_w0 : (l == 1 ? &map_w1 : &map_w2);
+          for (int c = 0; c < KL[l] / 32; ++c, ++wg) {
+            const int ws = wg % kStages;
+            if (wg >= kStages) mbar_wait(bar_w_free + 8 * ws, ((wg / kStages) - 1) & 1);
+            mbar_expect_tx(bar_w_full + 8 * ws, 2u * NO[l] * 128u);
+            tma_load_2d(m, w0 + ws * kWStage, bar_w_full + 8 * ws, c * 32, 0);  // [w_hi NO rows; w_lo NO rows] x 32
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
+    const uint64_t desc_hi = (uint64_t)(64u | (1u << 14) | (2u << 29)) << 32;
+    const uint32_t lbo = 1u << 16;
+    const uint32_t ah_base = lbo | ((a_hi & 0x3FFFF) >> 4), al_base = lbo | ((a_lo & 0x3FFFF) >> 4);
+    const uint32_t b_base = lbo | ((w0 & 0x3FFFF) >> 4);
+    int wg = 0, job = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+#pragma unroll
+      for (int l = 0; l < NL; ++l, ++job) {
+        const int buf = job & 1, n = NO[l], nchunks = KL[l] / 32;
+        mbar_wait(bar_a_ready, job & 1);
+        if (job >= 2) mbar_wait(bar_acc_empty + 8 * buf, ((job >> 1) - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 256);
+          const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * n) >> 3) << 17), idesc1 = idesc_base | ((uint32_t)(n >> 3) << 17);
+          for (int c = 0; c < nchunks; ++c) {
+            const int ws = (wg + c) % kStages;
+            mbar_wait(bar_w_full + 8 * ws, ((wg + c) / kStages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ah = ah_base + (uint32_t)c * (kAtom >> 4), al = al_base + (uint32_t)c * (kAtom >> 4);
+            const uint32_t b16 = b_base + (uint32_t)ws * (kWStage >> 4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t dah = desc_hi | (ah + 2u * kk), dal = desc_hi | (al + 2u * kk), db = desc_hi | (b16 + 2u * kk);
+              umma_tf32(tmem_d, dah, db, idesc2, (c | kk) ? 1u : 0u);
+              umma_tf32(tmem_d + (uint32_t)n, dal, db, idesc1, 1u);
+            }
+            umma_commit(bar_w_free + 8 * ws);
+          }
+          umma_commit(bar_acc_full + 8 * buf);
+        }
+        __syncwarp();
+        wg += nchunks;
+      }
+    }
+  } else {
+    // ===================== input rows, epilogues, segment max =====================
+    const int r = (warp & 3) * 32 + lane, h = warp >> 2;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const int ctid = (int)threadIdx.x;
+    float4 g[ITEMS];
+    int seg_next = -1;
+    auto prefetch = [&](int tile) {
+      const int base = tile * 128;
+      seg_next = base + r < a.n ? a.seg[base + r] : -1;
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const int e = it * 256 + ctid, p = e / QPR, q = e % QPR;
+        const int j = base + p < a.n ? base + p : base;  // padding rows copy the tile's first row (never reduced)
+        const int src = a.src_idx ? a.src_idx[j] : j;
+        g[it] = reinterpret_cast<const float4*>(a.feat + (size_t)src * K0)[q];
+      }
+    };
+    if ((int)blockIdx.x < a.n_tiles) prefetch(blockIdx.x);
+    int job = 0;
+    const bool st_on = a.stats != nullptr && threadIdx.x == 0;
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = st_on ? clock64() : 0;
+#define PCAB_PHASE(kk)                     \
+  if (st_on) {                             \
+    const long long tnow = clock64();      \
+    ph[kk] += tnow - tprev, tprev = tnow;  \
+  }
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const int seg = seg_next;
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const int e = it * 256 + ctid, p = e / QPR, q = e % QPR;
+        put4(a_hi, a_lo, p, 4 * q, g[it].x, g[it].y, g[it].z, g[it].w);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_a_ready);
+      PCAB_PHASE(0)
+#pragma unroll
+      for (int l = 0; l < NL; ++l, ++job) {
+        const int buf = job & 1;
+        if (l == NL - 1 && tile + (int)gridDim.x < a.n_tiles) prefetch(tile + gridDim.x);  // flies while the last layer's MMAs run
+        mbar_wait(bar_acc_full + 8 * buf, (job >> 1) & 1);
+        PCAB_PHASE(1 + 2 * l)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tm = tmem_base + lane_addr + (uint32_t)(buf * 256);
+        const int n = NO[l], per = n / 2;
+        if (l < NL - 1) {
+          auto epi = [&](auto hc) {
+            constexpr int HH = decltype(hc)::value;
+#pragma unroll
+            for (int b = 0; b < NO[l] / 32; ++b) {
+              uint32_t vm[16], vc[16];
+              const int c0 = HH * per + b * 16;
+              tmem_ld16(tm + (uint32_t)c0, vm);
+              tmem_ld16(tm + (uint32_t)(n + c0), vc);
+              tmem_ld_wait16(vm, vc);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  v[u] = fmaxf((__uint_as_float(vm[4 * q + u]) + __uint_as_float(vc[4 * q + u])) + k.b[l][c0 + 4 * q + u], 0.f);
+                put4(a_hi, a_lo, r, c0 + 4 * q, v[0], v[1], v[2], v[3]);
+              }
+            }
+          };
+          if (h == 0) epi(std::integral_constant<int, 0>{}); else epi(std::integral_constant<int, 1>{});
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+          mbar_arrive(bar_a_ready);
+          PCAB_PHASE(2 + 2 * l)
+        } else {
+          // last layer (no activation).  Its MMAs are done, so the A planes are free: the tile's outputs go there
+          // channel-major ([128 ch][132]), and after a barrier thread (channel, half of the rows) scans its 64 rows: a run
+          // strictly inside the scan range is a whole segment (plain store), runs touching an edge go through one atomic
+          // max each.  (A shuffle-based segmented scan in registers costs 5 dependent SHFLs per value: 4x slower.)
+          constexpr uint32_t LDT = 132;
+          const uint32_t s_seg = sbase + 128u * LDT * 4u;
+          auto epi = [&](auto hc) {
+            constexpr int HH = decltype(hc)::value;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              uint32_t vm[16], vc[16];
+              const int c0 = HH * 64 + b * 16;
+              tmem_ld16(tm + (uint32_t)c0, vm);
+              tmem_ld16(tm + (uint32_t)(128 + c0), vc);
+              tmem_ld_wait16(vm, vc);
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                const float v = (__uint_as_float(vm[u]) + __uint_as_float(vc[u])) + k.b[l][c0 + u];
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbase + ((uint32_t)(c0 + u) * LDT + (uint32_t)r) * 4u), "f"(v) : "memory");
+              }
+            }
+          };
+          if (h == 0) epi(std::integral_constant<int, 0>{}); else epi(std::integral_constant<int, 1>{});
+          if (h == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_seg + 4u * r), "r"(seg) : "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          {
+            const int c = ctid & 127, r0 = (ctid >> 7) * 64, r1 = r0 + 64;
+            int cur = -1, start = r0;
+            float v = -INFINITY;
+            for (int rr = r0; rr <= r1; ++rr) {
+              int sg = -2;
+              float x = 0.f;
+              if (rr < r1) {
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sg) : "r"(s_seg + 4u * rr));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(sbase + ((uint32_t)c * LDT + (uint32_t)rr) * 4u));
+              }
+              if (sg != cur) {
+                if (cur >= 0) {
+                  float* dst = a.out + (size_t)cur * 128 + c;
+                  if (start > r0 && rr < r1) *dst = v; else mlp::atomic_max_float(dst, v);
+                }
+                cur = sg, start = rr, v = -INFINITY;
+              }
+              if (rr < r1) v = fmaxf(v, x);
+            }
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");  // the next tile's input rows overwrite the planes
+          PCAB_PHASE(2 + 2 * l)
+        }
+      }
+    }
+    if (st_on) {
+      long long* sp = a.stats + blockIdx.x * 8;
+      for (int q = 0; q < 8; ++q) sp[q] += ph[q];
+    }
+#undef PCAB_PHASE
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 9) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+__global__ void k_fill_f(float* __restrict__ a, long long n, float v) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) a[i] = v;
+}
+__global__ void k_neg_inf_to_zero(float* __restrict__ a, long long n) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+    if (a[i] == -INFINITY) a[i] = 0.f;  // torch_scatter leaves empty segments at 0
+}
+
+// TubeNet positional embedding, layer 0 on the CUDA cores: [p - anchor centroid(inst), t/T] (4) -> 32, ReLU; rows [n][32]
+__global__ void k_tpn_pos_l0(const float* __restrict__ pts, const int* __restrict__ inst, const int* __restrict__ tidx, int n,
+                             int T, const double* __restrict__ sums, const float* __restrict__ pk /* W[4][32] b[32] */,
+                             float* __restrict__ rows, int* __restrict__ seg) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, q = threadIdx.x & 7;  // 8 threads per row, 4 outputs each
+  if (j >= n) return;
+  const int ki = inst[j], t = tidx[j];
+  const double* s = sums + (size_t)ki * T * 4;  // anchor frame (t = 0) of the instance
+  const double cnt = s[3] > 0 ? s[3] : 1.0;
+  const float x[4] = {pts[3 * j] - (float)(s[0] / cnt), pts[3 * j + 1] - (float)(s[1] / cnt), pts[3 * j + 2] - (float)(s[2] / cnt),
+                      (float)((double)t / (double)T)};
+  float v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int c = 4 * q + u;
+    float acc = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) acc = fmaf(x[kk], pk[kk * 32 + c], acc);
+    v[u] = fmaxf(acc + pk[128 + c], 0.f);
+  }
+  reinterpret_cast<float4*>(rows + (size_t)j * 32)[q] = make_float4(v[0], v[1], v[2], v[3]);
+  if (q == 0) seg[j] = ki * T + t;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -413,8 +702,6 @@ int encode_weights(EncodeTiledFn enc, CUtensorMap* map, const float* w, int rows
   }
   return PCAB_OK;
 }
-
-long long* g_head_stats = nullptr;
 
 }  // namespace
 
@@ -473,5 +760,84 @@ extern "C" int pcab_stpn_head_tc(const float* mos_feats_nhwc, int H, int W, cons
   const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
   k_stpn_head_tc<<<grid, kNT, kSmemBytes, stream>>>(m1, m2, a, k);
   PCAB_CHECK_LAUNCH("pcab_stpn_head_tc");
+  return PCAB_OK;
+}
+
+namespace {
+template <int K0, int N1, int N2>
+int launch_embed(EncodeTiledFn enc, const float* feat, const int* src_idx, const int* seg, int n, int n_seg, const float* w0,
+                 const float* w1, const float* w2, const float* b0, const float* b1, const float* b2, float* out,
+                 cudaStream_t stream) {
+  constexpr int NOUT1 = N2 ? N2 : 128;
+  CUtensorMap m0, m1, m2;
+  int rc = encode_weights(enc, &m0, w0, 2 * N1, K0, 2 * N1);
+  if (rc != PCAB_OK) return rc;
+  rc = encode_weights(enc, &m1, w1, 2 * NOUT1, N1, 2 * NOUT1);
+  if (rc != PCAB_OK) return rc;
+  if (N2) {
+    rc = encode_weights(enc, &m2, w2, 256, N2, 256);
+    if (rc != PCAB_OK) return rc;
+  } else {
+    m2 = m1;
+  }
+  EmbedConsts k;
+  memset(&k, 0, sizeof(k));
+  memcpy(k.b[0], b0, N1 * sizeof(float));
+  memcpy(k.b[1], b1, NOUT1 * sizeof(float));
+  if (N2) memcpy(k.b[2], b2, 128 * sizeof(float));
+  EmbedArgs a;
+  a.feat = feat, a.src_idx = src_idx, a.seg = seg, a.n = n, a.out = out, a.n_tiles = cdiv(n, 128);
+  a.stats = g_head_stats;
+  static bool configured = false;
+  if (!configured) {
+    PCAB_CUDA(cudaFuncSetAttribute(k_embed_tc<K0, N1, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    configured = true;
+  }
+  const long long total = (long long)n_seg * 128;
+  k_fill_f<<<grid_for(total, 256), 256, 0, stream>>>(out, total, -INFINITY);
+  const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
+  k_embed_tc<K0, N1, N2><<<grid, kNT, kSmemBytes, stream>>>(m0, m1, m2, a, k);
+  k_neg_inf_to_zero<<<grid_for(total, 256), 256, 0, stream>>>(out, total);
+  return PCAB_OK;
+}
+}  // namespace
+
+// TubeNet embeddings on the tensor cores.  which: 0 = motion_embed (64 -> 64 -> 128 -> 128), 1 = geo_embed (32 -> 32 -> 64 ->
+// 128), 2 = layers 1-2 of pos_embed (32 -> 64 -> 128; `feat` = the rows written by pcab_tpn_pos_l0).  w*_tc: [hi rows; lo rows]
+// K-major per layer (tc_pack.split_tf32); bias_host: the layers' biases back to back, on the HOST.  `seg` ascending.
+extern "C" int pcab_embed_segmax_tc(int which, const float* feat, const int* src_idx, const int* seg, int n, int n_seg,
+                                    const float* w0_tc, const float* w1_tc, const float* w2_tc, const float* bias_host,
+                                    float* out /* [n_seg,128] */, cudaStream_t stream) {
+  if (n <= 0 || n_seg <= 0) return PCAB_OK;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    pcab_set_error("pcab_embed_segmax_tc: cuTensorMapEncodeTiled unavailable");
+    return PCAB_ERR_CUDA;
+  }
+  PCAB_REQUIRE(bias_host != nullptr && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)w0_tc & 15) == 0 && ((uintptr_t)w1_tc & 15) == 0,
+               "alignment / null arguments");
+  int rc;
+  if (which == 0)
+    rc = launch_embed<64, 64, 128>(enc, feat, src_idx, seg, n, n_seg, w0_tc, w1_tc, w2_tc, bias_host, bias_host + 64, bias_host + 192, out, stream);
+  else if (which == 1)
+    rc = launch_embed<32, 32, 64>(enc, feat, src_idx, seg, n, n_seg, w0_tc, w1_tc, w2_tc, bias_host, bias_host + 32, bias_host + 96, out, stream);
+  else if (which == 2)
+    rc = launch_embed<32, 64, 0>(enc, feat, src_idx, seg, n, n_seg, w0_tc, w1_tc, nullptr, bias_host, bias_host + 64, nullptr, out, stream);
+  else {
+    pcab_set_error("pcab_embed_segmax_tc: which must be 0, 1 or 2");
+    return PCAB_ERR_ARG;
+  }
+  if (rc != PCAB_OK) return rc;
+  PCAB_CHECK_LAUNCH("pcab_embed_segmax_tc");
+  return PCAB_OK;
+}
+
+// layer 0 of pos_embed for every (padded) TubeNet row + the (instance, frame) segment id of the row
+extern "C" int pcab_tpn_pos_l0(const float* points, const int* inst, const int* tidx, int n, int T, const double* frame_sums,
+                               const float* pack_pos /* device: W0[4][32] b0[32] .. */, float* rows /* [n,32] */,
+                               int* seg /* [n] */, cudaStream_t stream) {
+  if (n <= 0) return PCAB_OK;
+  k_tpn_pos_l0<<<cdiv(n * 8, 256), 256, 0, stream>>>(points, inst, tidx, n, T, frame_sums, pack_pos, rows, seg);
+  PCAB_CHECK_LAUNCH("pcab_tpn_pos_l0");
   return PCAB_OK;
 }

@@ -594,7 +594,9 @@ extern "C" size_t pcab_tpn_iteration_workspace(int K, int T) {
 extern "C" int pcab_tpn_iteration(const float* points, const int* inst, const int* tidx, int n, int K, int T,
                                   const float* mos_emb, const float* geo_emb, const float* pack_pos,
                                   const float* pack_regressor, float* pose_out, float* pose_centered_out,
-                                  float* rep_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                                  float* rep_out, void* workspace, size_t workspace_bytes, const float* pos_w0_tc,
+                                  const float* pos_w1_tc, const float* pos_bias_host, void* pos_scratch,
+                                  cudaStream_t stream) {
   PCAB_REQUIRE(workspace_bytes >= pcab_tpn_iteration_workspace(K, T), "workspace too small");
   size_t kt = (size_t)K * T;
   float* f = (float*)workspace;
@@ -617,9 +619,20 @@ extern "C" int pcab_tpn_iteration(const float* points, const int* inst, const in
     cfg = true;
   }
   k_tpn_frame_sums<<<grid_for(n, 256), 256, 0, stream>>>(points, inst, tidx, T, n, sums);
-  k_fill<<<grid_for((long long)kt * 128, 256), 256, 0, stream>>>(frame_emb, (long long)kt * 128, -INFINITY);
-  k_tpn_pos_embed<<<cdiv(n, PTS), mlp::NT, smem, stream>>>(points, inst, tidx, n, T, sums, pack_pos, frame_emb);
-  k_fix_neg_inf<<<grid_for((long long)kt * 128, 256), 256, 0, stream>>>(frame_emb, (long long)kt * 128);
+  if (pos_w0_tc) {
+    // tensor-core path (csrc/mlp_tc.cu): layer 0 on the CUDA cores, layers 1-2 + the (instance, frame) max on tcgen05
+    PCAB_REQUIRE(pos_w1_tc && pos_bias_host && pos_scratch, "tensor-core positional embedding needs its packs and scratch");
+    float* rows = (float*)pos_scratch;
+    int* seg = (int*)(rows + (size_t)n * 32);
+    int rc = pcab_tpn_pos_l0(points, inst, tidx, n, T, sums, pack_pos, rows, seg, stream);
+    if (rc != PCAB_OK) return rc;
+    rc = pcab_embed_segmax_tc(2, rows, nullptr, seg, n, (int)kt, pos_w0_tc, pos_w1_tc, nullptr, pos_bias_host, frame_emb, stream);
+    if (rc != PCAB_OK) return rc;
+  } else {
+    k_fill<<<grid_for((long long)kt * 128, 256), 256, 0, stream>>>(frame_emb, (long long)kt * 128, -INFINITY);
+    k_tpn_pos_embed<<<cdiv(n, PTS), mlp::NT, smem, stream>>>(points, inst, tidx, n, T, sums, pack_pos, frame_emb);
+    k_fix_neg_inf<<<grid_for((long long)kt * 128, 256), 256, 0, stream>>>(frame_emb, (long long)kt * 128);
+  }
   k_tpn_regressor_input<<<grid_for((long long)kt * 512, 256), 256, 0, stream>>>(geo_emb, mos_emb, frame_emb, (int)kt, T, X);
   const float* W0 = pack_regressor;
   const float* b0 = W0 + 512 * 256;

@@ -309,6 +309,9 @@ class MotionNet(nn.Module):
                               _t(seq[4].weight), _v(seq[4].bias)]).contiguous()
 
         W["tpn_motion"], W["tpn_geo"], W["tpn_pos"] = mlp_pack(al.motion_embed), mlp_pack(al.geo_embed), mlp_pack(al.pos_embed)
+        from .tc_pack import pack_embed_tc
+        W["tpn_motion_tc"], W["tpn_geo_tc"] = pack_embed_tc(al.motion_embed), pack_embed_tc(al.geo_embed)
+        W["tpn_pos_tc"] = pack_embed_tc(al.pos_embed, first=1)  # layer 0 (4 -> 32) stays on the CUDA cores
         r = al.regressor
         s0, t0 = _bn_affine(r[1])
         s1, t1 = _bn_affine(r[4])
@@ -845,8 +848,17 @@ class MotionNet(nn.Module):
             motion0_fn = lambda: motion_kept
         mos_emb = torch.empty(K, 128, device=dev)
         geo_emb = torch.empty(K, 128, device=dev)
-        call("pcab_tpn_static_embed", P(inp["motion_feats"]), P(inp["backbone_feats"]), P(p_idx32), P(p_inst32), I(n_pad),
-             I(K), P(W["tpn_motion"]), P(W["tpn_geo"]), P(mos_emb), P(geo_emb), stream())
+        tc = self.use_tensor_cores
+        if tc:
+            for which, feat, (ws_tc, bias), dst in ((0, inp["motion_feats"], W["tpn_motion_tc"], mos_emb),
+                                                    (1, inp["backbone_feats"], W["tpn_geo_tc"], geo_emb)):
+                call("pcab_embed_segmax_tc", I(which), P(feat), P(p_idx32), P(p_inst32), I(n_pad), I(K), P(ws_tc[0]), P(ws_tc[1]),
+                     P(ws_tc[2]), P(bias), P(dst), stream())
+        else:
+            call("pcab_tpn_static_embed", P(inp["motion_feats"]), P(inp["backbone_feats"]), P(p_idx32), P(p_inst32), I(n_pad),
+                 I(K), P(W["tpn_motion"]), P(W["tpn_geo"]), P(mos_emb), P(geo_emb), stream())
+        pos_tc, pos_bias = W["tpn_pos_tc"]
+        pos_scratch = torch.empty(n_pad * 33, device=dev) if tc else None
         results["tpointnet_loss_terms"] = {}
         final = None
         ws = scratch(size("pcab_tpn_iteration_workspace", I(K), I(T)), dev)
@@ -866,7 +878,8 @@ class MotionNet(nn.Module):
             pose_c = torch.empty(K * T, 4, 4, device=dev)
             rep = torch.empty(K * T, 7, device=dev)
             call("pcab_tpn_iteration", P(p_pts), P(p_inst32), P(p_time32), I(n_pad), I(K), I(T), P(mos_emb), P(geo_emb),
-                 P(W["tpn_pos"]), P(W["tpn_reg"]), P(pose), P(pose_c), P(rep), P(ws), Z(ws.numel()), stream())
+                 P(W["tpn_pos"]), P(W["tpn_reg"]), P(pose), P(pose_c), P(rep), P(ws), Z(ws.numel()),
+                 P(pos_tc[0] if tc else None), P(pos_tc[1] if tc else None), P(pos_bias if tc else None), P(pos_scratch), stream())
             poses.append(pose)
 
             def compute(it=it, pts=p_pts, pose=pose, pose_c=pose_c, rep=rep):

@@ -26,3 +26,10 @@ def pack_stpn_head_tc(mh):
     w = torch.cat([split_tf32(mh.final_proj[0].weight), split_tf32(mh.mos_seg.seg_head[0].weight),
                    split_tf32(mh.offset_head.seg_head[0].weight)], 0).contiguous()
     return w1, w
+
+
+def pack_embed_tc(seq, first=0):
+    """Tensor-core packs of a TubeNet embedding MLP (nn.Sequential of Linear / ReLU): ([split weight per Linear from
+    ``first``], host tensor of their biases back to back)."""
+    lin = [m for m in seq if hasattr(m, "weight")][first:]
+    return [split_tf32(m.weight) for m in lin], torch.cat([m.bias.detach().float().reshape(-1) for m in lin]).cpu().contiguous()
