@@ -171,6 +171,15 @@ int pcab_apply_seg_pose(const float* points, const int* seg, const float* pose, 
                         pcab_stream_t stream);
 int pcab_scatter_rows3(const float* src, const int* idx, int k, float* dst, pcab_stream_t stream);
 
+/* ---- evaluation tail: libs/tester.py:58-88, toolbox/register_utils.py:59-93, toolbox/sf_eval_utils.py:46-52,71-100,
+ *      libs/loss.py:17-48,139-149 ------------------------------------------------------------ */
+int pcab_flow_eval(const float* input_points, const int* time_idx, const float* rec_est, const float* ego_motion_gt /* [T,4,4] */,
+                   const long long* inst_labels, const float* inst_motion_gt /* [K,T,4,4] */, int n_instances,
+                   const long long* fb_labels, const long long* sd_labels, const float* mos_est /* [N,2] */,
+                   const long long* fb_est_per_point, int n_points, int n_frames, float* epe_out /* [N] */,
+                   float* rel_out /* [N] */, double* sf_counters /* [3][6], accumulated */,
+                   long long* mos_counters /* [8], accumulated */, pcab_stream_t stream);
+
 /* ---- Chamfer distance: chamfer_distance/chamfer_distance.cpp:27-56 (forward_cuda / backward_cuda) --------- */
 size_t pcab_chamfer_workspace(int B, int n, int m);
 int pcab_chamfer_forward(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1, float* dist2,

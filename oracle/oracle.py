@@ -729,3 +729,51 @@ class OracleMotionNet:
             }, results)
             results["rec_est"][rec_mask] = results["sub_rec_est"]
         return results
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluation tail of the test loop.  TEST INFRASTRUCTURE like the rest of this file.
+# ------------------------------------------------------------------------------------------------
+def ego_motion_compensation(points, time_indice, tsfm):
+    """toolbox/register_utils.py:59-69."""
+    pt = tsfm[time_indice.long()]
+    return (torch.matmul(pt[:, :3, :3], points[:, :, None]) + pt[:, :3, 3][:, :, None]).squeeze(-1)
+
+
+def reconstruct_sequence(points, time_indice, inst_labels, tsfm, n_frames):
+    """toolbox/register_utils.py:72-93."""
+    pt = tsfm.view(-1, 4, 4)[(inst_labels.long() * n_frames + time_indice).long()]
+    return (torch.matmul(pt[:, :3, :3], points[:, :, None]) + pt[:, :3, 3][:, :, None]).squeeze(-1)
+
+
+def sf_counts(epe, rel):
+    """Counts behind toolbox/sf_eval_utils.py:71-88 (compute_sf_metrics_torch): n, sum EPE, Acc3DS, Acc3DR, Outlier, ROutlier."""
+    return [int(epe.numel()), float(epe.double().sum()),
+            int(torch.logical_or(epe < 0.05, rel < 0.05).sum()), int(torch.logical_or(epe < 0.1, rel < 0.1).sum()),
+            int(torch.logical_or(epe > 0.3, rel > 0.1).sum()), int(torch.logical_and(epe > 0.3, rel > 0.3).sum())]
+
+
+def flow_eval(input_dict, predictions, n_frames):
+    """libs/tester.py:58-88 for one scene (B = 1) + the category split of toolbox/sf_eval_utils.py:90-102 (restricted to the
+    points the tester keeps, ``time_indice > 0``) + the motion-segmentation IoU counters of libs/loss.py:17-48,139-149."""
+    pts = input_dict["input_points"].float()
+    t = input_dict["time_indice"][:, 1].long()
+    ego_gt = input_dict["ego_motion_gt"].float()[0]
+    inst_gt = input_dict["inst_motion_gt"][0].float()
+    inst = input_dict["inst_labels"][:, 0]
+    fb, sd = input_dict["fb_labels"][:, 0], input_dict["sd_labels"][:, 0]
+    rec_gt = reconstruct_sequence(ego_motion_compensation(pts, t, ego_gt), t, inst, inst_gt, n_frames)
+    err = (predictions["rec_est"] - pts) - (rec_gt - pts)
+    epe = torch.norm(err, p=2, dim=1)
+    rel = epe / (torch.norm(rec_gt - pts, p=2, dim=1) + 1e-20)
+    sel = t > 0
+    out = {"epe_per_point": epe, "relative_error": rel, "sel": sel,
+           "sf": {"all": sf_counts(epe[sel], rel[sel]), "dynamic": sf_counts(epe[sel & (sd == 1)], rel[sel & (sd == 1)]),
+                  "static": sf_counts(epe[sel & (fb == 1)], rel[sel & (fb == 1)])}}
+    mask = torch.logical_or(fb == 1, predictions["fb_est_per_points"][:, 0] == 1)
+    pred, gt = predictions["mos_est"].argmax(1)[mask], sd.long()[mask]
+    out["mos"] = {"masked": int(mask.sum()),
+                  "intersection": [int(((pred == c) & (gt == c)).sum()) for c in (0, 1)],
+                  "pred_positives": [int((pred == c).sum()) for c in (0, 1)],
+                  "gt_positives": [int((gt == c).sum()) for c in (0, 1)]}
+    return out

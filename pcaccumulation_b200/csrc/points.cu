@@ -289,7 +289,15 @@ __global__ void k_linear_rows(const float* __restrict__ X, int R, int IN, int OU
     int r = (int)(e / OUT), o = (int)(e % OUT);
     const float* x = X + (size_t)r * IN;
     float a = 0.f;
-    for (int k = 0; k < IN; ++k) a = fmaf(x[k], W[(size_t)k * OUT + o], a);
+    const float* w = W + o;
+#pragma unroll 1
+    for (int k0 = 0; k0 < IN; k0 += 16) {  // IN is a multiple of 16 for every layer of the regressor
+      float xv[16], wv[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) xv[u] = x[k0 + u], wv[u] = w[(size_t)(k0 + u) * OUT];  // 32 independent loads in flight
+#pragma unroll
+      for (int u = 0; u < 16; ++u) a = fmaf(xv[u], wv[u], a);
+    }
     a += b[o];
     if (scale) a = fmaf(a, scale[o], shift[o]);
     Y[e] = relu ? fmaxf(a, 0.f) : a;

@@ -1,0 +1,76 @@
+"""Evaluation tail of the reference's test loop on the GPU.
+
+Mirrors ``libs/tester.py:58-107``: per-point end-point error and relative error of the accumulated cloud against the
+ground-truth accumulation (``ego_motion_compensation`` + ``reconstruct_sequence`` with the GT instance motions,
+``toolbox/register_utils.py:59-93``), restricted to ``time_indice > 0``, plus the motion-segmentation IoU counters
+(``libs/loss.py:17-48,139-149``) and the scene-flow threshold metrics of ``toolbox/sf_eval_utils.py:46-52,71-100``.
+One fused kernel per scene (``pcab_flow_eval``) instead of a dozen full-size torch ops and five host copies; the
+counters stay on the device until ``summary()``.
+"""
+import numpy as np
+import torch
+
+from . import _lib as L
+from ._lib import I, P, call, stream
+
+CATEGORIES = ("all", "dynamic", "static")
+SF_KEYS = ("EPE3D", "Acc3DS", "Acc3DR", "Outlier", "ROutlier")
+
+
+class FlowEvaluator:
+    def __init__(self, n_frames, device="cuda", keep_per_point=True):
+        self.n_frames = int(n_frames)
+        self.device = torch.device(device)
+        self.sf = torch.zeros(3, 6, dtype=torch.float64, device=self.device)
+        self.mos = torch.zeros(8, dtype=torch.int64, device=self.device)
+        self.keep_per_point = keep_per_point
+        self.dump = {k: [] for k in ("epe_per_point", "relative_error", "time_indice", "fb_label", "sd_label")}
+
+    @torch.no_grad()
+    def update(self, input_dict, predictions):
+        """One scene (batch size 1, as ``libs/tester.py``).  Returns the per-point (epe, relative_error) device tensors."""
+        dev = self.device
+        pts = input_dict["input_points"].to(dev).float().contiguous()
+        n = pts.shape[0]
+        fast = input_dict.get("_pcab")
+        tidx = fast["ptime"] if fast is not None else input_dict["time_indice"][:, 1].to(dev).to(torch.int32).contiguous()
+        ego_gt = input_dict["ego_motion_gt"].to(dev).float()[0].contiguous()
+        inst_gt = input_dict["inst_motion_gt"][0].to(dev).float().contiguous()
+        i64 = lambda t: t.to(dev).reshape(-1).to(torch.int64).contiguous()
+        inst, fb, sd = i64(input_dict["inst_labels"]), i64(input_dict["fb_labels"]), i64(input_dict["sd_labels"])
+        rec = predictions["rec_est"].float().contiguous()
+        mos_est = predictions["mos_est"].float().contiguous()
+        fb_est = i64(predictions["fb_est_per_points"])
+        epe = torch.empty(n, device=dev)
+        rel = torch.empty(n, device=dev)
+        call("pcab_flow_eval", P(pts), P(tidx), P(rec), P(ego_gt), P(inst), P(inst_gt), I(inst_gt.shape[0]), P(fb), P(sd),
+             P(mos_est), P(fb_est), I(n), I(self.n_frames), P(epe), P(rel), P(self.sf), P(self.mos), stream())
+        if self.keep_per_point:  # what libs/tester.py:81-85 appends (fp16 errors, int8 / bool labels), gathered on the device
+            sel = tidx > 0
+            self.dump["epe_per_point"].append(epe[sel].to(torch.float16))
+            self.dump["relative_error"].append(rel[sel].to(torch.float16))
+            self.dump["time_indice"].append(tidx[sel].to(torch.int8))
+            self.dump["fb_label"].append(fb[sel] != 0)
+            self.dump["sd_label"].append(sd[sel] != 0)
+        return epe, rel
+
+    def per_point_arrays(self):
+        """The dict ``libs/tester.py:99-107`` saves with ``np.savez_compressed`` (one host copy per array, at the end)."""
+        return {k: (torch.cat(v).cpu().numpy() if v else np.zeros(0)) for k, v in self.dump.items()}
+
+    def summary(self):
+        sf = self.sf.cpu().numpy()
+        mos = self.mos.cpu().numpy()
+        out = {}
+        for c, name in enumerate(CATEGORIES):
+            n = max(sf[c, 0], 1.0)
+            out[name] = {"count": int(sf[c, 0]), "EPE3D": sf[c, 1] / n, "Acc3DS": sf[c, 2] / n, "Acc3DR": sf[c, 3] / n,
+                         "Outlier": sf[c, 4] / n, "ROutlier": sf[c, 5] / n}
+        inter = np.array([mos[0], mos[3]], dtype=np.float64)
+        pred = np.array([mos[1], mos[4]], dtype=np.float64)
+        gt = np.array([mos[2], mos[5]], dtype=np.float64)
+        union = pred + gt - inter
+        out["mos"] = {"intersection": inter, "union": union, "pred_positives": pred, "gt_positives": gt,
+                      "iou": inter / np.maximum(union, 1.0), "recall": inter / np.maximum(gt, 1.0),
+                      "precision": inter / np.maximum(pred, 1.0), "masked_points": int(mos[6])}
+        return out

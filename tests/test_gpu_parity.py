@@ -699,3 +699,59 @@ def test_stpn_head_tensor_core_matches_fp32_head(fixture_weights, n_fg):
     for a, b in zip(outs[0], outs[1]):
         assert_close_rel(b[sel], a[sel], 2e-5, "tensor-core head")
         assert bool((b[rest] == 7.0).all()), "rows outside fg_idx must not be written"
+
+
+# -------------------------------------------------------------------------------------------------------------
+# evaluation tail
+# -------------------------------------------------------------------------------------------------------------
+def test_flow_evaluator_matches_oracle(fixture_weights):
+    """pcab_flow_eval against the restatement of libs/tester.py:58-88 / sf_eval_utils / compute_iou on a scene with moving
+    instances; per-point errors to 1e-5, integer counters exactly (thresholds are applied to the kernel's own errors)."""
+    from oracle import oracle
+    from pcaccumulation_b200 import config, synth
+    from pcaccumulation_b200.evaluation import FlowEvaluator
+
+    cfg = config.workload_config("C1")
+    T = cfg["voxel_generator"]["n_sweeps"]
+    s = synth.make_workload_scene("C1", 21)
+    p4 = np.concatenate((s["input_points"], s["time_indice"]), 1).astype(np.float32)
+    vg = cfg["voxel_generator"]
+    s.update(oracle.voxelize(p4, vg["voxel_size"], vg["range"], T))
+    inp = synth.collate([s])
+    n = inp["input_points"].shape[0]
+    g = torch.Generator().manual_seed(3)
+    # predictions: the GT accumulation with errors spread over five decades so every threshold of the metrics is exercised
+    t = inp["time_indice"][:, 1].long()
+    rec_gt = oracle.reconstruct_sequence(oracle.ego_motion_compensation(inp["input_points"].float(), t, inp["ego_motion_gt"].float()[0]),
+                                         t, inp["inst_labels"][:, 0], inp["inst_motion_gt"][0].float(), T)
+    noise = torch.randn(n, 3, generator=g) * (10.0 ** torch.empty(n, 1).uniform_(-4, 0.5, generator=g))
+    pred = {"rec_est": (rec_gt + noise).float(), "mos_est": torch.randn(n, 2, generator=g),
+            "fb_est_per_points": (torch.rand(n, 1, generator=g) < 0.3).long()}
+    assert int((inp["sd_labels"] == 1).sum()) > 100 and int(inp["inst_labels"].max()) >= 3
+    ref = oracle.flow_eval(inp, pred, T)
+    ev = FlowEvaluator(T)
+    epe, rel = ev.update(cuda_dict(inp), {k: v.cuda() for k, v in pred.items()})
+    assert float((epe.cpu() - ref["epe_per_point"]).abs().max()) <= 1e-5 * max(1.0, float(ref["epe_per_point"].max()))
+    big = ref["relative_error"] < 1e6  # a static point has |gt flow| ~ 1e-7: its relative error is the ratio of two roundings
+    assert float(((rel.cpu() - ref["relative_error"]).abs() / ref["relative_error"].clamp(min=1e-3))[big].max()) < 1e-2
+    sel = ref["sel"]
+    fb, sd = inp["fb_labels"][:, 0], inp["sd_labels"][:, 0]
+    own = {"all": oracle.sf_counts(epe.cpu()[sel], rel.cpu()[sel]),
+           "dynamic": oracle.sf_counts(epe.cpu()[sel & (sd == 1)], rel.cpu()[sel & (sd == 1)]),
+           "static": oracle.sf_counts(epe.cpu()[sel & (fb == 1)], rel.cpu()[sel & (fb == 1)])}
+    sf = ev.sf.cpu().numpy()
+    for c, name in enumerate(("all", "dynamic", "static")):
+        want = own[name]
+        assert [int(sf[c, 0])] + [int(v) for v in sf[c, 2:]] == [want[0]] + want[2:], name
+        assert abs(sf[c, 1] - want[1]) <= 1e-6 * max(1.0, want[1]), name
+        # and against the oracle's own errors: only points within rounding of a threshold may differ
+        assert all(abs(int(a) - int(b)) <= 5 for a, b in zip([sf[c, 0]] + list(sf[c, 2:]), [ref["sf"][name][0]] + ref["sf"][name][2:])), name
+    mos = ev.mos.cpu().numpy()
+    assert int(mos[6]) == ref["mos"]["masked"]
+    for c in (0, 1):
+        assert [int(mos[3 * c]), int(mos[3 * c + 1]), int(mos[3 * c + 2])] == \
+            [ref["mos"]["intersection"][c], ref["mos"]["pred_positives"][c], ref["mos"]["gt_positives"][c]]
+    summ = ev.summary()
+    assert 0.0 <= summ["all"]["Acc3DS"] <= summ["all"]["Acc3DR"] <= 1.0 and summ["mos"]["masked_points"] == ref["mos"]["masked"]
+    arrays = ev.per_point_arrays()
+    assert arrays["epe_per_point"].dtype == np.float16 and arrays["epe_per_point"].shape[0] == int(sel.sum())
