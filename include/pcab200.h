@@ -171,6 +171,14 @@ int pcab_apply_seg_pose(const float* points, const int* seg, const float* pose, 
                         pcab_stream_t stream);
 int pcab_scatter_rows3(const float* src, const int* idx, int k, float* dst, pcab_stream_t stream);
 
+/* ---- data front-end: libs/dataset.py:163-207 steps 2-4 (crop, ground removal) ------------- */
+size_t pcab_prep_points_workspace(int n_points);
+int pcab_prep_points(const float* raw_points /* [N,3] */, const long long* time_idx, const long long* sd_labels,
+                     const long long* fb_labels, const long long* inst_labels, int n_points, float crop_xy, float crop_z_min,
+                     float crop_z_max, int remove_ground, float ground_height /* incl. slack */, float* points4_out /* [N,4] */,
+                     int* time_out, long long* sd_out, long long* fb_out, long long* inst_out, int* count_out /* device */,
+                     void* workspace, size_t workspace_bytes, pcab_stream_t stream);
+
 /* ---- evaluation tail: libs/tester.py:58-88, toolbox/register_utils.py:59-93, toolbox/sf_eval_utils.py:46-52,71-100,
  *      libs/loss.py:17-48,139-149 ------------------------------------------------------------ */
 int pcab_flow_eval(const float* input_points, const int* time_idx, const float* rec_est, const float* ego_motion_gt /* [T,4,4] */,

@@ -777,3 +777,25 @@ def flow_eval(input_dict, predictions, n_frames):
                   "pred_positives": [int((pred == c).sum()) for c in (0, 1)],
                   "gt_positives": [int((gt == c).sum()) for c in (0, 1)]}
     return out
+
+
+def prep_input_test_mode(raw_points, time_indice, sd_labels, fb_labels, inst_labels, cfg):
+    """libs/dataset.py:163-207, steps 2-4 of ``BaseDataset.prep_input`` (no augmentation): crop, ground removal, voxelise."""
+    vg, dc = cfg["voxel_generator"], cfg["data"]
+    crop_xy, z_min, z_max = vg["crop_range"]
+    ground = dc["ground_height"] + dc["ground_slack"]
+    sel_xy = np.logical_and(np.abs(raw_points[:, 0]) < crop_xy, np.abs(raw_points[:, 1]) < crop_xy)
+    sel_z = np.logical_and(raw_points[:, 2] < z_max, raw_points[:, 2] > z_min)
+    sel = np.logical_and(sel_xy, sel_z)
+    raw_points, time_indice = raw_points[sel], time_indice[sel]
+    sd_labels, fb_labels, inst_labels = sd_labels[sel], fb_labels[sel], inst_labels[sel]
+    if dc["remove_ground"]:
+        ng = raw_points[:, 2] > ground
+        raw_points, time_indice = raw_points[ng], time_indice[ng]
+        sd_labels, fb_labels, inst_labels = sd_labels[ng], fb_labels[ng], inst_labels[ng]
+    points = np.concatenate((raw_points, time_indice[:, None]), axis=1).astype(np.float32)
+    data = {"input_points": raw_points, "num_points": np.array([raw_points.shape[0]], dtype=np.int64),
+            "time_indice": time_indice[:, None], "sd_labels": sd_labels[:, None], "inst_labels": inst_labels[:, None],
+            "fb_labels": fb_labels[:, None]}
+    data.update(voxelize(points, vg["voxel_size"], vg["range"], vg["n_sweeps"]))
+    return data

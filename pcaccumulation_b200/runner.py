@@ -68,6 +68,39 @@ class SceneRunner:
             d["point_to_voxel_map"] = v["point_to_voxel_map"].to(torch.int64)[:, None]
         return d
 
+    def prep_raw(self, sample):
+        """Steps 2-4 of ``libs/dataset.py:prep_input`` (test mode: no augmentation) on the device.
+
+        ``sample``: the arrays of one ``.npz`` file as CUDA tensors - ``raw_points`` f32 [N,3] and ``time_indice``,
+        ``sd_labels``, ``fb_labels``, ``inst_labels`` i64 [N].  Returns (points4 [M,4] f32, labels dict with [M,1] i64
+        tensors, M): scene crop + ground removal as one stable compaction.
+        """
+        from ._lib import F, I, P, Z, call, scratch, size, stream
+        dev = self.device
+        raw = sample["raw_points"].to(dev).float().contiguous()
+        n = raw.shape[0]
+        i64 = lambda k: sample[k].to(dev).reshape(-1).to(torch.int64).contiguous()
+        vg, dc = self.cfg["voxel_generator"], self.cfg["data"]
+        p4 = torch.empty(n, 4, device=dev)
+        t32 = torch.empty(n, dtype=torch.int32, device=dev)
+        outs = {k: torch.empty(n, dtype=torch.int64, device=dev) for k in ("sd_labels", "fb_labels", "inst_labels")}
+        count = torch.empty(1, dtype=torch.int32, device=dev)
+        ws = scratch(size("pcab_prep_points_workspace", I(n)), dev)
+        call("pcab_prep_points", P(raw), P(i64("time_indice")), P(i64("sd_labels")), P(i64("fb_labels")), P(i64("inst_labels")),
+             I(n), F(vg["crop_range"][0]), F(vg["crop_range"][1]), F(vg["crop_range"][2]), I(int(dc["remove_ground"])),
+             F(dc["ground_height"] + dc["ground_slack"]), P(p4), P(t32), P(outs["sd_labels"]), P(outs["fb_labels"]),
+             P(outs["inst_labels"]), P(count), P(ws), Z(ws.numel()), stream())
+        m = int(count.item())
+        return p4[:m], {k: v[:m, None] for k, v in outs.items()}, m
+
+    @torch.no_grad()
+    def run_raw(self, sample):
+        """Raw sample arrays (as stored by the reference's dataset writers) -> crop / ground removal -> voxelise -> forward."""
+        p4, labels, m = self.prep_raw(sample)
+        ego = sample["ego_motion_gt"].to(self.device).float()[None].contiguous()
+        inst_motion = [sample["inst_motion_gt"].to(self.device).float()] if "inst_motion_gt" in sample else None
+        return self.model(self.build_input(p4, [m], labels=labels, ego_motion_gt=ego, inst_motion_gt=inst_motion))
+
     def warmup(self, batch_size=1):
         """Capture the model's CUDA graphs (see ``MotionNet.warmup``); call after loading weights, before serving."""
         self.model.warmup(batch_size)

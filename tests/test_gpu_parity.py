@@ -755,3 +755,56 @@ def test_flow_evaluator_matches_oracle(fixture_weights):
     assert 0.0 <= summ["all"]["Acc3DS"] <= summ["all"]["Acc3DR"] <= 1.0 and summ["mos"]["masked_points"] == ref["mos"]["masked"]
     arrays = ev.per_point_arrays()
     assert arrays["epe_per_point"].dtype == np.float16 and arrays["epe_per_point"].shape[0] == int(sel.sum())
+
+
+# -------------------------------------------------------------------------------------------------------------
+# data front-end
+# -------------------------------------------------------------------------------------------------------------
+def test_prep_raw_matches_dataset_prep_input(fixture_weights):
+    """Device crop + ground removal + voxelisation against libs/dataset.py:163-207 (oracle restatement), bit-exact, incl. points
+    exactly on the crop / ground thresholds and an empty result."""
+    from oracle import oracle
+    from pcaccumulation_b200 import config, synth
+    from pcaccumulation_b200.runner import SceneRunner
+
+    cfg = config.workload_config("C1")
+    vg, dc = cfg["voxel_generator"], cfg["data"]
+    s = synth.make_workload_scene("C1", 31)
+    rng = np.random.default_rng(9)
+    pts, t = s["input_points"].astype(np.float32), s["time_indice"][:, 0].astype(np.int64)
+    n0 = pts.shape[0]
+    ground = np.float32(dc["ground_height"] + dc["ground_slack"])
+    # add ground returns, points outside the crop box and points exactly ON every threshold (strict comparisons drop them)
+    extra = np.concatenate([
+        np.stack([rng.uniform(-31, 31, 4000), rng.uniform(-31, 31, 4000), rng.uniform(-1.5, float(ground), 4000)], 1),
+        np.stack([rng.uniform(-40, 40, 3000), rng.uniform(-40, 40, 3000), rng.uniform(-3, 8, 3000)], 1),
+        np.array([[vg["crop_range"][0], 0, 1], [0, -vg["crop_range"][0], 1], [1, 1, vg["crop_range"][2]], [1, 1, ground],
+                  [1, 1, np.nextafter(ground, np.float32(10))]]),
+    ]).astype(np.float32)
+    ne = extra.shape[0]
+    raw = np.concatenate([pts, extra])
+    tt = np.concatenate([t, rng.integers(0, vg["n_sweeps"], ne)])
+    lab = {k: np.concatenate([s[k][:, 0].astype(np.int64), np.zeros(ne, np.int64)]) for k in ("sd_labels", "fb_labels", "inst_labels")}
+    order = np.argsort(tt, kind="stable")
+    perm = np.concatenate([rng.permutation(np.nonzero(tt == f)[0]) for f in range(vg["n_sweeps"])])  # shuffled inside each frame
+    raw, tt = raw[perm], tt[perm]
+    lab = {k: v[perm] for k, v in lab.items()}
+    ref = oracle.prep_input_test_mode(raw, tt, lab["sd_labels"], lab["fb_labels"], lab["inst_labels"], cfg)
+    assert 0 < ref["input_points"].shape[0] < raw.shape[0] - 5000
+    runner = SceneRunner(cfg)
+    sample = {"raw_points": torch.tensor(raw).cuda(), "time_indice": torch.tensor(tt).cuda(),
+              **{k: torch.tensor(v).cuda() for k, v in lab.items()}}
+    p4, labels, m = runner.prep_raw(sample)
+    assert m == ref["input_points"].shape[0]
+    assert np.array_equal(p4[:, :3].cpu().numpy(), ref["input_points"])
+    assert np.array_equal(p4[:, 3].cpu().numpy().astype(np.int64), ref["time_indice"][:, 0])
+    for k in ("sd_labels", "fb_labels", "inst_labels"):
+        assert np.array_equal(labels[k].cpu().numpy(), ref[k]), k
+    d = runner.build_input(p4, [m], labels=labels, reference_schema=True)
+    assert np.array_equal(d["coordinates"][:, 1:].cpu().numpy().astype(np.int32), ref["coordinates"])
+    assert np.array_equal(d["point_to_voxel_map"].cpu().numpy(), ref["point_to_voxel_map"])
+    # nothing survives: empty, not an error
+    far = {k: v.clone() for k, v in sample.items()}
+    far["raw_points"] = far["raw_points"] + 1000.0
+    p4e, _, me = runner.prep_raw(far)
+    assert me == 0 and p4e.shape == (0, 4)
