@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="force the FP32 CUDA-core convolution path")
-    ap.add_argument("--in-flight", type=int, default=3, help="independent scenes kept in flight per GPU (1 = serial)")
+    ap.add_argument("--in-flight", type=int, default=4, help="independent scenes kept in flight per GPU (1 = serial)")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
