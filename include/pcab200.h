@@ -82,6 +82,12 @@ int pcab_conv3x3_tc(const float* src0, int c0, const float* src1, int c1, const 
                     const float* weight_tc_packed, const float* bias, const float* bn_scale, const float* bn_shift,
                     int relu, float* out, int n_images, int H, int W, int Cout, int out_cstride, int out_coff,
                     pcab_stream_t stream);
+/* the same with fp16-pair operands (kind::f16): weights as fp16 [2][Cout][9*cin/32][64] (32 used per group), pre-multiplied by
+ * 1/weight_scale_inv (a power of two) */
+int pcab_conv3x3_tc_f16(const float* src0, int c0, const float* src1, int c1, const float* src2, int c2, int temporal_T,
+                        const void* weight_f16_packed, float weight_scale_inv, const float* bias, const float* bn_scale,
+                        const float* bn_shift, int relu, float* out, int n_images, int H, int W, int Cout, int out_cstride,
+                        int out_coff, pcab_stream_t stream);
 
 /* ---- heads / BEV ops: models/motionnet.py:45-135,167-170,188-194 ------------------------------------------ */
 int pcab_head2_conv(const float* in_nhwc, int cin, const float* weight_packed /* [9][cin][2] */, const float* bias,

@@ -17,6 +17,7 @@
 // plane lands.  Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = a_lo split and
 // epilogue (tcgen05.ld -> bias/BN/ReLU -> NHWC global stores).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "pcab200.h"
@@ -289,6 +290,7 @@ struct Args {
   int relu;
   int out_cstride, out_coff;
   int store32;  // output rows are 32 B aligned: 256-bit stores
+  float wscale_inv;  // fp16-pair operands: the weights were scaled by a power of two on the host; 1 for the tf32 operands
   const float* bias;
   const float* bn_scale;
   const float* bn_shift;
@@ -332,7 +334,12 @@ __device__ __forceinline__ bool src_valid(const Args& a, int s, int tframe) {
   return a.T <= 1 || (tframe + s - 1 >= 0 && tframe + s - 1 < a.T);
 }
 
-template <int C>
+// F16 = false: 3xTF32 (A = the raw FP32 plane + a residual plane, kind::tf32, K = 8 per MMA).
+// F16 = true : the same three products with both operands split into fp16 PAIRS (x = h + l, h = fp16(x), l = fp16(x - h); 22
+//   significant bits, products exact in FP32): the splitter packs [32 ch h | 32 ch l] into ONE 128-byte row per pixel, the
+//   MMAs run kind::f16 (K = 16 per MMA: half as many MMAs for the same bytes per MMA, i.e. half the tensor-pipe and
+//   shared-memory-operand time per chunk).  Weights arrive pre-split as fp16 rows of 64 (32 used) per 32-channel group.
+template <int C, bool F16>
 __global__ void __launch_bounds__(kThreads2, 1)
 k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
               const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b, Args a) {
@@ -415,7 +422,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_a0, const __grid_constant_
                 if (a.dbg & 4) continue;
                 if (wg >= kWStages) mbar_wait(bar_w_free + 8 * ws, ((wg / kWStages) - 1) & 1);
                 mbar_expect_tx(bar_w_full + 8 * ws, kWBytes);
-                const int k0 = kbase_src + tap * Cs + c0;
+                const int k0 = (kbase_src + tap * Cs + c0) * (F16 ? 2 : 1);  // fp16 rows: 64 elements per 32-channel group
                 tma_load_2d(&map_b, w0 + ws * kWBytes, bar_w_full + 8 * ws, k0, t.co0);
                 tma_load_2d(&map_b, w0 + ws * kWBytes + C * 128u, bar_w_full + 8 * ws, k0, a.Cout + t.co0);
               }
@@ -434,7 +441,8 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_a0, const __grid_constant_
     // lane per warp runs the whole chunk (9 taps, fully unrolled: tap offsets, weight stage and parity are literals).
     const int mi = warp - 14;
     if (mi < a.mt) {
-      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
+      const uint32_t idesc_base = F16 ? ((1u << 4) | ((128u >> 4) << 24))  // D = F32, A = B = F16
+                                      : ((1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24));
       const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * C) >> 3) << 17);
       const uint32_t idesc1 = idesc_base | ((uint32_t)(C >> 3) << 17);
       const uint32_t sbo_a = a.strip ? (uint32_t)a.Wp * 8u : 64u;  // stride between 8-row groups, in 16 B units
@@ -473,13 +481,25 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_a0, const __grid_constant_
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               const uint32_t shift16 = (uint32_t)(tap / 3) * wp8 + (uint32_t)(tap % 3) * 8u;
               const uint32_t b16 = b_base + (uint32_t)ws * (kWBytes >> 4);
+              if (F16) {
+                // packed plane (the "lo" buffers): bytes 0-63 of a row = h halves (k-steps 0, 1), bytes 64-127 = l halves
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t dah = desc_hi_a | (ah + shift16 + 2u * kk);
-                const uint64_t dal = desc_hi_a | (al + shift16 + 2u * kk);
-                const uint64_t db = desc_hi_b | (b16 + 2u * kk);
-                umma_tf32(tmem_d, dah, db, idesc2, (tap == 0 && kk == 0) ? 0u : 1u);  // [a_hi*w_hi | a_hi*w_lo]
-                umma_tf32(tmem_d + (uint32_t)C, dal, db, idesc1, 1u);                // += a_lo*w_hi into the second half
+                for (int kk = 0; kk < 2; ++kk) {
+                  const uint64_t dah = desc_hi_a | (al + shift16 + 2u * kk);
+                  const uint64_t dal = desc_hi_a | (al + shift16 + 4u + 2u * kk);
+                  const uint64_t db = desc_hi_b | (b16 + 2u * kk);
+                  umma_f16(tmem_d, dah, db, idesc2, (tap == 0 && kk == 0) ? 0u : 1u);  // [a_h*w_h | a_h*w_l]
+                  umma_f16(tmem_d + (uint32_t)C, dal, db, idesc1, 1u);                // += a_l*w_h into the second half
+                }
+              } else {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint64_t dah = desc_hi_a | (ah + shift16 + 2u * kk);
+                  const uint64_t dal = desc_hi_a | (al + shift16 + 2u * kk);
+                  const uint64_t db = desc_hi_b | (b16 + 2u * kk);
+                  umma_tf32(tmem_d, dah, db, idesc2, (tap == 0 && kk == 0) ? 0u : 1u);  // [a_hi*w_hi | a_hi*w_lo]
+                  umma_tf32(tmem_d + (uint32_t)C, dal, db, idesc1, 1u);                // += a_lo*w_hi into the second half
+                }
               }
               umma_commit(bar_w_free + 8 * ws);
             }
@@ -520,6 +540,31 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_a0, const __grid_constant_
         const long long ts0 = st_on ? clock64() : 0;
         const uint32_t hi = hi0 + st * kPlaneBytes, lo = lo0 + st * kPlaneBytes;
         int i = (a.dbg & 1) ? n_f4 : et;
+        if (F16) {
+          // 16-byte chunk i of the TMA plane = row i>>3, physical chunk i&7 = channels 4q..4q+3 with q = (i&7) ^ (row&7)
+          // (128B swizzle).  Its h halves go to logical chunk q>>1 (byte (q&1)*8), its l halves to logical chunk 4 + (q>>1).
+          auto pack = [&](int ii, const float4& v) {
+            const uint32_t row = (uint32_t)ii >> 3, sw = row & 7u, q = ((uint32_t)ii & 7u) ^ sw;
+            const float x0 = fminf(fmaxf(v.x, -65504.f), 65504.f), x1 = fminf(fmaxf(v.y, -65504.f), 65504.f);
+            const float x2 = fminf(fmaxf(v.z, -65504.f), 65504.f), x3 = fminf(fmaxf(v.w, -65504.f), 65504.f);
+            const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+            const uint32_t base = lo + row * 128u + (q & 1u) * 8u;
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + (((q >> 1) ^ sw) << 4)),
+                         "r"(*reinterpret_cast<const uint32_t*>(&h01)), "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + (((4u + (q >> 1)) ^ sw) << 4)),
+                         "r"(*reinterpret_cast<const uint32_t*>(&l01)), "r"(*reinterpret_cast<const uint32_t*>(&l23)) : "memory");
+          };
+          for (; i + 7 * 128 < n_f4; i += 1024) {  // eight independent 128-bit loads in flight per thread
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = lds128(hi + 16u * (i + 128 * u));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pack(i + 128 * u, v[u]);
+          }
+          for (; i < n_f4; i += 128) pack(i, lds128(hi + 16u * i));
+        }
         for (; i + 7 * 128 < n_f4; i += 1024) {  // eight independent 128-bit loads in flight per thread
           float4 v[8];
 #pragma unroll
@@ -614,7 +659,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_a0, const __grid_constant_
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + cbase + 8 * q + 4));
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int u = 0; u < 8; ++u) o[u] = acc[mi][8 * q + u] + bb[u];
+              for (int u = 0; u < 8; ++u) o[u] = fmaf(acc[mi][8 * q + u], a.wscale_inv, bb[u]);  // wscale_inv = 1: plain add
               if (a.bn_scale) {
                 const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.bn_scale + cbase + 8 * q));
                 const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.bn_scale + cbase + 8 * q + 4));
@@ -816,9 +861,9 @@ extern "C" size_t pcab_conv3x3_tc_pack_floats(int cin_total, int Cout) { return 
 
 namespace {
 int conv3x3_tc_v2(EncodeTiledFn enc, const float* src0, int c0, const float* src1, int c1, const float* src2, int c2,
-                  int temporal_T, const float* weight_tc_packed, const float* bias, const float* bn_scale,
+                  int temporal_T, const void* weight_tc_packed, const float* bias, const float* bn_scale,
                   const float* bn_shift, int relu, float* out, int n_images, int H, int W, int Cout, int out_cstride,
-                  int out_coff, cudaStream_t stream) {
+                  int out_coff, cudaStream_t stream, bool f16 = false, float wscale_inv = 1.f) {
   v2::Cfg cfg;
   PCAB_REQUIRE(v2::choose(n_images, H, W, Cout, &cfg), "unsupported shape");
   PCAB_REQUIRE(out_cstride % 4 == 0 && out_coff % 4 == 0 && ((uintptr_t)out & 15) == 0, "output channel layout must be 16B aligned");
@@ -850,14 +895,16 @@ int conv3x3_tc_v2(EncodeTiledFn enc, const float* src0, int c0, const float* src
     }
   }
   {
-    cuuint64_t K = (cuuint64_t)9 * cin_total;
+    // tf32: [2*Cout rows][K] fp32, box 32 x c (128 B rows).  fp16 pairs: [2*Cout rows][2K] fp16 (64 per 32-channel group, 32
+    // used), box 64 x c (128 B rows again)
+    cuuint64_t K = (cuuint64_t)9 * cin_total * (f16 ? 2 : 1);
     cuuint64_t dims[2] = {K, (cuuint64_t)2 * Cout};
-    cuuint64_t strides[1] = {K * 4};
-    cuuint32_t box[2] = {32, (cuuint32_t)cfg.c};
+    cuuint64_t strides[1] = {K * (f16 ? 2 : 4)};
+    cuuint32_t box[2] = {f16 ? 64u : 32u, (cuuint32_t)cfg.c};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&maps[3], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)weight_tc_packed, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(&maps[3], f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)weight_tc_packed,
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       pcab_set_error("pcab_conv3x3_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r);
       return PCAB_ERR_CUDA;
@@ -873,23 +920,47 @@ int conv3x3_tc_v2(EncodeTiledFn enc, const float* src0, int c0, const float* src
   a.tiles_x = cfg.tiles_x, a.tiles_y = cfg.tiles_y, a.n_ctile = cfg.n_ctile, a.total_items = cfg.total;
   a.relu = relu, a.out_cstride = out_cstride, a.out_coff = out_coff;
   a.bias = bias, a.bn_scale = bn_scale, a.bn_shift = bn_shift, a.out = out;
+  a.wscale_inv = wscale_inv;
   a.stats = g_stats;
   a.dbg = g_dbg;
   static bool configured = false;
   if (!configured) {
-    PCAB_CUDA(cudaFuncSetAttribute(v2::k_conv3x3_tc2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::smem_bytes(32)));
-    PCAB_CUDA(cudaFuncSetAttribute(v2::k_conv3x3_tc2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::smem_bytes(64)));
+    PCAB_CUDA(cudaFuncSetAttribute(v2::k_conv3x3_tc2<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::smem_bytes(32)));
+    PCAB_CUDA(cudaFuncSetAttribute(v2::k_conv3x3_tc2<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::smem_bytes(64)));
+    PCAB_CUDA(cudaFuncSetAttribute(v2::k_conv3x3_tc2<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::smem_bytes(32)));
+    PCAB_CUDA(cudaFuncSetAttribute(v2::k_conv3x3_tc2<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::smem_bytes(64)));
     configured = true;
   }
   const int grid = cfg.total < 148 ? cfg.total : 148;
-  if (cfg.c == 64)
-    v2::k_conv3x3_tc2<64><<<grid, v2::kThreads2, v2::smem_bytes(64), stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+  if (cfg.c == 64 && f16)
+    v2::k_conv3x3_tc2<64, true><<<grid, v2::kThreads2, v2::smem_bytes(64), stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+  else if (cfg.c == 64)
+    v2::k_conv3x3_tc2<64, false><<<grid, v2::kThreads2, v2::smem_bytes(64), stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+  else if (f16)
+    v2::k_conv3x3_tc2<32, true><<<grid, v2::kThreads2, v2::smem_bytes(32), stream>>>(maps[0], maps[1], maps[2], maps[3], a);
   else
-    v2::k_conv3x3_tc2<32><<<grid, v2::kThreads2, v2::smem_bytes(32), stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+    v2::k_conv3x3_tc2<32, false><<<grid, v2::kThreads2, v2::smem_bytes(32), stream>>>(maps[0], maps[1], maps[2], maps[3], a);
   PCAB_CHECK_LAUNCH("pcab_conv3x3_tc(v2)");
   return PCAB_OK;
 }
 }  // namespace
+
+// The same convolution with fp16-pair operands (kind::f16, twice the MMA rate of the tf32 formulation at the same accuracy
+// class).  weight_f16_packed: fp16 [2 (h, l)][Cout][9*cin_total/32][64] - per 32-channel group of the tf32 pack's K order 32 values
+// + 32 zeros - of the weights multiplied by 1/weight_scale_inv (a power of two that keeps the l halves out of the fp16
+// subnormals).  Activations beyond +-65504 saturate.
+extern "C" int pcab_conv3x3_tc_f16(const float* src0, int c0, const float* src1, int c1, const float* src2, int c2,
+                                   int temporal_T, const void* weight_f16_packed, float weight_scale_inv, const float* bias,
+                                   const float* bn_scale, const float* bn_shift, int relu, float* out, int n_images, int H,
+                                   int W, int Cout, int out_cstride, int out_coff, cudaStream_t stream) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    pcab_set_error("pcab_conv3x3_tc_f16: cuTensorMapEncodeTiled unavailable");
+    return PCAB_ERR_CUDA;
+  }
+  return conv3x3_tc_v2(enc, src0, c0, src1, c1, src2, c2, temporal_T, weight_f16_packed, bias, bn_scale, bn_shift, relu, out,
+                       n_images, H, W, Cout, out_cstride, out_coff, stream, true, weight_scale_inv);
+}
 
 extern "C" int pcab_conv3x3_tc(const float* src0, int c0, const float* src1, int c1, const float* src2, int c2,
                                int temporal_T, const float* weight_tc_packed, const float* bias, const float* bn_scale,

@@ -197,6 +197,7 @@ class _ConvLayer:
         self.bn = _bn_affine(bn) if bn is not None else (None, None)
         self.weight = w  # for the tensor-core pack (built lazily)
         self.tc_pack = None
+        self.tc_pack16 = None
         self.tc_ok = {}  # (H, W) -> does the tensor-core kernel take this layer at that map size
 
 
@@ -225,6 +226,9 @@ class MotionNet(nn.Module):
         self._packed_key = None
         self._plist = None
         self.use_tensor_cores = True
+        # operand format of the tensor-core convolutions: "f16" = fp16 pairs (kind::f16, activations saturate at +-65504),
+        # "tf32" = 3xTF32 (kind::tf32, full FP32 range, ~1.3x slower); both keep ~22 significant bits per operand
+        self.conv_operands = "f16"
         self.stages = {}  # stage-boundary tensors of the last forward (for stage-wise parity tests)
         self.keep_stages = False
         # stage-wise parity protocol: tensors placed here replace the computed value for the stages
@@ -415,7 +419,16 @@ class MotionNet(nn.Module):
             if tc_ok is None:
                 tc_ok = layer.tc_ok[(H, W_)] = bool(L.lib().pcab_conv3x3_tc_supported(
                     I(len(layer.splits)), I(c[0]), I(c[1]), I(c[2]), I(layer.cout), I(H), I(W_)))
-        if tc_ok:
+        if tc_ok and self.conv_operands == "f16":
+            if layer.tc_pack16 is None:
+                from .tc_pack import pack_conv_tc_f16
+                layer.tc_pack16 = pack_conv_tc_f16(layer)
+            from .tc_pack import F16_WEIGHT_SCALE
+            call("pcab_conv3x3_tc_f16", P(s[0]), I(c[0]), P(s[1]), I(c[1]), P(s[2]), I(c[2]), I(T if layer.temporal else 1),
+                 P(layer.tc_pack16), F(1.0 / F16_WEIGHT_SCALE), P(layer.bias), P(scale), P(shift), I(int(relu)), P(out), I(n_img),
+                 I(H), I(W_), I(layer.cout), I(layer.cout), I(0), stream())
+            path = "tc-f16pair"
+        elif tc_ok:
             if layer.tc_pack is None:
                 layer.tc_pack = self._pack_tc(layer)
             call("pcab_conv3x3_tc", P(s[0]), I(c[0]), P(s[1]), I(c[1]), P(s[2]), I(c[2]), I(T if layer.temporal else 1),

@@ -33,3 +33,19 @@ def pack_embed_tc(seq, first=0):
     ``first``], host tensor of their biases back to back)."""
     lin = [m for m in seq if hasattr(m, "weight")][first:]
     return [split_tf32(m.weight) for m in lin], torch.cat([m.bias.detach().float().reshape(-1) for m in lin]).cpu().contiguous()
+
+
+F16_WEIGHT_SCALE = 256.0  # power of two: keeps the l halves of O(0.01) weights out of the fp16 subnormals
+
+
+def pack_conv_tc_f16(layer):
+    """fp16-pair pack of a 3x3 convolution for ``pcab_conv3x3_tc_f16``: [2 (h, l)][Cout][K/32][64] fp16, the first 32 of every 64
+    = one 32-channel group of the tf32 pack's K order, the rest zero.  h = fp16(s*w), l = fp16(s*w - h)."""
+    k = layer.pack.numel() // layer.cout
+    w = layer.pack.view(k, layer.cout).t().contiguous() * F16_WEIGHT_SCALE  # [Cout][K]
+    h = w.half()
+    l = (w - h.float()).half()
+    out = torch.zeros(2, layer.cout, k // 32, 64, dtype=torch.float16, device=w.device)
+    out[0, :, :, :32] = h.view(layer.cout, k // 32, 32)
+    out[1, :, :, :32] = l.view(layer.cout, k // 32, 32)
+    return out.contiguous()

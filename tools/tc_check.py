@@ -60,7 +60,25 @@ for n, cs, cout, H, W, T in shapes:
         y64 = F.relu(F.conv2d(x64, w.double(), layer.bias.double(), padding=1) * sc.double()[None, :, None, None] + sh.double()[None, :, None, None])
         y64 = y64.permute(0, 2, 3, 1)
         print("   vs float64: f32 path err %.3e | tc path err %.3e" % ((ref.double() - y64).abs().max().item(), (out.double() - y64).abs().max().item()))
-    nan = torch.isnan(out).sum().item()
+    # fp16-pair operand variant
+    from pcaccumulation_b200._lib import F
+    out16 = torch.full((n, H, W, cout), float("nan"), device=dev)
+    w16 = tc_pack.pack_conv_tc_f16(layer)
+    args16 = lambda o: (P(srcs[0]), I(c3[0]), P(srcs[1]), I(c3[1]), P(srcs[2]), I(c3[2]), I(T), P(w16), F(1.0 / tc_pack.F16_WEIGHT_SCALE),
+                        P(layer.bias), P(sc), P(sh), I(1), P(o), I(n), I(H), I(W), I(cout), I(cout), I(0), stream())
+    call("pcab_conv3x3_tc_f16", *args16(out16))
+    torch.cuda.synchronize()
+    err16 = (out16 - ref).abs().max().item()
+    for _ in range(2):
+        call("pcab_conv3x3_tc_f16", *args16(out16))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        call("pcab_conv3x3_tc_f16", *args16(out16))
+    e1.record()
+    torch.cuda.synchronize()
+    t16 = e0.elapsed_time(e1) / 10
+    nan = torch.isnan(out).sum().item() + torch.isnan(out16).sum().item()
     flops = 2.0 * 9 * cin * cout * H * W * n * (1 if T == 1 else (3 * T - 2) / T)
     ts = {}
     for name, fn, pack, o in (("f32", "pcab_conv3x3_f32", layer.pack, ref), ("tc", "pcab_conv3x3_tc", tcw, out)):
@@ -90,4 +108,5 @@ for n, cs, cout, H, W, T in shapes:
         print("   stats (mean cycles per CTA, %d CTAs): " % int(act.sum()) + ", ".join(f"{nm}={m[i].item():.0f}" for i, nm in enumerate(names)),
               "| per chunk: total %.0f" % (m[7] / m[8]).item())
     print(f"n={n} cs={cs} cout={cout} {H}x{W} T={T}: maxerr {err:.3e} (ref max {ref.abs().max().item():.1f}) nan {nan} | "
-          f"f32 {ts['f32']:.3f} ms {flops / ts['f32'] / 1e9:.1f} TF/s | tc {ts['tc']:.3f} ms {flops / ts['tc'] / 1e9:.1f} TF/s")
+          f"f32 {ts['f32']:.3f} ms {flops / ts['f32'] / 1e9:.1f} TF/s | tc {ts['tc']:.3f} ms {flops / ts['tc'] / 1e9:.1f} TF/s | "
+          f"f16-pair maxerr {err16:.3e} {t16:.3f} ms {flops / t16 / 1e9:.1f} TF/s")
