@@ -350,7 +350,8 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_a0, const __grid_constant_
   const uint32_t bars = w0 + kWStages * kWBytes;
   // barrier slots (8 B each)
   const uint32_t bar_hi_full = bars, bar_plane_free = bars + 16, bar_lo_full = bars + 32, bar_w_full = bars + 48,
-                 bar_w_free = bars + 72, bar_acc_full = bars + 96, bar_acc_empty = bars + 112, tmem_slot = bars + 128;
+                 bar_w_free = bars + 72, bar_acc_full = bars + 96, bar_acc_empty = bars + 112, tmem_slot = bars + 128,
+                 bar_raw_free = bars + 136;  // fp16 pairs only: the TMA plane has been read by the split warps
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // warp-uniform for the compiler
   const uint32_t tmem_cols_needed = 4u * a.mt * C;  // 2 stages x mt tiles x [main c | corr c]
@@ -362,6 +363,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_a0, const __grid_constant_
       mbar_init(bar_hi_full + 8 * i, 1);
       mbar_init(bar_plane_free + 8 * i, a.mt);  // one tcgen05.commit per issuing warp
       mbar_init(bar_lo_full + 8 * i, 128);
+      mbar_init(bar_raw_free + 8 * i, 128);
       mbar_init(bar_acc_full + 8 * i, a.mt);
       mbar_init(bar_acc_empty + 8 * i, 256);
     }
@@ -398,7 +400,9 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_a0, const __grid_constant_
           for (int c0 = 0; c0 < a.src_c[s]; c0 += 32, ++g) {
             const int st = g & 1;
             if (a.dbg & 8) continue;
-            if (g >= 2) mbar_wait(bar_plane_free + 8 * st, ((g >> 1) - 1) & 1);
+            // tf32: the MMAs read this buffer (a_hi), it is free when they are done.  fp16 pairs: only the split warps read it,
+            // so the next plane can land while the MMAs of the previous chunk still run on the packed buffer.
+            if (g >= 2) mbar_wait((F16 ? bar_raw_free : bar_plane_free) + 8 * st, ((g >> 1) - 1) & 1);
             mbar_expect_tx(bar_hi_full + 8 * st, box_bytes);
             tma_load_4d(am, hi0 + st * kPlaneBytes, bar_hi_full + 8 * st, c0, t.x0 - 1, t.y0 - 1, img);
           }
@@ -545,16 +549,19 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_a0, const __grid_constant_
           // (128B swizzle).  Its h halves go to logical chunk q>>1 (byte (q&1)*8), its l halves to logical chunk 4 + (q>>1).
           auto pack = [&](int ii, const float4& v) {
             const uint32_t row = (uint32_t)ii >> 3, sw = row & 7u, q = ((uint32_t)ii & 7u) ^ sw;
-            const float x0 = fminf(fmaxf(v.x, -65504.f), 65504.f), x1 = fminf(fmaxf(v.y, -65504.f), 65504.f);
-            const float x2 = fminf(fmaxf(v.z, -65504.f), 65504.f), x3 = fminf(fmaxf(v.w, -65504.f), 65504.f);
-            const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
-            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-            const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+            // saturating conversions: beyond +-65504 h (and then l) clamp instead of becoming inf - inf
+            uint32_t uh01, uh23, ul01, ul23;
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(uh01) : "f"(v.y), "f"(v.x));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(uh23) : "f"(v.w), "f"(v.z));
+            const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&uh01));
+            const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&uh23));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(ul01) : "f"(v.y - f01.y), "f"(v.x - f01.x));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(ul23) : "f"(v.w - f23.y), "f"(v.z - f23.x));
             const uint32_t base = lo + row * 128u + (q & 1u) * 8u;
             asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + (((q >> 1) ^ sw) << 4)),
-                         "r"(*reinterpret_cast<const uint32_t*>(&h01)), "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
+                         "r"(uh01), "r"(uh23) : "memory");
             asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + (((4u + (q >> 1)) ^ sw) << 4)),
-                         "r"(*reinterpret_cast<const uint32_t*>(&l01)), "r"(*reinterpret_cast<const uint32_t*>(&l23)) : "memory");
+                         "r"(ul01), "r"(ul23) : "memory");
           };
           for (; i + 7 * 128 < n_f4; i += 1024) {  // eight independent 128-bit loads in flight per thread
             float4 v[8];
@@ -579,6 +586,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_a0, const __grid_constant_
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(bar_lo_full + 8 * st);
+        if (F16) mbar_arrive(bar_raw_free + 8 * st);
         if (st_on) c_work += clock64() - ts0;
       }
     }

@@ -808,3 +808,62 @@ def test_prep_raw_matches_dataset_prep_input(fixture_weights):
     far["raw_points"] = far["raw_points"] + 1000.0
     p4e, _, me = runner.prep_raw(far)
     assert me == 0 and p4e.shape == (0, 4)
+
+
+# -------------------------------------------------------------------------------------------------------------
+# tensor-core convolution: both operand formats against a float64 reference
+# -------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("operands", ["f16", "tf32"])
+@pytest.mark.parametrize("case", ["single", "concat", "temporal", "small_map", "large_values"])
+def test_conv3x3_tensor_core_operand_formats(lib, case, operands):
+    """pcab_conv3x3_tc (3xTF32) and pcab_conv3x3_tc_f16 (fp16 pairs) keep FP32-class accuracy: 1e-5 of the output scale
+    against float64, with bias / BatchNorm / ReLU epilogue, concatenated sources, the Conv3d formulation and ragged tiles."""
+    import types
+
+    from pcaccumulation_b200 import motionnet as mn, tc_pack
+    from pcaccumulation_b200._lib import F as Fl, I, P, call, stream
+
+    g = torch.Generator().manual_seed(11)
+    T = 1
+    if case == "single":
+        n, cs, cout, H, W = 2, [32], 64, 100, 76
+    elif case == "concat":
+        n, cs, cout, H, W = 2, [64, 32], 32, 40, 56
+    elif case == "temporal":
+        n, cs, cout, H, W, T = 6, [32], 32, 36, 44, 3
+    elif case == "small_map":
+        n, cs, cout, H, W = 1, [128], 128, 9, 9
+    else:
+        n, cs, cout, H, W = 1, [32], 32, 48, 48
+    cin = sum(cs)
+    scale_in = 3.0e3 if case == "large_values" else 1.0  # activations in the thousands: far from 1, still inside fp16 range
+    xs = [torch.randn(n, H, W, c, generator=g) * scale_in for c in cs]
+    bias = torch.randn(cout, generator=g)
+    sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    if T > 1:
+        w = torch.randn(cout, cs[0], 3, 3, 3, generator=g) * 0.1
+        layer = mn._ConvLayer(types.SimpleNamespace(weight=w.cuda(), bias=bias.cuda()), temporal=True)
+        x5 = xs[0].view(n // T, T, H, W, cs[0]).permute(0, 4, 1, 2, 3).double()
+        ref = F.conv3d(x5, w.double(), bias.double(), padding=1).permute(0, 2, 3, 4, 1).reshape(n, H, W, cout)
+        srcs, c3 = [xs[0].cuda()] * 3, [cs[0]] * 3
+    else:
+        w = torch.randn(cout, cin, 3, 3, generator=g) * 0.1
+        layer = mn._ConvLayer(types.SimpleNamespace(weight=w.cuda(), bias=bias.cuda()), splits=cs)
+        x4 = torch.cat(xs, 3).permute(0, 3, 1, 2).double()
+        ref = F.conv2d(x4, w.double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+        srcs, c3 = [x.cuda() for x in xs] + [None] * (3 - len(xs)), cs + [0] * (3 - len(cs))
+    ref = F.relu(ref * sc.double() + sh.double())
+    assert lib.lib().pcab_conv3x3_tc_supported(I(3 if T > 1 else len(cs)), I(c3[0]), I(c3[1]), I(c3[2]), I(cout), I(H), I(W))
+    out = torch.full((n, H, W, cout), float("nan"), device="cuda")
+    scd, shd = sc.cuda(), sh.cuda()
+    head = (P(srcs[0]), I(c3[0]), P(srcs[1]), I(c3[1]), P(srcs[2]), I(c3[2]), I(T))
+    tail = (P(layer.bias), P(scd), P(shd), I(1), P(out), I(n), I(H), I(W), I(cout), I(cout), I(0), stream())
+    if operands == "f16":
+        pack = tc_pack.pack_conv_tc_f16(layer)
+        call("pcab_conv3x3_tc_f16", *head, P(pack), Fl(1.0 / tc_pack.F16_WEIGHT_SCALE), *tail)
+    else:
+        pack = tc_pack.pack_conv_tc(layer)
+        call("pcab_conv3x3_tc", *head, P(pack), *tail)
+    torch.cuda.synchronize()
+    assert not bool(torch.isnan(out).any())
+    assert_close_rel(out, ref, 1e-5, f"{case}/{operands}")

@@ -98,7 +98,10 @@ for n, cs, cout, H, W, T in shapes:
     if "--stats" in sys.argv:
         st = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
         _lib.lib().pcab_conv3x3_tc_set_stats(P(st))
-        call("pcab_conv3x3_tc", *args(tcw, out))
+        if "--f16" in sys.argv:
+            call("pcab_conv3x3_tc_f16", *args16(out16))
+        else:
+            call("pcab_conv3x3_tc", *args(tcw, out))
         torch.cuda.synchronize()
         _lib.lib().pcab_conv3x3_tc_set_stats(P(None))
         s2 = st.view(148, 16).double()
