@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 from pcaccumulation_b200 import config, fixture, synth  # noqa: E402
 
 N_SCENES = 4  # distinct synthetic scenes cycled through the steps
-CONV_DRAM_BYTES_PER_LAUNCH = {"C2": 32.81e6}  # measured with ncu (profiles/r1_conv_dram.csv), see the roofline block below
+CONV_DRAM_BYTES_PER_LAUNCH = {"C2": 32.53e6}  # measured with ncu (profiles/r1_conv_dram.csv), see the roofline block below
 
 
 def env_int(name, default):
