@@ -54,6 +54,14 @@ class FlowEvaluator:
             self.dump["sd_label"].append(sd[sel] != 0)
         return epe, rel
 
+    def all_reduce(self):
+        """Sum the counters over the ranks of a scene-sharded run (the only collective of the path: a 26-number all-reduce,
+        NCCL on GPUs / gloo in the CPU tests).  The per-point dumps stay rank-local, as the reference's per-scene files do."""
+        from .dist_utils import reduce_metrics
+        self.sf = reduce_metrics(self.sf, op="sum")
+        self.mos = reduce_metrics(self.mos, op="sum")
+        return self
+
     def per_point_arrays(self):
         """The dict ``libs/tester.py:99-107`` saves with ``np.savez_compressed`` (one host copy per array, at the end)."""
         return {k: (torch.cat(v).cpu().numpy() if v else np.zeros(0)) for k, v in self.dump.items()}

@@ -134,3 +134,76 @@ def test_scene_sharding_and_metric_reduction_gloo_world2():
     assert res[0][1] == [0, 2, 4, 6] and res[1][1] == [1, 3, 5]
     for r in res:
         assert r[2] == [7.0, 21.0, 4.5] and r[3] == [20.0]
+
+
+def _gloo_eval_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from pcaccumulation_b200.evaluation import FlowEvaluator
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ev = FlowEvaluator(5, device="cpu", keep_per_point=False)  # counters only: no kernel call in this test
+    ev.sf += torch.arange(18, dtype=torch.float64).view(3, 6) * (rank + 1)
+    ev.mos += torch.arange(8) * (10 ** rank)
+    ev.all_reduce()
+    q.put((rank, ev.sf.tolist(), ev.mos.tolist(), ev.summary()["all"]["count"]))
+    dist.destroy_process_group()
+
+
+def test_flow_evaluator_counters_all_reduce_gloo_world2():
+    """The evaluation counters of a scene-sharded run are summed over the ranks."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_eval_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    want_sf = (torch.arange(18, dtype=torch.float64).view(3, 6) * 3).tolist()
+    want_mos = (torch.arange(8) * 11).tolist()
+    for r in res:
+        assert r[1] == want_sf and r[2] == want_mos and r[3] == 0
+
+
+def test_oracle_evaluation_tail_and_data_prep_properties():
+    """CPU-only checks of the two oracle restatements added for rows f2 / f3: a perfect prediction scores EPE 0 / accuracy 1,
+    and the crop + ground filter equals one explicit mask (libs/dataset.py:163-190)."""
+    from oracle import oracle
+    from pcaccumulation_b200 import config, synth
+
+    cfg = config.workload_config("C1")
+    vg, dc = cfg["voxel_generator"], cfg["data"]
+    T = vg["n_sweeps"]
+    s = synth.make_workload_scene("C1", 5, pts_per_frame=3000)
+    p4 = np.concatenate((s["input_points"], s["time_indice"]), 1).astype(np.float32)
+    s.update(oracle.voxelize(p4, vg["voxel_size"], vg["range"], T))
+    inp = synth.collate([s])
+    t = inp["time_indice"][:, 1].long()
+    pts = inp["input_points"].float()
+    rec_gt = oracle.reconstruct_sequence(oracle.ego_motion_compensation(pts, t, inp["ego_motion_gt"].float()[0]), t,
+                                         inp["inst_labels"][:, 0], inp["inst_motion_gt"][0].float(), T)
+    n = pts.shape[0]
+    pred = {"rec_est": rec_gt.clone(), "mos_est": torch.stack((1.0 - inp["sd_labels"][:, 0].float(), inp["sd_labels"][:, 0].float()), 1),
+            "fb_est_per_points": inp["fb_labels"].clone()}
+    ev = oracle.flow_eval(inp, pred, T)
+    assert float(ev["epe_per_point"].max()) == 0.0
+    n_sel = int((t > 0).sum())
+    assert ev["sf"]["all"] == [n_sel, 0.0, n_sel, n_sel, 0, 0]
+    m = ev["mos"]
+    assert m["intersection"] == m["pred_positives"] == m["gt_positives"] and sum(m["gt_positives"]) == m["masked"]
+    # frame 0 is the anchor: its points are their own accumulation
+    assert torch.equal(rec_gt[(t == 0) & (inp["inst_labels"][:, 0] == 0)], pts[(t == 0) & (inp["inst_labels"][:, 0] == 0)])
+    # data prep: one explicit float32 mask
+    rng = np.random.default_rng(0)
+    raw = rng.uniform(-40, 40, (5000, 3)).astype(np.float32)
+    raw[:, 2] = rng.uniform(-3, 8, 5000)
+    tt = np.sort(rng.integers(0, T, 5000))
+    lab = rng.integers(0, 2, 5000)
+    ref = oracle.prep_input_test_mode(raw, tt, lab, lab, lab, cfg)
+    g = np.float32(dc["ground_height"] + dc["ground_slack"])
+    keep = (np.abs(raw[:, 0]) < vg["crop_range"][0]) & (np.abs(raw[:, 1]) < vg["crop_range"][0]) & \
+        (raw[:, 2] < vg["crop_range"][2]) & (raw[:, 2] > vg["crop_range"][1]) & (raw[:, 2] > g)
+    assert np.array_equal(ref["input_points"], raw[keep]) and np.array_equal(ref["time_indice"][:, 0], tt[keep])
+    assert ref["point_to_voxel_map"].shape[0] == int(keep.sum()) and int(ref["num_points"][0]) == int(keep.sum())
