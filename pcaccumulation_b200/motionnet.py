@@ -387,7 +387,7 @@ class MotionNet(nn.Module):
         vg = self.cfg["voxel_generator"]
         Nx = int(round((vg["range"][3] - vg["range"][0]) / vg["voxel_size"][0]))
         Ny = int(round((vg["range"][4] - vg["range"][1]) / vg["voxel_size"][1]))
-        B, T, tc = int(batch_size), self.n_sweeps, self.use_tensor_cores
+        B, T, tc = int(batch_size), self.n_sweeps, (self.use_tensor_cores, self.conv_operands)
         with L.pinned_stream():
             W = self._weights()
             for name, fn in (("backbone", self._backbone_stack(W, B, T, Ny, Nx)), ("stpn", self._stpn_stack(W, B, T, Ny, Nx, dev))):
@@ -566,7 +566,7 @@ class MotionNet(nn.Module):
 
         self._mark("index+stats")
         # 1. pillar encoder -> BEV canvas
-        tc = self.use_tensor_cores
+        tc = (self.use_tensor_cores, self.conv_operands)  # part of the graph key: a capture replays the kernels it recorded
         canvas = self._graph_input(("backbone", B, T, Ny, Nx, tc), (B * T, Ny, Nx, 32), dev)
         canvas.zero_()
         pillar_feats = torch.empty(M, 32, device=dev)
