@@ -1,6 +1,7 @@
 // Per-point MLPs on the 5th-generation tensor cores (tcgen05.mma kind::tf32, FP32 accumulators in TMEM, 3xTF32 error
 // compensation as in conv_tc.cu): the STPN point head of models/stpn.py:91-103 (positional encoding, bilinear pickup,
-// final_proj, mos_seg and offset_head).
+// final_proj, mos_seg and offset_head) and, further down, the TubeNet embeddings of models/tpointnet.py:171-262
+// (k_embed_tc: MLP + max over the rows of each segment).
 //
 // A CTA (one per SM, persistent) owns tiles of 128 foreground points = the 128 rows (M) of every MMA.  The activations
 // of a tile live in shared memory as the K-major, 128B-swizzled A operand: 4 "atoms" of [128 rows x 32 channels] per
