@@ -207,3 +207,30 @@ def test_oracle_evaluation_tail_and_data_prep_properties():
         (raw[:, 2] < vg["crop_range"][2]) & (raw[:, 2] > vg["crop_range"][1]) & (raw[:, 2] > g)
     assert np.array_equal(ref["input_points"], raw[keep]) and np.array_equal(ref["time_indice"][:, 0], tt[keep])
     assert ref["point_to_voxel_map"].shape[0] == int(keep.sum()) and int(ref["num_points"][0]) == int(keep.sum())
+
+
+def test_tensor_core_weight_packs_reconstruct_the_weights():
+    """Host-side operand splits (tc_pack.py): hi + lo reproduces the FP32 weight to ~2^-22, in the layouts the kernels expect."""
+    import types
+
+    from pcaccumulation_b200 import motionnet as mn, tc_pack
+
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(64, 96, 3, 3, generator=g) * 0.05
+    layer = mn._ConvLayer(types.SimpleNamespace(weight=w, bias=torch.zeros(64)), splits=[32, 64])
+    k = 9 * 96
+    ref = layer.pack.view(k, 64).t()  # [Cout][K] in the kernels' K order (source, tap, channel)
+    t32 = tc_pack.pack_conv_tc(layer)  # [hi rows; lo rows][K]
+    assert t32.shape == (128, k)
+    assert torch.equal(t32[:64] + t32[64:], ref)  # lo = w - hi exactly
+    assert int((t32[:64].view(torch.int32) & 0x1FFF).abs().sum()) == 0  # hi has tf32 precision: low 13 mantissa bits clear
+    f16 = tc_pack.pack_conv_tc_f16(layer)  # [2][Cout][K/32][64], 32 used
+    assert f16.dtype == torch.float16 and f16.shape == (2, 64, k // 32, 64)
+    assert float(f16[:, :, :, 32:].abs().max()) == 0.0
+    rec = (f16[0, :, :, :32].float() + f16[1, :, :, :32].float()).reshape(64, k) / tc_pack.F16_WEIGHT_SCALE
+    assert float((rec - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -21
+    lo = f16[1, :, :, :32].float().abs()
+    assert float(lo[lo > 0].min()) >= 2.0 ** -24  # representable (the scale keeps typical residuals out of the subnormals)
+    lin = torch.nn.Linear(48, 24)
+    s = tc_pack.split_tf32(lin.weight)
+    assert s.shape == (48, 48) and torch.equal(s[:24] + s[24:], lin.weight.detach())
