@@ -193,6 +193,12 @@ int pcab_flow_eval(const float* input_points, const int* time_idx, const float* 
                    const long long* fb_est_per_point, int n_points, int n_frames, float* epe_out /* [N] */,
                    float* rel_out /* [N] */, double* sf_counters /* [3][6], accumulated */,
                    long long* mos_counters /* [8], accumulated */, pcab_stream_t stream);
+/* instance-segmentation scores of toolbox/cluster_eval.py:71-152 for one scene; counters[28] doubles, accumulated:
+ * class c: [4c] sum of mean coverage, [4c+1] sum of weighted coverage, [4c+2] scenes with gt instances, [4c+3] gt instances;
+ * threshold k (0.5 .. 0.9), class c: tp at [8 + 2(2k+c)], fp at [8 + 2(2k+c) + 1] */
+size_t pcab_cluster_eval_workspace(int max_est, int max_gt);
+int pcab_cluster_eval(const long long* inst_est, const long long* inst_gt, const long long* mos_label, int n_points, int max_est,
+                      int max_gt, double* counters, void* workspace, size_t workspace_bytes, pcab_stream_t stream);
 
 /* ---- Chamfer distance: chamfer_distance/chamfer_distance.cpp:27-56 (forward_cuda / backward_cuda) --------- */
 size_t pcab_chamfer_workspace(int B, int n, int m);

@@ -799,3 +799,50 @@ def prep_input_test_mode(raw_points, time_indice, sd_labels, fb_labels, inst_lab
             "fb_labels": fb_labels[:, None]}
     data.update(voxelize(points, vg["voxel_size"], vg["range"], vg["n_sweeps"]))
     return data
+
+
+def cluster_eval(inst_est, inst_gt, mos_label):
+    """toolbox/cluster_eval.py:71-152 (ClusterEvaluation.forward) for one scene, returning the per-scene quantities it appends:
+    per class [mean_cov or None, mean_weighted_cov or None, n_gt_inst] and tp / fp lists per IoU threshold."""
+    thresholds = [0.5, 0.6, 0.7, 0.8, 0.9]
+    mos_label = mos_label.float()
+
+    def instances(labels):
+        out = [[], []]
+        for uid in torch.unique(labels):
+            if uid == 0:
+                continue
+            m = labels == uid
+            out[round(mos_label[m].mean().item())].append(m)
+        return out
+
+    est, gt = instances(inst_est), instances(inst_gt)
+    res = {"cov": [], "tp": {t: [None, None] for t in thresholds}, "fp": {t: [None, None] for t in thresholds}}
+    for c in range(2):
+        sum_cov, wcov, npts = 0.0, 0.0, 0
+        for g in gt[c]:
+            ovmax, ng = 0.0, g.sum().item()
+            npts += ng
+            for e in est[c]:
+                iou = float((g & e).sum() / (g | e).sum())
+                ovmax = max(ovmax, iou)
+            sum_cov += ovmax
+            wcov += ovmax * ng
+        n_inst = len(gt[c])
+        res["cov"].append([sum_cov / n_inst if n_inst else None, wcov / npts if n_inst else None, n_inst])
+    for c in range(2):
+        tp = {t: 0 for t in thresholds}
+        fp = {t: 0 for t in thresholds}
+        for e in est[c]:
+            ovmax = -1.0
+            for g in gt[c]:
+                iou = float((e & g).sum() / (e | g).sum())
+                ovmax = max(ovmax, iou)
+            for t in thresholds:
+                if ovmax > t:
+                    tp[t] += 1
+                else:
+                    fp[t] += 1
+        for t in thresholds:
+            res["tp"][t][c], res["fp"][t][c] = tp[t], fp[t]
+    return res

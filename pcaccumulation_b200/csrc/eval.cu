@@ -141,3 +141,121 @@ extern "C" int pcab_flow_eval(const float* input_points, const int* time_idx, co
   PCAB_CHECK_LAUNCH("pcab_flow_eval");
   return PCAB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Instance-segmentation part of the evaluation tail: toolbox/cluster_eval.py:71-152 (ClusterEvaluation.forward, adopted
+// there from ASIS).  The reference builds one boolean mask per instance and loops over all (gt, est) pairs in Python with a
+// device sync per pair; here one pass over the points fills the (est, gt) contingency table, and one small block turns it
+// into the coverage and precision / recall counters.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void k_contingency(const long long* __restrict__ est, const long long* __restrict__ gt,
+                              const long long* __restrict__ mos, int n, int E, int G, int* __restrict__ table,
+                              int* __restrict__ est_size, int* __restrict__ est_mos, int* __restrict__ gt_size,
+                              int* __restrict__ gt_mos) {
+  int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int e = (int)est[i], g = (int)gt[i], m = mos[i] != 0;
+    if (e > 0 && e <= E) atomicAdd(est_size + e, 1), atomicAdd(est_mos + e, m);
+    if (g > 0 && g <= G) atomicAdd(gt_size + g, 1), atomicAdd(gt_mos + g, m);
+    if (e > 0 && e <= E && g > 0 && g <= G) atomicAdd(table + (size_t)e * (G + 1) + g, 1);
+  }
+}
+
+// out (doubles, ACCUMULATED): per class c in {0, 1}: [c*4 + 0] sum of per-scene mean coverage, [c*4 + 1] sum of per-scene
+// weighted coverage, [c*4 + 2] scenes that had a gt instance of the class, [c*4 + 3] gt instances; then for threshold k in
+// 0..4 and class c: tp at [8 + (k*2 + c)*2], fp at [8 + (k*2 + c)*2 + 1].
+__global__ void __launch_bounds__(256) k_cluster_scores(const int* __restrict__ table, const int* __restrict__ est_size,
+                                                        const int* __restrict__ est_mos, const int* __restrict__ gt_size,
+                                                        const int* __restrict__ gt_mos, int E, int G,
+                                                        double* __restrict__ out) {
+  __shared__ double s_cov[2], s_wcov[2];
+  __shared__ int s_ngt[2], s_npts[2], s_tp[10], s_fp[10];
+  if (threadIdx.x < 2) s_cov[threadIdx.x] = s_wcov[threadIdx.x] = 0.0, s_ngt[threadIdx.x] = s_npts[threadIdx.x] = 0;
+  if (threadIdx.x < 10) s_tp[threadIdx.x] = s_fp[threadIdx.x] = 0;
+  __syncthreads();
+  // an instance's class = round(mean(mos_label)) with Python's round-half-to-even: 1 iff 2*sum > count
+  // coverage: every gt instance looks for its best-overlapping predicted instance of the same class
+  for (int g = 1 + threadIdx.x; g <= G; g += blockDim.x) {
+    const int ng = gt_size[g];
+    if (ng == 0) continue;
+    const int cls = 2 * gt_mos[g] > ng;
+    float ovmax = 0.f;
+    for (int e = 1; e <= E; ++e) {
+      const int ne = est_size[e];
+      if (ne == 0 || (2 * est_mos[e] > ne) != cls) continue;
+      const int inter = table[(size_t)e * (G + 1) + g];
+      const float iou = (float)inter / (float)(ne + ng - inter);  // int64 / int64 -> float32 true division, as torch
+      if (iou > ovmax) ovmax = iou;
+    }
+    atomicAdd(&s_cov[cls], (double)ovmax);
+    atomicAdd(&s_wcov[cls], (double)ovmax * ng);
+    atomicAdd(&s_ngt[cls], 1);
+    atomicAdd(&s_npts[cls], ng);
+  }
+  // precision / recall: every predicted instance looks for its best gt instance of the same class
+  const double thr[5] = {0.5, 0.6, 0.7, 0.8, 0.9};
+  for (int e = 1 + threadIdx.x; e <= E; e += blockDim.x) {
+    const int ne = est_size[e];
+    if (ne == 0) continue;
+    const int cls = 2 * est_mos[e] > ne;
+    float ovmax = -1.f;
+    for (int g = 1; g <= G; ++g) {
+      const int ng = gt_size[g];
+      if (ng == 0 || (2 * gt_mos[g] > ng) != cls) continue;
+      const int inter = table[(size_t)e * (G + 1) + g];
+      const float iou = (float)inter / (float)(ne + ng - inter);
+      if (iou > ovmax) ovmax = iou;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      if ((double)ovmax > thr[k]) atomicAdd(&s_tp[k * 2 + cls], 1);
+      else atomicAdd(&s_fp[k * 2 + cls], 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const int c = threadIdx.x;
+    if (s_ngt[c] > 0) {
+      out[c * 4 + 0] += s_cov[c] / s_ngt[c];
+      out[c * 4 + 1] += s_wcov[c] / s_npts[c];
+      out[c * 4 + 2] += 1.0;
+    }
+    out[c * 4 + 3] += s_ngt[c];
+  }
+  if (threadIdx.x < 10) {
+    out[8 + threadIdx.x * 2] += s_tp[threadIdx.x];
+    out[8 + threadIdx.x * 2 + 1] += s_fp[threadIdx.x];
+  }
+}
+
+size_t al256e(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" size_t pcab_cluster_eval_workspace(int max_est, int max_gt) {
+  return al256e(((size_t)(max_est + 1) * (max_gt + 1) + 2 * (size_t)(max_est + 1) + 2 * (size_t)(max_gt + 1)) * 4) + 256;
+}
+
+// One scene.  inst_est / inst_gt: 0 = background, instances 1..max_est / 1..max_gt; mos_label: 0 static, 1 dynamic.
+// counters: 28 doubles, ACCUMULATED over scenes (layout above k_cluster_scores): zero them before the first scene.
+extern "C" int pcab_cluster_eval(const long long* inst_est, const long long* inst_gt, const long long* mos_label, int n_points,
+                                 int max_est, int max_gt, double* counters, void* workspace, size_t workspace_bytes,
+                                 cudaStream_t stream) {
+  PCAB_REQUIRE(max_est >= 0 && max_gt >= 0, "negative instance count");
+  PCAB_REQUIRE(workspace_bytes >= pcab_cluster_eval_workspace(max_est, max_gt), "workspace too small");
+  const size_t ints = (size_t)(max_est + 1) * (max_gt + 1) + 2 * (size_t)(max_est + 1) + 2 * (size_t)(max_gt + 1);
+  int* table = (int*)workspace;
+  int* est_size = table + (size_t)(max_est + 1) * (max_gt + 1);
+  int* est_mos = est_size + (max_est + 1);
+  int* gt_size = est_mos + (max_est + 1);
+  int* gt_mos = gt_size + (max_gt + 1);
+  PCAB_CUDA(cudaMemsetAsync(workspace, 0, ints * 4, stream));
+  if (n_points > 0)
+    k_contingency<<<grid_for(n_points, 256), 256, 0, stream>>>(inst_est, inst_gt, mos_label, n_points, max_est, max_gt, table,
+                                                               est_size, est_mos, gt_size, gt_mos);
+  k_cluster_scores<<<1, 256, 0, stream>>>(table, est_size, est_mos, gt_size, gt_mos, max_est, max_gt, counters);
+  PCAB_CHECK_LAUNCH("pcab_cluster_eval");
+  return PCAB_OK;
+}

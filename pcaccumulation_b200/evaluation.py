@@ -82,3 +82,48 @@ class FlowEvaluator:
                       "iou": inter / np.maximum(union, 1.0), "recall": inter / np.maximum(gt, 1.0),
                       "precision": inter / np.maximum(pred, 1.0), "masked_points": int(mos[6])}
         return out
+
+
+class ClusterEvaluator:
+    """``toolbox/cluster_eval.py:ClusterEvaluation`` (coverage + precision / recall of the predicted instances at IoU
+    0.5 .. 0.9, per motion class) with the per-scene work on the device: one pass over the points builds the (est, gt)
+    contingency table (``pcab_cluster_eval``); the reference loops over all instance pairs in Python with boolean masks."""
+
+    THRESHOLDS = (0.5, 0.6, 0.7, 0.8, 0.9)
+
+    def __init__(self, device="cuda"):
+        self.device = torch.device(device)
+        self.counters = torch.zeros(28, dtype=torch.float64, device=self.device)
+
+    @torch.no_grad()
+    def update(self, inst_est, inst_gt, mos_label):
+        """One scene: inst_est / inst_gt [N] (0 = background), mos_label [N] (0 static, 1 dynamic), as
+        ``libs/loss.py:261-270`` passes them per batch element."""
+        from ._lib import Z, scratch, size
+        dev = self.device
+        i64 = lambda t: t.to(dev).reshape(-1).to(torch.int64).contiguous()
+        est, gt, mos = i64(inst_est), i64(inst_gt), i64(mos_label)
+        n = est.shape[0]
+        if n == 0:
+            return
+        max_est, max_gt = [int(v) for v in torch.stack((est.max(), gt.max())).tolist()]
+        ws = scratch(size("pcab_cluster_eval_workspace", I(max_est), I(max_gt)), dev)
+        call("pcab_cluster_eval", P(est), P(gt), P(mos), I(n), I(max_est), I(max_gt), P(self.counters), P(ws), Z(ws.numel()),
+             stream())
+
+    def all_reduce(self):
+        from .dist_utils import reduce_metrics
+        self.counters = reduce_metrics(self.counters, op="sum")
+        return self
+
+    def summary(self):
+        """The numbers ``ClusterEvaluation.final_eval`` logs (toolbox/cluster_eval.py:33-69), per class [static, dynamic]."""
+        c = self.counters.cpu().numpy()
+        scenes = np.maximum(c[[2, 6]], 1.0)
+        out = {"MUCov": c[[0, 4]] / scenes, "MWCov": c[[1, 5]] / scenes, "total_gt_inst": c[[3, 7]]}
+        for k, thr in enumerate(self.THRESHOLDS):
+            tp = np.array([c[8 + 2 * (2 * k + cls)] for cls in (0, 1)])
+            fp = np.array([c[8 + 2 * (2 * k + cls) + 1] for cls in (0, 1)])
+            out[f"@{thr}"] = {"precision": tp / np.maximum(tp + fp, 1.0), "recall": tp / np.maximum(out["total_gt_inst"], 1.0),
+                              "tp": tp, "fp": fp}
+        return out

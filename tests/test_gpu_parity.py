@@ -867,3 +867,55 @@ def test_conv3x3_tensor_core_operand_formats(lib, case, operands):
     torch.cuda.synchronize()
     assert not bool(torch.isnan(out).any())
     assert_close_rel(out, ref, 1e-5, f"{case}/{operands}")
+
+
+def test_cluster_evaluator_matches_oracle():
+    """pcab_cluster_eval (contingency table + scores) against the restatement of toolbox/cluster_eval.py:71-152: perturbed
+    copies of the ground-truth instances (splits, merges, noise, misses) over two scenes, counters compared exactly."""
+    from oracle import oracle
+    from pcaccumulation_b200 import config, synth
+    from pcaccumulation_b200.evaluation import ClusterEvaluator
+
+    ev = ClusterEvaluator()
+    want = np.zeros(28)
+    for scene_idx in (41, 42):
+        s = synth.make_workload_scene("C1", scene_idx, pts_per_frame=6000)
+        gt = torch.tensor(s["inst_labels"][:, 0].astype(np.int64))
+        mos = torch.tensor(s["sd_labels"][:, 0].astype(np.int64))
+        g = torch.Generator().manual_seed(scene_idx)
+        est = gt.clone()
+        ids = torch.unique(gt)
+        ids = ids[ids > 0]
+        for k, uid in enumerate(ids.tolist()):
+            m = gt == uid
+            r = k % 5
+            if r == 0:
+                est[m] = 0  # missed instance
+            elif r == 1:
+                est[m & (torch.rand(m.shape, generator=g) < 0.4)] = 1000 + uid  # split in two
+            elif r == 2:
+                est[m & (torch.rand(m.shape, generator=g) < 0.2)] = 0  # eroded: IoU ~ 0.8
+            elif r == 3 and k + 1 < len(ids):
+                est[gt == ids[k + 1]] = uid  # merged with the next one
+        est[(gt == 0) & (torch.rand(gt.shape, generator=g) < 0.002)] = 5000  # a false-positive blob
+        _, est = torch.unique(est, return_inverse=True)  # canonical ids 0..L (0 stays background: it is the smallest id)
+        assert int(est.max()) > 5
+        ref = oracle.cluster_eval(est, gt, mos)
+        for c in range(2):
+            mc, mw, n_inst = ref["cov"][c]
+            if n_inst:
+                want[4 * c] += mc
+                want[4 * c + 1] += mw
+                want[4 * c + 2] += 1
+            want[4 * c + 3] += n_inst
+        for k, t in enumerate((0.5, 0.6, 0.7, 0.8, 0.9)):
+            for c in range(2):
+                want[8 + 2 * (2 * k + c)] += ref["tp"][t][c]
+                want[8 + 2 * (2 * k + c) + 1] += ref["fp"][t][c]
+        ev.update(est.cuda(), gt.cuda(), mos.cuda())
+    got = ev.counters.cpu().numpy()
+    assert np.array_equal(got[[2, 3, 6, 7]], want[[2, 3, 6, 7]]) and np.array_equal(got[8:], want[8:]), (got, want)
+    assert np.allclose(got[[0, 1, 4, 5]], want[[0, 1, 4, 5]], rtol=0, atol=1e-6)
+    assert want[8:].sum() > 10 and want[3] + want[7] > 10
+    summ = ev.summary()
+    assert summ["@0.5"]["tp"].sum() >= summ["@0.9"]["tp"].sum()
