@@ -170,3 +170,101 @@ def test_kabsch_recovers_known_transform():
     y = x @ R.T + t
     Re, te = oracle.kabsch(x, y, torch.ones(1, 50))
     assert torch.allclose(Re[0], R, atol=1e-5) and torch.allclose(te[0, :, 0], t, atol=1e-5)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference only exists in the build container")
+def test_eval_tail_and_data_prep_restatements_match_reference_when_present(tmp_path):
+    """Pins the oracle functions behind rows f2 / f3 (oracle.flow_eval, cluster_eval, prep_input_test_mode) on the UNMODIFIED
+    reference code: toolbox/register_utils.py, toolbox/sf_eval_utils.py, toolbox/cluster_eval.py, libs/loss.py:compute_iou and
+    libs/dataset.py:BaseDataset.prep_input."""
+    import importlib
+    import sys
+    import types
+
+    from pcaccumulation_b200 import config, synth
+
+    ns = ref_loader.load()
+    ru = ns["register_utils"]
+    if "IPython" not in sys.modules:  # toolbox/sf_eval_utils.py imports IPython.display for its notebook helpers only
+        ip, disp = types.ModuleType("IPython"), types.ModuleType("IPython.display")
+        disp.display = print
+        ip.display = disp
+        sys.modules["IPython"], sys.modules["IPython.display"] = ip, disp
+    sf = importlib.import_module("toolbox.sf_eval_utils")
+    ce = importlib.import_module("toolbox.cluster_eval")
+    loss = importlib.import_module("libs.loss")
+    ds = importlib.import_module("libs.dataset")
+
+    cfg = config.workload_config("C1")
+    vg, dc = cfg["voxel_generator"], cfg["data"]
+    T = vg["n_sweeps"]
+    s = synth.make_workload_scene("C1", 7, pts_per_frame=5000)
+    p4 = np.concatenate((s["input_points"], s["time_indice"]), 1).astype(np.float32)
+    s.update(oracle.voxelize(p4, vg["voxel_size"], vg["range"], T))
+    inp = synth.collate([s])
+    pts, t = inp["input_points"].float(), inp["time_indice"][:, 1].long()
+    ego_gt, inst_gt = inp["ego_motion_gt"].float()[0], inp["inst_motion_gt"][0].float()
+    inst = inp["inst_labels"][:, 0]
+    # GT accumulation
+    a = ru.reconstruct_sequence(ru.ego_motion_compensation(pts, t, ego_gt), t, inst, inst_gt, T)
+    b = oracle.reconstruct_sequence(oracle.ego_motion_compensation(pts, t, ego_gt), t, inst, inst_gt, T)
+    assert torch.equal(a, b)
+    # scene-flow errors and metrics, as libs/tester.py:58-77 + compute_sf_metrics_torch
+    g = torch.Generator().manual_seed(1)
+    n = pts.shape[0]
+    pred = {"rec_est": a + torch.randn(n, 3, generator=g) * (10.0 ** torch.empty(n, 1).uniform_(-4, 0.3, generator=g)),
+            "mos_est": torch.randn(n, 2, generator=g), "fb_est_per_points": (torch.rand(n, 1, generator=g) < 0.3).long()}
+    ev = oracle.flow_eval(inp, pred, T)
+    err = (pred["rec_est"] - pts) - (a - pts)
+    epe = torch.norm(err, p=2, dim=1)
+    rel = epe / (torch.norm(a - pts, p=2, dim=1) + ns["utils"]._EPS)
+    assert torch.equal(ev["epe_per_point"], epe) and torch.equal(ev["relative_error"], rel)
+    sel = t > 0
+    m = sf.compute_sf_metrics_torch(epe[sel], rel[sel])
+    cnt = ev["sf"]["all"]
+    assert m["EPE3D"][1] == cnt[0] and abs(m["EPE3D"][0] - cnt[1] / cnt[0]) < 1e-6
+    for key, idx in (("Acc3DS", 2), ("Acc3DR", 3), ("Outlier", 4), ("ROutlier", 5)):
+        assert abs(m[key][0] - cnt[idx] / cnt[0]) < 1e-6, key
+    # motion-segmentation IoU counters (libs/loss.py:17-48 on the FG mask of :144-149)
+    fb, sd = inp["fb_labels"][:, 0], inp["sd_labels"][:, 0].long()
+    mask = torch.logical_or(fb == 1, pred["fb_est_per_points"][:, 0] == 1)
+    st = loss.compute_iou(pred["mos_est"].argmax(1)[mask], sd[mask], 2, -1)
+    assert np.allclose(st["intersection"] * 1e3, ev["mos"]["intersection"]) and np.allclose(st["pred_positives"] * 1e3, ev["mos"]["pred_positives"])
+    assert np.allclose(st["gt_positives"] * 1e3, ev["mos"]["gt_positives"])
+    union = np.array(ev["mos"]["pred_positives"]) + np.array(ev["mos"]["gt_positives"]) - np.array(ev["mos"]["intersection"])
+    assert np.allclose(st["union"] * 1e3, union)
+    # instance scores: ClusterEvaluation.forward
+    est = inst.clone()
+    ids = torch.unique(inst)
+    ids = ids[ids > 0]
+    for k, uid in enumerate(ids.tolist()):
+        sel_i = inst == uid
+        if k % 3 == 0:
+            est[sel_i & (torch.rand(sel_i.shape, generator=g) < 0.3)] = 0
+        elif k % 3 == 1:
+            est[sel_i & (torch.rand(sel_i.shape, generator=g) < 0.5)] = 900 + uid
+    ref_ce = ce.ClusterEvaluation({"save_dir": str(tmp_path)})
+    ref_ce(est, inst, inp["sd_labels"][:, 0].float())
+    mine = oracle.cluster_eval(est, inst, inp["sd_labels"][:, 0])
+    for c in range(2):
+        mc, mw, n_inst = mine["cov"][c]
+        assert ref_ce.total_gt_inst[c] == n_inst
+        if n_inst:
+            assert ref_ce.all_mean_cov[c] == [mc] and ref_ce.all_mean_weighted_cov[c] == [mw]
+        for thr in (0.5, 0.6, 0.7, 0.8, 0.9):
+            assert sum(ref_ce.tpsins[f"@{thr}"][c]) == mine["tp"][thr][c] and sum(ref_ce.fpsins[f"@{thr}"][c]) == mine["fp"][thr][c]
+    # data preparation: BaseDataset.prep_input with a stand-in for `self` (its constructor needs the dataset on disk)
+    rng = np.random.default_rng(2)
+    raw = rng.uniform(-40, 40, (6000, 3)).astype(np.float32)
+    raw[:, 2] = rng.uniform(-3, 8, 6000)
+    tt = np.sort(rng.integers(0, T, 6000))
+    lab = rng.integers(0, 2, 6000)
+    fake = types.SimpleNamespace(augmentation=False, n_frames=T, crop_xy=vg["crop_range"][0], crop_z_min=vg["crop_range"][1],
+                                 crop_z_max=vg["crop_range"][2], remove_ground=dc["remove_ground"],
+                                 ground_height=dc["ground_height"] + dc["ground_slack"], voxeliser=ns["Voxelization"](vg))
+    ego = np.tile(np.eye(4, dtype=np.float32), (T, 1, 1))
+    want = ds.BaseDataset.prep_input(fake, raw, lab, lab, lab, tt, ego, ego[None])
+    got = oracle.prep_input_test_mode(raw, tt, lab, lab, lab, cfg)
+    for k in ("input_points", "num_points", "time_indice", "sd_labels", "inst_labels", "fb_labels", "coordinates", "num_voxels",
+              "shape", "point_to_voxel_map"):
+        assert np.array_equal(np.asarray(want[k]), np.asarray(got[k])), k
