@@ -268,3 +268,42 @@ def test_eval_tail_and_data_prep_restatements_match_reference_when_present(tmp_p
     for k in ("input_points", "num_points", "time_indice", "sd_labels", "inst_labels", "fb_labels", "coordinates", "num_voxels",
               "shape", "point_to_voxel_map"):
         assert np.array_equal(np.asarray(want[k]), np.asarray(got[k])), k
+
+
+def test_eval_tail_and_data_prep_match_reference_golden():
+    """The f2 / f3 oracle functions against outputs of the UNMODIFIED reference (tests/golden/eval_tail.npz, written by
+    oracle/make_golden_eval.py) - runs wherever the reference checkout is absent (the GPU box)."""
+    from pcaccumulation_b200 import config
+
+    g = np.load(os.path.join(GOLDEN, "eval_tail.npz"))
+    cfg = config.workload_config("C1")
+    T = cfg["voxel_generator"]["n_sweeps"]
+    n = g["pts"].shape[0]
+    i64 = lambda k: torch.tensor(g[k].astype(np.int64))
+    inp = {"input_points": torch.tensor(g["pts"]), "time_indice": torch.stack((torch.zeros(n, dtype=torch.float64), i64("t").double()), 1),
+           "ego_motion_gt": torch.tensor(g["ego_gt"])[None], "inst_motion_gt": [torch.tensor(g["inst_gt"])],
+           "inst_labels": i64("inst")[:, None], "fb_labels": i64("fb")[:, None], "sd_labels": i64("sd")[:, None]}
+    pred = {"rec_est": torch.tensor(g["rec_est"]), "mos_est": torch.tensor(g["mos_est"]), "fb_est_per_points": i64("fb_est")[:, None]}
+    ev = oracle.flow_eval(inp, pred, T)
+    assert np.array_equal(ev["epe_per_point"].numpy(), g["epe"]) and np.array_equal(ev["relative_error"].numpy(), g["rel"])
+    for name in ("all", "dynamic", "static"):
+        cnt, want = ev["sf"][name], g["sf_" + name]
+        assert cnt[0] == int(want[0])
+        got = np.array([cnt[1] / cnt[0]] + [c / cnt[0] for c in cnt[2:]])
+        assert np.allclose(got, want[1:], rtol=0, atol=1e-6), name
+    m = ev["mos"]
+    union = np.array(m["pred_positives"]) + np.array(m["gt_positives"]) - np.array(m["intersection"])
+    assert np.allclose(g["mos_stats"], np.stack([m["intersection"], union, m["pred_positives"], m["gt_positives"]]))
+    ce = oracle.cluster_eval(i64("cluster_est"), i64("inst"), i64("sd"))
+    for c in range(2):
+        mc, mw, n_inst = ce["cov"][c]
+        assert n_inst == int(g["cluster_cov"][c, 2])
+        if n_inst:
+            assert mc == g["cluster_cov"][c, 0] and mw == g["cluster_cov"][c, 1]
+        for k, thr in enumerate((0.5, 0.6, 0.7, 0.8, 0.9)):
+            assert [ce["tp"][thr][c], ce["fp"][thr][c]] == g["cluster_tp_fp"][k, c].astype(int).tolist()
+    lab = g["prep_lab"].astype(np.int64)
+    d = oracle.prep_input_test_mode(g["prep_raw"], g["prep_t"].astype(np.int64), lab, lab, lab, cfg)
+    assert np.array_equal(d["input_points"], g["prep_points"]) and np.array_equal(d["time_indice"][:, 0], g["prep_time"])
+    assert np.array_equal(d["sd_labels"][:, 0], g["prep_sd"]) and np.array_equal(d["coordinates"], g["prep_coordinates"])
+    assert np.array_equal(d["point_to_voxel_map"][:, 0], g["prep_p2v"]) and np.array_equal(d["num_voxels"], g["prep_num_voxels"])
