@@ -377,28 +377,6 @@ def main():
         epe = compare(not args.no_tc)
         epe_fp32 = compare(False) if not args.no_tc else None
 
-    sf_vs_gt = None
-    if rank == 0:
-        # the reference's own scene-flow / motion-IoU formulas (libs/tester.py:58-88) against the synthetic ground truth, through
-        # the device evaluation tail.  Informational (random fixture weights): it shows that the metric path runs end to end.
-        try:
-            from pcaccumulation_b200.evaluation import FlowEvaluator
-
-            ev = FlowEvaluator(cfg["voxel_generator"]["n_sweeps"], device=dev, keep_per_point=False)
-            for i in range(N_SCENES):
-                s = scenes[i]
-                labels = {k: torch.from_numpy(s[k]).to(dev) for k in ("sd_labels", "inst_labels", "fb_labels")}
-                inp = runner.build_input(dev_pts[i], nums[i], labels=labels, ego_motion_gt=dev_ego[i],
-                                         inst_motion_gt=[torch.from_numpy(s["inst_motion_gt"]).to(dev)])
-                torch.manual_seed(1000 + i)
-                with torch.no_grad():
-                    ev.update(inp, runner.model(inp))
-            sm = ev.summary()
-            sf_vs_gt = {k: {m: float(v) for m, v in sm[k].items()} for k in ("all", "dynamic", "static")}
-            sf_vs_gt["mos_iou"] = [float(x) for x in sm["mos"]["iou"]]
-        except Exception as e:  # never let the informational block cost the benchmark line
-            sf_vs_gt = {"error": repr(e)[:200]}
-
     if rank == 0:
         line = {
             "metric": "scenes/sec", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
@@ -426,7 +404,6 @@ def main():
             "cpu_baseline": cpu_base,
             "parity_vs_oracle": epe,
             "parity_vs_oracle_fp32_path": epe_fp32,
-            "scene_flow_vs_gt": sf_vs_gt,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
