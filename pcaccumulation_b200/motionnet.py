@@ -233,7 +233,7 @@ class MotionNet(nn.Module):
         self.keep_stages = False
         # stage-wise parity protocol: tensors placed here replace the computed value for the stages
         # DOWNSTREAM of it; keys: 'fb_est_map' [B,T,1,Ny,Nx], 'ego_motion_est' [B,T,4,4], 'mos_est' [N,2],
-        # 'offset_est' [N,2], 'inst_labels_est' [N]
+        # 'offset_est' [N,2], 'inst_labels_est' [N], 'transformed_points' [N,3] (consumed by clustering / TubeNet only)
         self.inject = {}
         self.stage_marks = None  # when a list: (name, cuda event) at stage boundaries (profiling aid)
         self.rng = None  # torch.Generator for the keypoint permutations (None = the global CPU generator, as upstream)
@@ -641,6 +641,8 @@ class MotionNet(nn.Module):
             full_mos = self.inject["mos_est"].to(dev).float().contiguous()
         if "offset_est" in self.inject:
             full_off = self.inject["offset_est"].to(dev).float().contiguous()
+        if "transformed_points" in self.inject:
+            tp = self.inject["transformed_points"].to(dev).float().contiguous()
         rec_est = tp.clone()
         results["rec_est"] = rec_est
 

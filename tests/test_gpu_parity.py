@@ -237,154 +237,87 @@ def _seeded(model, inp, seed, inject=None):
     return out
 
 
-def _check_protocol(model, inp_cuda, ref, seed, rel=REL):
-    """Stage-wise parity with injected upstream oracle tensors (discrete decisions amplify).
+from oracle.protocol import REPORT, run_protocol, write_report  # noqa: E402  (the staged float32 / float64 parity protocol)
 
-    A  nothing injected : everything up to and including the ego pose.
-    B  oracle pose      : warp -> STPN -> motion logits / offsets (a 5e-6 pose difference moves the bilinear taps of
-                          the high-frequency feature maps, so these stages are compared from an identical pose).
-    C  + oracle logits  : clustering (integer labels, bit-exact) and TubeNet.
-    """
-    a = _seeded(model, inp_cuda, seed)
-    assert torch.equal(a["fb_seg_gt"].cpu(), ref["fb_seg_gt"])
-    assert_close_rel(a["fb_seg_est"], ref["fb_seg_est"], rel, "fb_seg_est")
-    flips = int((a["fb_est_per_points"].cpu() != ref["fb_est_per_points"]).sum())
-    if not model.use_tensor_cores:
-        assert flips == 0, "FP32 path: FG/BG labels must be bit-exact"
-    else:
-        # tensor-core path: logits agree to ~3e-5 relative; a pillar whose two logits tie to that precision may flip.
-        # One flip changes the background count n and with it torch.randperm(n) (H3), so the remaining stages are
-        # then checked from the oracle's label map.
-        fb_map_ref = ref["fb_seg_est"].max(dim=2, keepdim=True)[1]
-        occupied = ref["occ_map"] > 0
-        cells = int(((a["fb_seg_est"].cpu().max(dim=2, keepdim=True)[1] != fb_map_ref) & occupied).sum())
-        assert cells <= 3 and flips <= 12, (cells, flips)
-        if flips:
-            a = _seeded(model, inp_cuda, seed, {"fb_est_map": fb_map_ref})
-            assert torch.equal(a["fb_est_per_points"].cpu(), ref["fb_est_per_points"])
-            model._fb_inject = fb_map_ref
-    extra = {"fb_est_map": model._fb_inject} if getattr(model, "_fb_inject", None) is not None else {}
-    for k in ("occ_map", "fb_seg_est", "ego_motion_est", "ego_motion_gt", "transformed_points"):
-        assert_close_rel(a[k], ref[k], rel, k)
-    assert len(a["perm_matrix"]) == len(ref["perm_matrix"])
-    # the transport plan is exp(affinity / 0.027): it amplifies feature differences 37x, so on the tensor-core path
-    # (3e-5 features) it is compared at 3e-4 of its largest entry; the pose it produces is still held to 1e-4
-    prel = 3 * rel if model.use_tensor_cores else rel
-    for x, y in zip(a["perm_matrix"], ref["perm_matrix"]):
-        assert_close_rel(x, y, prel, "perm_matrix")
-    assert abs(float(a["ego_l1_loss"]) - float(ref["ego_l1_loss"])) < 1e-4 * max(1.0, float(ref["ego_l1_loss"]))
-    assert abs(float(a["ego_l2_loss"]) - float(ref["ego_l2_loss"])) < 1e-4 * max(1.0, float(ref["ego_l2_loss"]))
-    assert abs(a["ego_trans_error"] - ref["ego_trans_error"]) < 1e-4 * max(1.0, ref["ego_trans_error"])
-    # acos near 1 is ill-conditioned: rotations are compared on the matrices above, the angle only loosely
-    assert abs(a["ego_rot_error"] - ref["ego_rot_error"]) < 5e-3 * max(1.0, ref["ego_rot_error"])
-    # un-injected end-to-end agreement (reported, loose): labels and accumulated points
-    agree = float((a["inst_labels_est"].cpu() == ref["inst_labels_est"]).float().mean()) if "inst_labels_est" in ref else 1.0
-    assert agree > 0.995, agree
-    assert float((a["rec_est"].cpu() - ref["rec_est"]).norm(dim=1).median()) < 1e-4
 
-    b = _seeded(model, inp_cuda, seed, dict(extra, ego_motion_est=ref["ego_motion_est"]))
-    assert torch.equal(b["transformed_points"].cpu(), ref["transformed_points"]) or \
-        float((b["transformed_points"].cpu() - ref["transformed_points"]).abs().max()) < 1e-5
-    # motion logits / offsets come out of warp + 4 Conv3d + a 19-conv UNet + a 4-layer MLP on random weights: FP32
-    # rounding alone reaches 1.0e-4 of the +-20 clamp range there, so this stage gets 2e-4
-    assert_close_rel(b["mos_est"], ref["mos_est"], 2 * rel, "mos_est")
-    assert_close_rel(b["offset_est"], ref["offset_est"], 2 * rel, "offset_est")
-    mos_flips = int((b["mos_est"].cpu().argmax(1) != ref["mos_est"].argmax(1)).sum())
-    if not model.use_tensor_cores:
-        assert mos_flips == 0, "FP32 path: motion labels must be bit-exact"
-    else:
-        assert mos_flips <= max(2, b["mos_est"].shape[0] // 50000), mos_flips  # ties at the 3e-5 level of the tensor-core path
+def _oracle_input(cfg, scene):
+    from oracle import oracle
+    from pcaccumulation_b200 import synth
 
-    inj = dict(extra, ego_motion_est=ref["ego_motion_est"], mos_est=ref["mos_est"], offset_est=ref["offset_est"])
-    c = _seeded(model, inp_cuda, seed, inj)
-    model._fb_inject = None
-    if "inst_labels_est" in ref:
-        assert torch.equal(c["inst_labels_est"].cpu(), ref["inst_labels_est"]), "instance labels"
-    assert "inst_pose_est" in ref, "the test scene must exercise the TubeNet branch"
-    assert torch.equal(c["inst_labels_adjusted"].cpu(), ref["inst_labels_adjusted"])
-    # TubeNet outputs sit at the end of a ~60-layer chain; the tensor-core path (3e-5 per conv stack) gets 2e-4 here
-    trel = 2 * rel if model.use_tensor_cores else rel
-    assert_close_rel(c["inst_pose_est"], ref["inst_pose_est"], trel, "inst_pose_est")
-    assert_close_rel(c["sub_rec_est"], ref["sub_rec_est"], trel, "sub_rec_est")
-    assert_close_rel(c["rec_est"], ref["rec_est"], trel, "rec_est")
-    assert abs(c["inst_l2_error"] - ref["inst_l2_error"]) < 1e-4 * max(1.0, ref["inst_l2_error"])
-    assert abs(c["dynamic_inst_l2_error"] - ref["dynamic_inst_l2_error"]) < 1e-4 * max(1.0, ref["dynamic_inst_l2_error"])
-    for it, terms in ref["tpointnet_loss_terms"].items():
-        assert_close_rel(c["tpointnet_loss_terms"][it]["inst_est_motion"], terms["inst_est_motion"], trel, "inst_est_motion")
-        for name in ("l1_loss", "l2_loss", "rot_loss", "trans_loss"):
-            x, y = float(c["tpointnet_loss_terms"][it][name]), float(terms[name])
-            assert abs(x - y) <= 2e-4 * max(1.0, abs(y)), (it, name, x, y)
-    return a
+    p4 = np.concatenate((scene["input_points"], scene["time_indice"]), 1).astype(np.float32)
+    vg = cfg["voxel_generator"]
+    s = dict(scene)
+    s.update(oracle.voxelize(p4, vg["voxel_size"], vg["range"], vg["n_sweeps"]))
+    return synth.collate([s])
 
 
 @pytest.mark.parametrize("tc", [False, True], ids=["fp32conv", "tcgen05conv"])
 @pytest.mark.parametrize("mode", ["test", "val"])
 def test_forward_vs_oracle_synthetic(fixture_weights, mode, tc):
-    from oracle import oracle
     from pcaccumulation_b200 import config, synth
 
     cfg = config.workload_config("C1", mode=mode)
     sd = fixture_weights(cfg)
-    s = synth.make_workload_scene("C1", 5)
-    p4 = np.concatenate((s["input_points"], s["time_indice"]), 1).astype(np.float32)
-    vg = cfg["voxel_generator"]
-    s.update(oracle.voxelize(p4, vg["voxel_size"], vg["range"], vg["n_sweeps"]))
-    inp = synth.collate([s])
-    torch.manual_seed(7)
-    ref = oracle.OracleMotionNet(cfg, sd).forward(inp)
+    inp = _oracle_input(cfg, synth.make_workload_scene("C1", 5))
     model = make_model(cfg, sd, tc)
-    inp_c = cuda_dict(inp)
-    res = _check_protocol(model, inp_c, ref, 7)
+    res, _ = run_protocol(model, cfg, sd, inp, 7, f"C1/{mode}/{'tcgen05' if tc else 'fp32'}", cache_key=("C1", mode))
     # determinism: same seed, same result
-    res2 = _seeded(model, inp_c, 7)
+    res2 = _seeded(model, cuda_dict(inp), 7)
     assert torch.equal(res["rec_est"], res2["rec_est"]) and torch.equal(res["ego_motion_est"], res2["ego_motion_est"])
+
+
+@pytest.mark.parametrize("tc", [False, True], ids=["fp32conv", "tcgen05conv"])
+@pytest.mark.parametrize("name", ["C2", "C3", "C5"])
+def test_forward_vs_oracle_baseline_configs_full_size(fixture_weights, name, tc):
+    """BASELINE.json configs[1] (Waymo-shaped 5 x 150k, 288^2), configs[2] (nuScenes-shaped 10 x 35k) and configs[4]
+    (5 x 400k points, 512^2 grid) at FULL size: the whole protocol on the path that is benchmarked, plus the
+    reference-generated golden of the same scene (tests/golden/full_<name>.npz, oracle/make_golden_full.py)."""
+    from pcaccumulation_b200 import config, synth
+
+    cfg = config.workload_config(name)
+    sd = fixture_weights(cfg)
+    scene = synth.make_workload_scene(name, 0)
+    inp = _oracle_input(cfg, scene)
+    model = make_model(cfg, sd, tc)
+    _, r32 = run_protocol(model, cfg, sd, inp, 42, f"{name}/test/{'tcgen05' if tc else 'fp32'}", cache_key=(name, "full"))
+    _check_full_golden(name, r32, REPORT[f"{name}/test/{'tcgen05' if tc else 'fp32'}"])
+    write_report()
+
+
+def _check_full_golden(name, r32, rec):
+    """The float32 oracle run of THIS box against the unmodified reference's outputs for the same scene (made in the build
+    container).  Integer outputs are expected bit-identical; BLAS / oneDNN pick kernels by CPU model and thread count, so
+    a different host may round differently -- mismatches are counted and bounded, floats compared at 1e-5."""
+    g = np.load(os.path.join(GOLDEN, f"full_{name}.npz"))
+    n, stride = int(g["n_points"][0]), int(g["stride"][0])
+    assert r32["rec_est"].shape[0] == n
+    fb = np.unpackbits(g["fb_bits"])[:n]
+    mos = np.unpackbits(g["mos_bits"])[:n]
+    d = {"fb": int((r32["fb_est_per_points"][:, 0].numpy() != fb).sum()), "mos": int((r32["mos_est"].argmax(1).numpy() != mos).sum()),
+         "inst": int((r32["inst_labels_est"].numpy() != g["inst_labels_est"]).sum())}
+    rec["oracle_here_vs_reference_golden_label_mismatches"] = d
+    assert d["fb"] <= 3 * 64 and d["mos"] <= 16, d  # a handful of ties at most (0 on the CPU the golden was made on)
+    if d["fb"] == 0:
+        for k in ("ego_motion_est", "ego_motion_gt"):
+            np.testing.assert_allclose(r32[k].numpy(), g[k], rtol=0, atol=1e-5 * max(1.0, np.abs(g[k]).max()), err_msg=k)
+        np.testing.assert_allclose(r32["transformed_points"][::stride].numpy(), g["transformed_points_sample"], rtol=0, atol=2e-5 * 36)
+        np.testing.assert_allclose(r32["fb_seg_est"][:, :, :, ::8, ::8].numpy(), g["fb_seg_est_sample"], rtol=0,
+                                   atol=1e-5 * float(np.abs(g["fb_seg_est_sample"]).max()))
 
 
 @pytest.mark.parametrize("tc", [False, True], ids=["fp32conv", "tcgen05conv"])
 @pytest.mark.parametrize("name", ["waymo_small", "nuscene_small"])
 def test_forward_vs_reference_golden(fixture_weights, name, tc):
-    """Against outputs of the UNMODIFIED reference (tests/golden, made by oracle/make_golden.py)."""
+    """Inputs of the goldens made by the UNMODIFIED reference (tests/golden, oracle/make_golden.py): the protocol against
+    the oracle, and the oracle's float32 run of this box against the reference's stored outputs."""
     cfg, g, v, inp = load_golden_forward(name)
-    model = make_model(cfg, fixture_weights(cfg), tc)
-    inp_c = cuda_dict(inp)
-    a = _seeded(model, inp_c, 42)
-    flips = int((a["fb_est_per_points"].cpu().numpy() != g["out_fb_est_per_points"]).sum())
-    if not tc:
-        assert flips == 0
-    else:
-        assert flips <= 12, flips
-    extra = {}
-    if flips:
-        # tensor-core path: a pillar whose two logits tie at the 3e-5 level flipped; continue the staged checks from the
-        # reference's own label map (rebuilt from its per-point labels: all points of a pillar share the pillar's label)
-        T, grid = cfg["voxel_generator"]["n_sweeps"], int(g["vox_shape"][0])
-        pillar_fb = np.zeros(v["coordinates"].shape[0], dtype=np.int64)
-        pillar_fb[v["point_to_voxel_map"][:, 0]] = g["out_fb_est_per_points"][:, 0]
-        fb_map = torch.zeros(1, T, 1, grid, grid, dtype=torch.int64)
-        co = v["coordinates"]
-        fb_map[0, co[:, 3], 0, co[:, 1], co[:, 2]] = torch.from_numpy(pillar_fb)
-        extra = {"fb_est_map": fb_map}
-        a = _seeded(model, inp_c, 42, extra)
-        assert np.array_equal(a["fb_est_per_points"].cpu().numpy(), g["out_fb_est_per_points"])
-    for k in ("ego_motion_est", "ego_motion_gt", "transformed_points"):
-        assert_close_rel(a[k], g["out_" + k], REL, k)
-    assert_close_rel(model.stages["pillar_feats"][::8], g["stage_pillar_feats_sub8"], 1e-5, "pillar_feats")
-    assert_close_rel(model.stages["bev_feats"].permute(0, 3, 1, 2)[:, :, ::16, ::16], g["stage_bev_feats_sample"], REL, "bev_feats")
-    rows = torch.stack([p[0].sum(1) for p in a["perm_matrix"]])
-    assert_close_rel(rows, g["out_perm_rowsum"], 3 * REL if tc else REL, "perm row sums")
-    pose = torch.tensor(g["out_ego_motion_est"])
-    b = _seeded(model, inp_c, 42, dict(extra, ego_motion_est=pose))
-    assert_close_rel(b["mos_est"], g["out_mos_est"], 2 * REL, "mos_est")
-    assert_close_rel(b["offset_est"], g["out_offset_est"], 2 * REL, "offset_est")
-    mos_flips = int((b["mos_est"].cpu().argmax(1).numpy() != g["out_mos_est"].argmax(1)).sum())
-    assert mos_flips == 0 if not tc else mos_flips <= 2, mos_flips
-    inj = dict(extra, ego_motion_est=pose, mos_est=torch.tensor(g["out_mos_est"]), offset_est=torch.tensor(g["out_offset_est"]))
-    c = _seeded(model, inp_c, 42, inj)
-    for k in ("inst_labels_est", "inst_labels_adjusted"):
-        assert np.array_equal(c[k].cpu().numpy(), g["out_" + k]), k
-    assert_close_rel(c["inst_pose_est"], g["out_inst_pose_est"], 2 * REL if tc else REL, "inst_pose_est")
-    for k in ("sub_rec_est", "rec_est"):
-        assert_close_rel(c[k], g["out_" + k], 2 * REL if tc else REL, k)
+    sd = fixture_weights(cfg)
+    model = make_model(cfg, sd, tc)
+    _, r32 = run_protocol(model, cfg, sd, inp, 42, f"golden_{name}/{'tcgen05' if tc else 'fp32'}", cache_key=("golden", name))
+    for k in ("fb_est_per_points", "inst_labels_est", "inst_labels_adjusted"):
+        assert np.array_equal(r32[k].numpy(), g["out_" + k]), k
+    for k in ("ego_motion_est", "transformed_points", "mos_est", "offset_est", "rec_est", "inst_pose_est"):
+        np.testing.assert_allclose(r32[k].numpy(), g["out_" + k], rtol=0, atol=1e-5 * max(1.0, np.abs(g["out_" + k]).max()), err_msg=k)
 
 
 def test_forward_batch_of_two_matches_oracle(fixture_weights):
@@ -401,11 +334,8 @@ def test_forward_batch_of_two_matches_oracle(fixture_weights):
         s.update(oracle.voxelize(p4, vg["voxel_size"], vg["range"], vg["n_sweeps"]))
         samples.append(s)
     inp = synth.collate(samples)
-    torch.manual_seed(3)
-    ref = oracle.OracleMotionNet(cfg, sd).forward(inp)
-    model = make_model(cfg, sd, False)
-    _check_protocol(model, cuda_dict(inp), ref, 3)
-    _check_protocol(make_model(cfg, sd, True), cuda_dict(inp), ref, 3)
+    run_protocol(make_model(cfg, sd, False), cfg, sd, inp, 3, "C1_batch2/fp32", cache_key="batch2")
+    run_protocol(make_model(cfg, sd, True), cfg, sd, inp, 3, "C1_batch2/tcgen05", cache_key="batch2")
 
 
 def test_runner_device_voxelise_equals_prevoxelised_input(fixture_weights):
@@ -584,37 +514,6 @@ def test_sequence_strategies_chain_and_full(fixture_weights, seq_pose):
     for x, y in zip(a["perm_matrix"], ref["perm_matrix"]):
         assert_close_rel(x, y, REL, "perm_matrix")
     assert abs(float(a["ego_l1_loss"]) - float(ref["ego_l1_loss"])) < 1e-4 * max(1.0, float(ref["ego_l1_loss"]))
-
-
-@pytest.mark.parametrize("name", ["C3", "C5"])
-def test_other_baseline_configs_run_at_full_size(fixture_weights, name):
-    """BASELINE.json configs[2] (nuScenes-shaped 10 x 35k, z-range [-5,3]) and configs[4] (5 x 400k points, 512 x 512 grid)."""
-    from pcaccumulation_b200 import config, synth
-    from pcaccumulation_b200.runner import SceneRunner, scene_to_points4
-
-    cfg = config.workload_config(name)
-    runner = SceneRunner(cfg)
-    runner.model.load_state_dict(fixture_weights(cfg))
-    s = synth.make_workload_scene(name, 0)
-    p4 = torch.tensor(scene_to_points4(s)).cuda()
-    torch.manual_seed(0)
-    res = runner.run_device(p4, [p4.shape[0]])
-    T = cfg["voxel_generator"]["n_sweeps"]
-    g = 512 if name == "C5" else 288
-    assert res["fb_seg_est"].shape == (1, T, 2, g, g) and res["ego_motion_est"].shape == (1, T, 4, 4)
-    assert torch.isfinite(res["rec_est"]).all() and res["rec_est"].shape == (p4.shape[0], 3)
-    R = res["ego_motion_est"][0, :, :3, :3]
-    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3, device="cuda").expand_as(R), atol=1e-5)
-    inst = res["inst_labels_est"]
-    labels = inst.unique().tolist()
-    assert labels == list(range(len(labels))) and len(labels) > 1
-    # the FP32 and tensor-core conv paths agree on this size too
-    runner.model.use_tensor_cores = False
-    torch.manual_seed(0)
-    res2 = runner.run_device(p4, [p4.shape[0]])
-    assert_close_rel(res2["fb_seg_est"], res["fb_seg_est"].cpu(), 2e-4, "fb_seg_est tc vs fp32")
-    flips = int((res2["fb_est_per_points"] != res["fb_est_per_points"]).sum())
-    assert flips <= 40, flips
 
 
 # -------------------------------------------------------------------------------------------------------------
