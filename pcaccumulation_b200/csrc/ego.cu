@@ -395,12 +395,19 @@ __global__ void k_ego_finalize(const float* __restrict__ pose, const float* __re
         mm4(Ti, S, M);
         for (int k = 0; k < 16; ++k) G[k] = (float)M[k];
       }
-      // rotation error: acos(clamp((trace(R_est^T R_gt) - 1) / 2)) in degrees; translation error: |t_est - t_gt|
-      float tr = 0.f;
+      // rotation error (toolbox/register_utils.py:19-42): the angle of R_est^T R_gt in degrees.  The reference takes
+      // acos((trace - 1) / 2) in float32, which loses half of its digits for the sub-degree angles that occur here; the same
+      // angle is evaluated as atan2(|axis part|, (trace - 1) / 2) in double, i.e. at least as close to the exact value.
+      double Rr[9];
       for (int i = 0; i < 3; ++i)
-        for (int k = 0; k < 3; ++k) tr += E[4 * k + i] * G[4 * k + i];
-      float e = fminf(fmaxf((tr - 1.f) / 2.f, -1.f), 1.f);
-      rot_sum += (double)(180.f * acosf(e) / 3.14159274101257324f);
+        for (int j = 0; j < 3; ++j) {
+          double s = 0;
+          for (int k = 0; k < 3; ++k) s += (double)E[4 * k + i] * (double)G[4 * k + j];
+          Rr[3 * i + j] = s;
+        }
+      const double cs = fmin(fmax((Rr[0] + Rr[4] + Rr[8] - 1.0) * 0.5, -1.0), 1.0);
+      const double ax = Rr[7] - Rr[5], ay = Rr[2] - Rr[6], az = Rr[3] - Rr[1];
+      rot_sum += 180.0 * atan2(0.5 * sqrt(ax * ax + ay * ay + az * az), cs) / 3.14159265358979323846;
       float dx = E[3] - G[3], dy = E[7] - G[7], dz = E[11] - G[11];
       trans_sum += (double)sqrtf(dx * dx + dy * dy + dz * dz);
     }
