@@ -4,11 +4,14 @@
  * voxeliser (libs/voxel_generator.py) and the Chamfer extension (chamfer_distance/).  Conventions:
  *   - every pointer is a DEVICE pointer owned by the caller (torch-owned memory in the Python host),
  *     except the small `const float* range6 / voxel_size3` geometry arrays, which are HOST pointers;
- *   - the library allocates nothing and keeps no state besides the thread-local error string;
+ *   - the library allocates nothing and keeps no state besides the thread-local error string and per-device caches of
+ *     immutable facts (SM count, "kernel attribute already set" marks);
  *   - calls are asynchronous on `stream`, never synchronise the device, return 0 on success or a negative
  *     PCAB_ERR_* code (pcab_last_error() gives the message); nothing is printed, nothing exits;
  *   - scratch memory is passed in; each pcab_*_workspace() returns the bytes the matching call needs;
- *   - activations are NHWC float32; integer outputs are bit-exact with the reference.
+ *   - BEV activations are NHWC, in one of two element formats selected by an `fmt` argument: 0 = float32, 1 = P16
+ *     (csrc/pair16.cuh: every 32-channel group of a pixel is 32 fp16 h | 32 fp16 l with x = h + l, the operand format of the
+ *     tcgen05 convolutions; same 4 bytes per element); integer outputs are bit-exact with the reference.
  *
  * The reference interface each entry replaces is cited as file:line (relative to the reference root).
  */
@@ -57,8 +60,8 @@ int pcab_pillar_encode(const float* xyz, const int* point_time, const int* order
                        const int* coords_zyxt, const int* pillar_cell, const float* pillar_mean,
                        const float* weight_pack, int n_points, int n_pillars, const float* range6 /* host */,
                        const float* voxel_size3 /* host */, int n_sweeps, float* pillar_feats /* [M,32] */,
-                       float* canvas_nhwc /* zero-filled by the caller */, void* workspace, size_t workspace_bytes,
-                       pcab_stream_t stream);
+                       float* canvas_nhwc /* zero-filled by the caller */, int canvas_fmt, void* workspace,
+                       size_t workspace_bytes, pcab_stream_t stream);
 
 /* ---- convolutions: models/unet.py:11-113, models/stpn.py:13-22,80 ---------------------------------------- */
 /* FP32 CUDA-core path; sources accumulate into one output (concat / temporal 3x3x3) */
@@ -69,14 +72,12 @@ int pcab_conv3x3_f32(const float* src0, int c0, const float* src1, int c1, const
 int pcab_convT2x2_f32(const float* in, const float* weight_packed /* [4][Cin][Cout] */, const float* bias, float* out,
                       int n_images, int H, int W, int Cin, int Cout, int out_cstride, int out_coff,
                       pcab_stream_t stream);
-int pcab_maxpool2x2(const float* in, float* out, int n_images, int H, int W, int C, pcab_stream_t stream);
-int pcab_temporal_max(const float* in, float* out, int B, int T, int H, int W, int C, pcab_stream_t stream);
+int pcab_maxpool2x2(const float* in, float* out, int n_images, int H, int W, int C, int fmt, pcab_stream_t stream);
+int pcab_temporal_max(const float* in, float* out, int B, int T, int H, int W, int C, int fmt, pcab_stream_t stream);
 
 /* tcgen05 tensor-core path (3xTF32 split, FP32 accumulate in TMEM); same semantics as pcab_conv3x3_f32 */
 int pcab_conv3x3_tc_supported(int n_sources, int c0, int c1, int c2, int Cout, int H, int W);
-int pcab_conv3x3_tc_set_base_offset_mode(int mode); /* debug: UMMA descriptor base-offset policy for shifted views */
 int pcab_conv3x3_tc_plan(int n_images, int H, int W, int Cout, int* out10 /* host: c, mt, strip, mtx, R, Wt, tiles_x, tiles_y, cout tiles, work items */);
-int pcab_conv3x3_tc_set_stats(long long* device_counters); /* debug: 148*16 int64 wait-cycle counters (NULL = off) */
 size_t pcab_conv3x3_tc_pack_floats(int cin_total, int Cout);
 int pcab_conv3x3_tc(const float* src0, int c0, const float* src1, int c1, const float* src2, int c2, int temporal_T,
                     const float* weight_tc_packed, const float* bias, const float* bn_scale, const float* bn_shift,
@@ -89,16 +90,32 @@ int pcab_conv3x3_tc_f16(const float* src0, int c0, const float* src1, int c1, co
                         const float* bn_shift, int relu, float* out, int n_images, int H, int W, int Cout, int out_cstride,
                         int out_coff, pcab_stream_t stream);
 
+/* tcgen05 path over P16 activations (csrc/conv_p16.cu): sources and output are P16 tensors, the epilogue writes the (h, l)
+ * pairs and TMA-stores them; weights as for pcab_conv3x3_tc_f16.  src0_cstride: 0, or the channel count of the tensor src0
+ * points INTO (src0 = first byte of the first used 32-channel group) -- reads a channel slice of a wider tensor.
+ * sat_counter (device, may be NULL) is incremented when an output beyond +-65504 was clamped.
+ * pcab_convT2x2_p16: ConvTranspose2d(kernel 2, stride 2) (models/unet.py:24-33) as a 1-tap GEMM with 4*Cout columns on the
+ * same pipeline; weights fp16 [2][4*Cout][Cin/32][64], column = (dy*2+dx)*Cout + co. */
+int pcab_conv3x3_p16_supported(int n_sources, int c0, int c1, int c2, int Cout, int H, int W);
+int pcab_conv_p16_plan(int n_images, int H, int W, int Cout, int cin_total, int ntaps, int* out12 /* host */);
+int pcab_conv3x3_p16(const void* src0, int c0, int src0_cstride, const void* src1, int c1, const void* src2, int c2,
+                     int temporal_T, const void* weight_f16_packed, float weight_scale_inv, const float* bias,
+                     const float* bn_scale, const float* bn_shift, int relu, void* out, int n_images, int H, int W, int Cout,
+                     unsigned int* sat_counter, pcab_stream_t stream);
+int pcab_convT2x2_p16(const void* in, int Cin, const void* weight_f16_packed, float weight_scale_inv, const float* bias,
+                      void* out /* [n,2H,2W,Cout] P16 */, int n_images, int H, int W, int Cout, unsigned int* sat_counter,
+                      pcab_stream_t stream);
+
 /* ---- heads / BEV ops: models/motionnet.py:45-135,167-170,188-194 ------------------------------------------ */
-int pcab_head2_conv(const float* in_nhwc, int cin, const float* weight_packed /* [9][cin][2] */, const float* bias,
-                    int n_images, int H, int W, float* logits_nchw /* [n,2,H,W] */, int* argmax_map /* [n,H,W] */,
-                    pcab_stream_t stream);
+int pcab_head2_conv(const float* in_nhwc, int cin, int in_cstride /* channels per pixel of `in` (>= cin) */, int fmt,
+                    const float* weight_packed /* [9][cin][2] */, const float* bias, int n_images, int H, int W,
+                    float* logits_nchw /* [n,2,H,W] */, int* argmax_map /* [n,H,W] */, pcab_stream_t stream);
 int pcab_fb_per_point(const int* fb_map, const int* pillar_cell, const int* p2v, int n_points,
                       long long* fb_per_point, pcab_stream_t stream);
 int pcab_canvases(const int* pillar_cell, const int* fb_sub, const float* pillar_mean, int n_pillars, int H, int W,
                   float* occ_map, long long* fb_map, float* mean_map /* [B*T,3,H,W] */, pcab_stream_t stream);
 int pcab_warp_bev(const float* bev_nhwc, const float* pose /* [B*T,4,4] */, int B, int T, int H, int W, int C, float vx,
-                  float vy, float x_min, float y_min, float* out_nhwc, pcab_stream_t stream);
+                  float vy, float x_min, float y_min, float* out_nhwc, int fmt, pcab_stream_t stream);
 int pcab_transform_points(const float* xyz, const int* point_frame, const float* pose, int n_points, float* out,
                           pcab_stream_t stream);
 
@@ -107,7 +124,7 @@ size_t pcab_bg_compact_workspace(long long n_cells);
 int pcab_bg_compact(const int* cell_to_pillar, const int* fb_est, int n_frames, int H, int W, int* bg_cells,
                     int* frame_off /* [n_frames+1] */, void* workspace, size_t workspace_bytes, pcab_stream_t stream);
 size_t pcab_ego_pairs_workspace(int npairs);
-int pcab_ego_pairs(const float* geo_nhwc /* [B*T,H,W,64] */, const int* cell_to_pillar, const float* pillar_mean,
+int pcab_ego_pairs(const float* geo_nhwc /* [B*T,H,W,64] */, int geo_fmt, const int* cell_to_pillar, const float* pillar_mean,
                    const int* pillar_frame, int n_pillars, const int* bg_cells, const int* frame_off,
                    const int* pair_frames /* [P,2] source,target frame */, const int* choice /* [P,2,1024] */,
                    const float* thr2 /* [P] */, int npairs, const float* alpha, const float* beta, int sinkhorn_iters,
@@ -120,7 +137,7 @@ int pcab_ego_pairs(const float* geo_nhwc /* [B*T,H,W,64] */, const int* cell_to_
 size_t pcab_select_workspace(int n);
 int pcab_select_indices(const int* flags, const long long* values, long long value, int n, int* idx, int* count,
                         void* workspace, size_t workspace_bytes, pcab_stream_t stream);
-int pcab_ungrid(const float* feats_nhwc, int C, int H, int W, const float* xyz, const int* frame_of_point,
+int pcab_ungrid(const float* feats_nhwc, int C, int fmt, int H, int W, const float* xyz, const int* frame_of_point,
                 const int* idx, int k, float x_abs, float y_abs, float* out /* [k,C] */, pcab_stream_t stream);
 int pcab_stpn_head_pack_size(void);
 int pcab_init_point_outputs(int n_points, float* mos, float* offset, pcab_stream_t stream);
@@ -131,8 +148,7 @@ int pcab_stpn_head(const float* mos_feats_nhwc /* [B,H,W,64] */, int H, int W, c
  * as [hi 64 rows; lo 64 rows][32]; which = 1: floats of w_tc = [final_proj; mos_seg[0]; offset_head[0]] x [hi 128 rows; lo 128
  * rows][128] (rows = output channels, K-major, hi = weight rounded to tf32, lo = weight - hi). */
 size_t pcab_stpn_head_tc_pack_floats(int which);
-int pcab_stpn_head_tc_set_stats(long long* device_counters /* 148*2*8 int64, or NULL */);
-int pcab_stpn_head_tc(const float* mos_feats_nhwc, int H, int W, const float* transformed_points, const int* point_batch,
+int pcab_stpn_head_tc(const float* mos_feats_nhwc, int feats_fmt, int H, int W, const float* transformed_points, const int* point_batch,
                       const int* fg_idx, int n_fg, const float* weight_pack_host /* HOST copy of the pcab_stpn_head pack */,
                       const float* w1_tc, const float* w_tc,
                       float x_abs, float y_abs, float* mos_out, float* offset_out, pcab_stream_t stream);

@@ -45,11 +45,12 @@ SYMBOLS = [
     "pcab_last_error", "pcab_version", "pcab_voxelize_workspace", "pcab_voxelize", "pcab_pillar_index_workspace",
     "pcab_pillar_index", "pcab_pillar_stats", "pcab_pillar_cells", "pcab_pfn_pack_size",
     "pcab_pillar_encode_workspace", "pcab_pillar_encode", "pcab_conv3x3_f32", "pcab_convT2x2_f32", "pcab_maxpool2x2",
-    "pcab_temporal_max", "pcab_conv3x3_tc_supported", "pcab_conv3x3_tc_set_base_offset_mode", "pcab_conv3x3_tc_set_stats", "pcab_conv3x3_tc_plan", "pcab_conv3x3_tc_pack_floats", "pcab_conv3x3_tc", "pcab_conv3x3_tc_f16",
+    "pcab_temporal_max", "pcab_conv3x3_tc_supported", "pcab_conv3x3_tc_plan", "pcab_conv3x3_tc_pack_floats", "pcab_conv3x3_tc", "pcab_conv3x3_tc_f16",
+    "pcab_conv3x3_p16_supported", "pcab_conv_p16_plan", "pcab_conv3x3_p16", "pcab_convT2x2_p16",
     "pcab_head2_conv", "pcab_fb_per_point", "pcab_canvases", "pcab_warp_bev", "pcab_transform_points",
     "pcab_bg_compact_workspace", "pcab_bg_compact", "pcab_ego_pairs_workspace", "pcab_ego_pairs",
     "pcab_select_workspace", "pcab_select_indices", "pcab_ungrid", "pcab_stpn_head_pack_size",
-    "pcab_init_point_outputs", "pcab_stpn_head", "pcab_stpn_head_tc_pack_floats", "pcab_stpn_head_tc_set_stats", "pcab_stpn_head_tc", "pcab_dynamic_flags", "pcab_cluster_workspace", "pcab_cluster_scene",
+    "pcab_init_point_outputs", "pcab_stpn_head", "pcab_stpn_head_tc_pack_floats", "pcab_stpn_head_tc", "pcab_dynamic_flags", "pcab_cluster_workspace", "pcab_cluster_scene",
     "pcab_tpn_relabel", "pcab_tpn_rows_workspace", "pcab_tpn_rows", "pcab_tpn_static_embed", "pcab_tpn_iteration_workspace", "pcab_tpn_iteration", "pcab_embed_segmax_tc", "pcab_tpn_pos_l0", "pcab_apply_seg_pose",
     "pcab_scatter_rows3", "pcab_prep_points_workspace", "pcab_prep_points", "pcab_flow_eval", "pcab_cluster_eval_workspace", "pcab_cluster_eval", "pcab_chamfer_workspace", "pcab_chamfer_forward", "pcab_chamfer_backward",
 ]

@@ -5,51 +5,60 @@
 // :188-194 (FB decision + inverse scatter), models/pillar_encoder.py:177-204 and the second conv of
 // SegHead2D (models/unet.py:268) for the 2-class semseg head.
 #include "common.cuh"
+#include "pair16.cuh"
 #include "pcab200.h"
 
 namespace {
 
-// conv3x3 Cin -> 2 (pad 1), NHWC input, planar NCHW logits out [n][2][H][W] + argmax (first max wins)
-template <int CIN>
+// conv3x3 Cin -> 2 (pad 1), NHWC input (float32 or P16), planar NCHW logits out [n][2][H][W] + argmax (first max wins).
+// CTA = 8 x 32 output pixels: the 10 x 34 halo tile is staged channel-planar in shared memory with coalesced 16-byte
+// loads (a thread-per-pixel gather would fetch nine whole 128-byte pixels per thread), then one thread per pixel runs
+// the 9 x CIN x 2 FMAs in the reference's (ky, kx, c) order from conflict-free shared-memory columns.
+constexpr int H2_TH = 8, H2_TW = 32, H2_P = 345;  // P: halo-tile pixel pitch of a channel plane, == 1 (mod 8): conflict-free transposing stores
+template <int CIN, bool P16>
 __global__ void __launch_bounds__(256) k_head2(const float* __restrict__ in, const float* __restrict__ w /* [9][CIN][2] */,
-                                               const float* __restrict__ bias, int N, int H, int W,
+                                               const float* __restrict__ bias, int N, int H, int W, int CS /* channels of `in` */,
                                                float* __restrict__ logits, int* __restrict__ argmax) {
-  __shared__ float sw[9 * CIN * 2];
+  extern __shared__ __align__(16) float sm_h2[];
+  float* tile = sm_h2;                 // [CIN][H2_P]
+  float* sw = sm_h2 + CIN * H2_P;      // [9][CIN][2]
   for (int i = threadIdx.x; i < 9 * CIN * 2; i += blockDim.x) sw[i] = w[i];
+  const int tiles_x = (W + H2_TW - 1) / H2_TW, tiles_y = (H + H2_TH - 1) / H2_TH;
+  const int tx0 = (blockIdx.x % tiles_x) * H2_TW, ty0 = ((blockIdx.x / tiles_x) % tiles_y) * H2_TH, n = blockIdx.x / (tiles_x * tiles_y);
+  constexpr int HW_ = H2_TW + 2, HH_ = H2_TH + 2, C4 = CIN / 4;
+  for (int e = threadIdx.x; e < HH_ * HW_ * C4; e += blockDim.x) {
+    const int q = e % C4, hp = e / C4, hy = hp / HW_, hx = hp % HW_;
+    const int gy = ty0 + hy - 1, gx = tx0 + hx - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = p16::ld4<P16>(in, ((size_t)n * H + gy) * W + gx, CS, 4 * q);
+    float* d = tile + (4 * q) * H2_P + hp;
+    d[0] = v.x, d[H2_P] = v.y, d[2 * H2_P] = v.z, d[3 * H2_P] = v.w;
+  }
   __syncthreads();
-  long long total = (long long)N * H * W;
-  long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
-    int x = (int)(e % W);
-    int y = (int)((e / W) % H);
-    int n = (int)(e / ((long long)W * H));
-    float a0 = 0.f, a1 = 0.f;
+  const int ty = threadIdx.x / H2_TW, tx = threadIdx.x % H2_TW;
+  const int y = ty0 + ty, x = tx0 + tx;
+  if (y >= H || x >= W) return;
+  float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      int gy = y + ky - 1;
-      if (gy < 0 || gy >= H) continue;
+  for (int ky = 0; ky < 3; ++ky) {
+    if (y + ky - 1 < 0 || y + ky - 1 >= H) continue;  // (zero padding: skipped like the taps outside the image before)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        int gx = x + kx - 1;
-        if (gx < 0 || gx >= W) continue;
-        const float4* p = reinterpret_cast<const float4*>(in + (((size_t)n * H + gy) * W + gx) * CIN);
-        const float* ww = sw + (ky * 3 + kx) * CIN * 2;
+    for (int kx = 0; kx < 3; ++kx) {
+      if (x + kx - 1 < 0 || x + kx - 1 >= W) continue;
+      const float* t = tile + (ty + ky) * HW_ + tx + kx;
+      const float* ww = sw + (ky * 3 + kx) * CIN * 2;
 #pragma unroll
-        for (int c4 = 0; c4 < CIN / 4; ++c4) {
-          float4 v = p[c4];
-          a0 = fmaf(v.x, ww[8 * c4 + 0], a0), a1 = fmaf(v.x, ww[8 * c4 + 1], a1);
-          a0 = fmaf(v.y, ww[8 * c4 + 2], a0), a1 = fmaf(v.y, ww[8 * c4 + 3], a1);
-          a0 = fmaf(v.z, ww[8 * c4 + 4], a0), a1 = fmaf(v.z, ww[8 * c4 + 5], a1);
-          a0 = fmaf(v.w, ww[8 * c4 + 6], a0), a1 = fmaf(v.w, ww[8 * c4 + 7], a1);
-        }
+      for (int c = 0; c < CIN; ++c) {
+        const float v = t[c * H2_P];
+        a0 = fmaf(v, ww[2 * c], a0), a1 = fmaf(v, ww[2 * c + 1], a1);
       }
     }
-    a0 += bias[0], a1 += bias[1];
-    size_t hw = (size_t)H * W;
-    logits[(size_t)n * 2 * hw + (size_t)y * W + x] = a0;
-    logits[(size_t)n * 2 * hw + hw + (size_t)y * W + x] = a1;
-    argmax[e] = a1 > a0 ? 1 : 0;
   }
+  a0 += bias[0], a1 += bias[1];
+  const size_t hw = (size_t)H * W;
+  logits[(size_t)n * 2 * hw + (size_t)y * W + x] = a0;
+  logits[(size_t)n * 2 * hw + hw + (size_t)y * W + x] = a1;
+  argmax[(size_t)n * hw + (size_t)y * W + x] = a1 > a0 ? 1 : 0;
 }
 
 __global__ void k_fb_per_point(const int* __restrict__ fb_map, const int* __restrict__ pillar_cell,
@@ -101,7 +110,9 @@ __device__ void inv4_rows01(const float* P, float* out6) {
 
 constexpr int kMaxWarpFrames = 256;
 
-// bilinear warp of frames 1..T-1 by inv(pose) (zeros padding, align_corners=False); slot 0 = frame T-1 (quirk Q1)
+// bilinear warp of frames 1..T-1 by inv(pose) (zeros padding, align_corners=False); slot 0 = frame T-1 (quirk Q1).
+// Input and output share the activation format (float32 NHWC or P16).
+template <bool P16>
 __global__ void __launch_bounds__(256) k_warp(const float* __restrict__ bev, const float* __restrict__ pose, int B,
                                               int T, int H, int W, int C4, float vx, float vy, float x_min, float y_min,
                                               float* __restrict__ out) {
@@ -109,7 +120,8 @@ __global__ void __launch_bounds__(256) k_warp(const float* __restrict__ bev, con
   for (int f = threadIdx.x; f < B * T; f += blockDim.x) inv4_rows01(pose + (size_t)f * 16, s_inv[f]);
   __syncthreads();
   long long total = (long long)B * T * H * W;
-  int lane_c = threadIdx.x % C4;  // threads of a pixel cover its channels (float4 each)
+  const int C = 4 * C4;
+  int lane_c = threadIdx.x % C4;  // threads of a pixel cover its channels (four each)
   int pix_per_block = blockDim.x / C4;
   for (long long pix = (long long)blockIdx.x * pix_per_block + threadIdx.x / C4; pix < total;
        pix += (long long)gridDim.x * pix_per_block) {
@@ -117,9 +129,8 @@ __global__ void __launch_bounds__(256) k_warp(const float* __restrict__ bev, con
     int y = (int)((pix / W) % H);
     int f = (int)(pix / ((long long)W * H));
     int b = f / T, t = f % T;
-    float4* dst = reinterpret_cast<float4*>(out) + pix * C4 + lane_c;
     if (t == 0) {
-      *dst = reinterpret_cast<const float4*>(bev)[(((size_t)(b * T + T - 1) * H + y) * W + x) * C4 + lane_c];
+      p16::st4<P16>(out, (size_t)pix, C, 4 * lane_c, p16::ld4<P16>(bev, ((size_t)(b * T + T - 1) * H + y) * W + x, C, 4 * lane_c));
       continue;
     }
     const float* iv = s_inv[f];
@@ -134,10 +145,10 @@ __global__ void __launch_bounds__(256) k_warp(const float* __restrict__ bev, con
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
     if (fx0 >= -1.f && fx0 <= (float)W && fy0 >= -1.f && fy0 <= (float)H) {
       int x0 = (int)fx0, y0 = (int)fy0;
-      const float4* src = reinterpret_cast<const float4*>(bev) + (size_t)f * H * W * C4 + lane_c;
+      const size_t fbase = (size_t)f * H * W;
       auto tap = [&](int xx, int yy, float wgt) {
         if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
-          float4 s = src[((size_t)yy * W + xx) * C4];
+          const float4 s = p16::ld4<P16>(bev, fbase + (size_t)yy * W + xx, C, 4 * lane_c);
           r.x = fmaf(s.x, wgt, r.x), r.y = fmaf(s.y, wgt, r.y), r.z = fmaf(s.z, wgt, r.z), r.w = fmaf(s.w, wgt, r.w);
         }
       };
@@ -146,7 +157,7 @@ __global__ void __launch_bounds__(256) k_warp(const float* __restrict__ bev, con
       tap(x0, y0 + 1, wx0 * wy1);
       tap(x0 + 1, y0 + 1, wx1 * wy1);
     }
-    *dst = r;
+    p16::st4<P16>(out, (size_t)pix, C, 4 * lane_c, r);
   }
 }
 
@@ -169,15 +180,19 @@ __global__ void k_transform_points(const float* __restrict__ xyz, const int* __r
 
 }  // namespace
 
-extern "C" int pcab_head2_conv(const float* in_nhwc, int cin, const float* weight_packed, const float* bias,
-                               int n_images, int H, int W, float* logits_nchw, int* argmax_map, cudaStream_t stream) {
-  long long total = (long long)n_images * H * W;
-  if (cin == 32)
-    k_head2<32><<<grid_for(total, 256, 16), 256, 0, stream>>>(in_nhwc, weight_packed, bias, n_images, H, W, logits_nchw,
-                                                             argmax_map);
-  else {
-    pcab_set_error("pcab_head2_conv: unsupported cin %d", cin);
-    return PCAB_ERR_ARG;
+extern "C" int pcab_head2_conv(const float* in_nhwc, int cin, int in_cstride, int fmt, const float* weight_packed,
+                               const float* bias, int n_images, int H, int W, float* logits_nchw, int* argmax_map,
+                               cudaStream_t stream) {
+  PCAB_REQUIRE(cin == 32 && in_cstride >= cin && in_cstride % 32 == 0, "cin == 32, read from the first 32 of in_cstride channels");
+  const int blocks = n_images * cdiv(H, H2_TH) * cdiv(W, H2_TW);
+  const size_t smem = (size_t)(32 * H2_P + 9 * 32 * 2) * sizeof(float);
+  static PcabSmemOnce once0, once1;
+  if (fmt) {
+    PCAB_CUDA(pcab_set_max_smem(k_head2<32, true>, (int)smem, once1));
+    k_head2<32, true><<<blocks, 256, smem, stream>>>(in_nhwc, weight_packed, bias, n_images, H, W, in_cstride, logits_nchw, argmax_map);
+  } else {
+    PCAB_CUDA(pcab_set_max_smem(k_head2<32, false>, (int)smem, once0));
+    k_head2<32, false><<<blocks, 256, smem, stream>>>(in_nhwc, weight_packed, bias, n_images, H, W, in_cstride, logits_nchw, argmax_map);
   }
   PCAB_CHECK_LAUNCH("pcab_head2_conv");
   return PCAB_OK;
@@ -199,13 +214,15 @@ extern "C" int pcab_canvases(const int* pillar_cell, const int* fb_sub, const fl
 }
 
 extern "C" int pcab_warp_bev(const float* bev_nhwc, const float* pose, int B, int T, int H, int W, int C, float vx,
-                             float vy, float x_min, float y_min, float* out_nhwc, cudaStream_t stream) {
-  PCAB_REQUIRE(C % 4 == 0 && 256 % (C / 4) == 0, "C/4 must divide 256");
+                             float vy, float x_min, float y_min, float* out_nhwc, int fmt, cudaStream_t stream) {
+  PCAB_REQUIRE(C % 4 == 0 && 256 % (C / 4) == 0 && (!fmt || C % 32 == 0), "C/4 must divide 256 (P16: C%32)");
   PCAB_REQUIRE(B * T <= kMaxWarpFrames, "too many frames per call");
   long long total = (long long)B * T * H * W;
   int pix_per_block = 256 / (C / 4);
-  k_warp<<<grid_for(total, pix_per_block, 16), 256, 0, stream>>>(bev_nhwc, pose, B, T, H, W, C / 4, vx, vy, x_min, y_min,
-                                                                out_nhwc);
+  if (fmt)
+    k_warp<true><<<grid_for(total, pix_per_block, 16), 256, 0, stream>>>(bev_nhwc, pose, B, T, H, W, C / 4, vx, vy, x_min, y_min, out_nhwc);
+  else
+    k_warp<false><<<grid_for(total, pix_per_block, 16), 256, 0, stream>>>(bev_nhwc, pose, B, T, H, W, C / 4, vx, vy, x_min, y_min, out_nhwc);
   PCAB_CHECK_LAUNCH("pcab_warp_bev");
   return PCAB_OK;
 }

@@ -83,7 +83,7 @@ int one_way(const float* q, int n, const float* t, int m, int B, float* dist, in
   cudaMemsetAsync(scratch, 0xff, (size_t)B * n * 8, stream);
   int qblocks = cdiv(n, 256);
   // enough CTAs for ~4 waves of 148 SMs x 8 resident blocks, but at least one tile per split
-  int want = (148 * 8 * 4 + qblocks * B - 1) / (qblocks * B);
+  int want = (pcab_sm_count() * 8 * 4 + qblocks * B - 1) / (qblocks * B);
   int max_splits = cdiv(m, TILE);
   int splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
   if (splits > 65535) splits = 65535;

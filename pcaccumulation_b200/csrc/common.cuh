@@ -39,10 +39,30 @@ void pcab_set_error(const char* fmt, ...);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// SM count of the CURRENT device (148 on B200), cached per device ordinal; thread-safe (racing writers store the same value)
+int pcab_sm_count();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: remember per device ordinal what
+// has been set instead of a process-wide flag.  Racing threads at worst set the same value twice.
+struct PcabSmemOnce {
+  int done[64] = {};
+};
+template <typename K>
+static inline cudaError_t pcab_set_max_smem(K kernel, int bytes, PcabSmemOnce& once) {
+  int d = 0;
+  cudaError_t e = cudaGetDevice(&d);
+  if (e != cudaSuccess) return e;
+  const bool tracked = d >= 0 && d < 64;
+  if (tracked && __atomic_load_n(&once.done[d], __ATOMIC_ACQUIRE) >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && tracked) __atomic_store_n(&once.done[d], bytes, __ATOMIC_RELEASE);
+  return e;
+}
+
 // grid sized as a multiple of the SM count for grid-stride kernels
 static inline int grid_for(long long n, int block, int per_sm = 8) {
   long long want = (n + block - 1) / block;
-  long long cap = 148LL * per_sm;
+  long long cap = (long long)pcab_sm_count() * per_sm;
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);
 }

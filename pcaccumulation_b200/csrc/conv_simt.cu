@@ -11,6 +11,7 @@
 // These kernels are the full-precision reference path inside the product (used for layers whose shape
 // does not suit the tcgen05 tiles and as the on-device cross-check of the tensor-core path).
 #include "common.cuh"
+#include "pair16.cuh"
 #include "pcab200.h"
 
 namespace {
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(128, 3) k_convT2x2(const float* __restrict__ i
   }
 }
 
+template <bool P16>
 __global__ void k_maxpool2(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C) {
   int Ho = H / 2, Wo = W / 2, C4 = C / 4;
   long long total = (long long)N * Ho * Wo * C4;
@@ -261,27 +263,31 @@ __global__ void k_maxpool2(const float* __restrict__ in, float* __restrict__ out
     r /= Wo;
     int y = (int)(r % Ho);
     int n = (int)(r / Ho);
-    const float4* p = reinterpret_cast<const float4*>(in + (((size_t)n * H + 2 * y) * W + 2 * x) * C) + c;
-    float4 a = p[0], b = p[C4], d = p[(size_t)W * C4], f = p[(size_t)W * C4 + C4];
+    const size_t p00 = ((size_t)n * H + 2 * y) * W + 2 * x;
+    // (P16: h + l is exact in float32 and splits back to the same pair, so pooling pairs equals pooling values)
+    const float4 a = p16::ld4<P16>(in, p00, C, 4 * c), b = p16::ld4<P16>(in, p00 + 1, C, 4 * c),
+                 d = p16::ld4<P16>(in, p00 + W, C, 4 * c), f = p16::ld4<P16>(in, p00 + W + 1, C, 4 * c);
     float4 m = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, f.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, f.y)),
                            fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, f.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, f.w)));
-    reinterpret_cast<float4*>(out)[e] = m;
+    p16::st4<P16>(out, ((size_t)n * Ho + y) * Wo + x, C, 4 * c, m);
   }
 }
 
 // max over the T frames of each scene: in [B*T, HW, C] -> out [B, HW, C]
-__global__ void k_temporal_max(const float* __restrict__ in, float* __restrict__ out, int B, int T, long long hwc4) {
-  long long total = (long long)B * hwc4;
+template <bool P16>
+__global__ void k_temporal_max(const float* __restrict__ in, float* __restrict__ out, int B, int T, long long hw, int C) {
+  const int C4 = C / 4;
+  long long total = (long long)B * hw * C4;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
-    long long b = e / hwc4, r = e % hwc4;
-    const float4* p = reinterpret_cast<const float4*>(in) + (size_t)b * T * hwc4 + r;
-    float4 m = p[0];
+    const int c = (int)(e % C4);
+    const long long pix = e / C4, b = pix / hw, r = pix % hw;
+    float4 m = p16::ld4<P16>(in, (size_t)(b * T) * hw + r, C, 4 * c);
     for (int t = 1; t < T; ++t) {
-      float4 v = p[(size_t)t * hwc4];
+      const float4 v = p16::ld4<P16>(in, (size_t)(b * T + t) * hw + r, C, 4 * c);
       m.x = fmaxf(m.x, v.x), m.y = fmaxf(m.y, v.y), m.z = fmaxf(m.z, v.z), m.w = fmaxf(m.w, v.w);
     }
-    reinterpret_cast<float4*>(out)[e] = m;
+    p16::st4<P16>(out, (size_t)pix, C, 4 * c, m);
   }
 }
 
@@ -289,11 +295,8 @@ template <int TH, int TW, int COT>
 int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   constexpr int NT = (TH * TW / 4) * (COT / 16);
   size_t smem = (size_t)(CK * (TH + 2) * (TW + 4) + 9 * CK * COT) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(k_conv3x3<TH, TW, COT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  static PcabSmemOnce once;
+  if (pcab_set_max_smem(k_conv3x3<TH, TW, COT>, (int)smem, once) != cudaSuccess) return -1;
   dim3 grid(cdiv(a.H, TH) * cdiv(a.W, TW), cdiv(a.Cout, COT), a.N);
   k_conv3x3<TH, TW, COT><<<grid, NT, smem, stream>>>(a);
   return 0;
@@ -340,28 +343,31 @@ extern "C" int pcab_convT2x2_f32(const float* in, const float* weight_packed, co
   int npix = n_images * H * W;
   dim3 grid(cdiv(npix, 64), Cout / 32);
   const size_t smem = (size_t)(2 * TK * TLD + 2 * TK * 128) * sizeof(float);
-  static bool cfg = false;
-  if (!cfg) {
-    cudaFuncSetAttribute(k_convT2x2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cfg = true;
-  }
+  static PcabSmemOnce once;
+  PCAB_CUDA(pcab_set_max_smem(k_convT2x2, (int)smem, once));
   k_convT2x2<<<grid, 128, smem, stream>>>(in, weight_packed, bias, out, npix, H, W, Cin, Cout, out_cstride, out_coff);
   PCAB_CHECK_LAUNCH("pcab_convT2x2_f32");
   return PCAB_OK;
 }
 
-extern "C" int pcab_maxpool2x2(const float* in, float* out, int n_images, int H, int W, int C, cudaStream_t stream) {
-  PCAB_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "C%4, even H/W");
+extern "C" int pcab_maxpool2x2(const float* in, float* out, int n_images, int H, int W, int C, int fmt, cudaStream_t stream) {
+  PCAB_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0 && (!fmt || C % 32 == 0), "C%4 (P16: C%32), even H/W");
   long long total = (long long)n_images * (H / 2) * (W / 2) * (C / 4);
-  k_maxpool2<<<grid_for(total, 256), 256, 0, stream>>>(in, out, n_images, H, W, C);
+  if (fmt)
+    k_maxpool2<true><<<grid_for(total, 256), 256, 0, stream>>>(in, out, n_images, H, W, C);
+  else
+    k_maxpool2<false><<<grid_for(total, 256), 256, 0, stream>>>(in, out, n_images, H, W, C);
   PCAB_CHECK_LAUNCH("pcab_maxpool2x2");
   return PCAB_OK;
 }
 
-extern "C" int pcab_temporal_max(const float* in, float* out, int B, int T, int H, int W, int C, cudaStream_t stream) {
-  PCAB_REQUIRE(C % 4 == 0, "C%4");
-  long long hwc4 = (long long)H * W * C / 4;
-  k_temporal_max<<<grid_for(B * hwc4, 256), 256, 0, stream>>>(in, out, B, T, hwc4);
+extern "C" int pcab_temporal_max(const float* in, float* out, int B, int T, int H, int W, int C, int fmt, cudaStream_t stream) {
+  PCAB_REQUIRE(C % 4 == 0 && (!fmt || C % 32 == 0), "C%4 (P16: C%32)");
+  long long hw = (long long)H * W, total = (long long)B * hw * (C / 4);
+  if (fmt)
+    k_temporal_max<true><<<grid_for(total, 256), 256, 0, stream>>>(in, out, B, T, hw, C);
+  else
+    k_temporal_max<false><<<grid_for(total, 256), 256, 0, stream>>>(in, out, B, T, hw, C);
   PCAB_CHECK_LAUNCH("pcab_temporal_max");
   return PCAB_OK;
 }

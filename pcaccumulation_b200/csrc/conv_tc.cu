@@ -10,12 +10,10 @@
 // plane  [(R+2) x (Wt+2) pixels][32 ch]  (zero-filled outside the image = the conv padding) into shared memory,
 // 128 bytes per pixel = one swizzle row.  Output pixels are indexed in the FLATTENED padded grid m = r*(Wt+2)+x,
 // so the A operand of tap (ky,kx) is the same plane viewed from row  m + ky*(Wt+2) + kx : nine shifted views of
-// one staged plane instead of nine loads (the two extra columns per row compute garbage that is never stored).
+// one staged plane instead of nine loads (the two extra columns per row compute garbage that is never stored; wide maps use 8-pixel strips instead, see below).
 // 3xTF32:  a = a_hi + a_lo, w = w_hi + w_lo; a_hi = the 19 bits the tensor core reads of a, w_hi = w rounded to tf32;
 //          acc += a_hi*[w_hi|w_lo] (one N=2*Cout MMA) + a_lo*w_hi   (a_lo*w_lo ~ 2^-22 is dropped).
-// w_hi / w_lo are pre-split on the host; a_lo is produced in shared memory by the epilogue warps right after the
-// plane lands.  Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = a_lo split and
-// epilogue (tcgen05.ld -> bias/BN/ReLU -> NHWC global stores).
+// w_hi / w_lo are pre-split on the host; a_lo is produced in shared memory by the split warps right after the plane lands.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -24,236 +22,12 @@
 
 namespace {
 
-constexpr int kThreads = 192;
-constexpr int kMaxSmem = 227 * 1024;
-
-struct TcArgs {
-  int nsrc;
-  int src_c[3];
-  int T;  // temporal frames per scene (1 = plain)
-  int N, H, W, Cout;
-  int cout_t;   // output channels per CTA (MMA N)
-  int mt;       // M tiles (of 128 flattened pixels) per CTA
-  int R, Wt, Wp;
-  int plane_rows;  // allocated rows (128 B each) per plane
-  int tiles_x, tiles_y;
-  int relu;
-  int out_cstride, out_coff;
-  int base_offset_mode;
-  int nst;  // weight pipeline stages (2..4)
-  const float* bias;
-  const float* bn_scale;
-  const float* bn_shift;
-  float* out;
-};
-
 using namespace pcab_tc;
 
-__global__ void __launch_bounds__(kThreads, 2)
-k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-             const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [plane_hi][plane_lo][b stage 0: hi, lo][b stage 1: hi, lo][barriers]
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t plane_bytes = (uint32_t)a.plane_rows * 128u;
-  const uint32_t b_bytes = (uint32_t)a.cout_t * 128u;
-  uint8_t* plane_hi = base;
-  uint8_t* plane_lo = base + plane_bytes;
-  uint8_t* b_stage = base + 2 * plane_bytes;  // stage s: hi at s*2*b_bytes, lo at +b_bytes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stage + 2 * a.nst * b_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  const uint32_t bar_a_full = smem_u32(bars + 0), bar_lo_done = smem_u32(bars + 1), bar_a_free = smem_u32(bars + 2);
-  const uint32_t bar_acc = smem_u32(bars + 3), bar_b_full0 = smem_u32(bars + 4), bar_b_empty0 = smem_u32(bars + 8);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, n = tile / (a.tiles_x * a.tiles_y);
-  const int x0 = tx * a.Wt, y0 = ty * a.R;
-  const int co0 = blockIdx.y * a.cout_t;
-  const int tframe = a.T > 1 ? n % a.T : 0;
-
-  // chunk list: (source, channel offset), identical for every role
-  int nchunks = 0;
-  for (int s = 0; s < a.nsrc; ++s) {
-    bool valid = a.T <= 1 || (tframe + s - 1 >= 0 && tframe + s - 1 < a.T);
-    if (valid) nchunks += a.src_c[s] / 32;
-  }
-
-  uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * a.mt * a.cout_t) tmem_cols <<= 1;  // main + correction accumulators
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar_a_full, 1);
-    mbar_init(bar_lo_done, 128);
-    mbar_init(bar_a_free, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(bar_b_full0 + 8 * i, 1), mbar_init(bar_b_empty0 + 8 * i, 1);
-    mbar_init(bar_acc, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int ci = 0, bs = 0, bph = 0;
-      int kbase_src = 0;
-      for (int s = 0; s < a.nsrc; ++s) {
-        const int Cs = a.src_c[s];
-        bool valid = a.T <= 1 || (tframe + s - 1 >= 0 && tframe + s - 1 < a.T);
-        if (valid) {
-          const CUtensorMap* am = a.T > 1 ? &map_a0 : (s == 0 ? &map_a0 : (s == 1 ? &map_a1 : &map_a2));
-          const int nsrc_img = a.T > 1 ? n + s - 1 : n;
-          for (int c0 = 0; c0 < Cs; c0 += 32, ++ci) {
-            if (ci > 0) mbar_wait(bar_a_free, (ci - 1) & 1);
-            mbar_expect_tx(bar_a_full, (uint32_t)(a.R + 2) * a.Wp * 128u);
-            tma_load_4d(am, smem_u32(plane_hi), bar_a_full, c0, x0 - 1, y0 - 1, nsrc_img);
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(bar_b_empty0 + 8 * bs, bph ^ 1);
-              mbar_expect_tx(bar_b_full0 + 8 * bs, 2 * b_bytes);
-              const int k0 = kbase_src + tap * Cs + c0;
-              tma_load_2d(&map_b, smem_u32(b_stage + (2 * bs) * b_bytes), bar_b_full0 + 8 * bs, k0, co0);
-              tma_load_2d(&map_b, smem_u32(b_stage + (2 * bs + 1) * b_bytes), bar_b_full0 + 8 * bs, k0, a.Cout + co0);
-              if (++bs == a.nst) bs = 0, bph ^= 1;
-            }
-          }
-        }
-        kbase_src += 9 * Cs;
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // The whole warp runs this loop with warp-uniform values (so descriptors live in uniform registers); only the
-    // tcgen05 instructions themselves are issued by one elected lane.  A descriptor differs from tile to tile only in
-    // its 14-bit start-address field, so it is built once and advanced with a 32-bit add per MMA.
-    {
-      // instruction descriptors: D=f32, A=B=tf32, K-major both, M = 128; N = 2*cout_t for the fused main MMA
-      // (weights staged as [w_hi rows | w_lo rows] = one 2*cout_t-row operand), N = cout_t for the a_lo correction
-      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
-      const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * a.cout_t) >> 3) << 17);
-      const uint32_t idesc1 = idesc_base | ((uint32_t)(a.cout_t >> 3) << 17);
-      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO, version, SWIZZLE_128B (upper word)
-      const uint32_t desc_lo0 = 1u << 16;                                          // LBO field (lower word)
-      const uint32_t ah16 = (smem_u32(plane_hi) & 0x3FFFF) >> 4, al16 = (smem_u32(plane_lo) & 0x3FFFF) >> 4;
-      const uint32_t b16 = (smem_u32(b_stage) & 0x3FFFF) >> 4, bstep16 = b_bytes >> 4;
-      int bs = 0, bph = 0;
-      for (int ci = 0; ci < nchunks; ++ci) {
-        mbar_wait(bar_lo_done, ci & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(bar_b_full0 + 8 * bs, bph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t shift16 = (uint32_t)((tap / 3) * a.Wp + (tap % 3)) * 8u;  // rows * 128 B / 16
-          const uint32_t bh16 = b16 + (uint32_t)(2 * bs) * bstep16;
-          for (int mt = 0; mt < a.mt; ++mt) {
-            // TMEM columns of tile mt: [0, c) = sum a_hi*w_hi (main), [c, 2c) = sum of the ~2^-11 smaller corrections
-            // a_hi*w_lo + a_lo*w_hi.  One N=2c MMA  a_hi x [w_hi | w_lo]  fills both halves reading a_hi ONCE (the kernel is
-            // bound by shared-memory operand bandwidth), one N=c MMA  a_lo x w_hi  adds into the correction half.  The
-            // tensor core truncates when it adds into an accumulator, so keeping the small terms out of the main half also
-            // cuts its number of (biased) roundings from 3K/8 to K/8.
-            const uint32_t tmem_d = tmem_base + (uint32_t)(mt * 2 * a.cout_t);
-            const uint32_t tmem_c = tmem_d + (uint32_t)a.cout_t;
-            const uint32_t arow16 = (uint32_t)(mt * 128) * 8u + shift16;
-            const uint32_t first = (ci == 0 && tap == 0) ? 0u : 1u;
-            if (elect_one()) {
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t dah = ((uint64_t)desc_hi << 32) | (desc_lo0 | (ah16 + arow16 + 2u * kk));
-                const uint64_t dal = ((uint64_t)desc_hi << 32) | (desc_lo0 | (al16 + arow16 + 2u * kk));
-                const uint64_t dbh = ((uint64_t)desc_hi << 32) | (desc_lo0 | (bh16 + 2u * kk));
-                umma_tf32(tmem_d, dah, dbh, idesc2, (kk == 0) ? first : 1u);
-                umma_tf32(tmem_c, dal, dbh, idesc1, 1u);
-              }
-            }
-            __syncwarp();
-          }
-          if (elect_one()) umma_commit(bar_b_empty0 + 8 * bs);  // frees this weight stage once the MMAs above retire
-          __syncwarp();
-          if (++bs == a.nst) bs = 0, bph ^= 1;
-        }
-        if (elect_one()) umma_commit(bar_a_free);  // planes may be overwritten
-        __syncwarp();
-      }
-      if (elect_one()) umma_commit(bar_acc);
-      __syncwarp();
-    }
-  } else {
-    // ===================== a_lo split, then epilogue =====================
-    const int et = threadIdx.x - 64;  // 0..127
-    const int n_f4 = (a.R + 2) * a.Wp * 8;  // float4 per plane (the rows the TMA box wrote)
-    for (int ci = 0; ci < nchunks; ++ci) {
-      mbar_wait(bar_a_full, ci & 1);
-      const float4* hi = reinterpret_cast<const float4*>(plane_hi);
-      float4* lo = reinterpret_cast<float4*>(plane_lo);
-      // a_hi is what the tensor core reads of the raw FP32 value (it ignores the low 13 mantissa bits), so the hi plane
-      // needs no rewrite; a_lo = a - trunc_tf32(a) is exact in FP32.  Four independent 128-bit loads in flight per thread.
-      auto low = [](float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); };
-      int i = et;
-      for (; i + 384 < n_f4; i += 512) {
-        float4 v0 = hi[i], v1 = hi[i + 128], v2 = hi[i + 256], v3 = hi[i + 384];
-        lo[i] = make_float4(low(v0.x), low(v0.y), low(v0.z), low(v0.w));
-        lo[i + 128] = make_float4(low(v1.x), low(v1.y), low(v1.z), low(v1.w));
-        lo[i + 256] = make_float4(low(v2.x), low(v2.y), low(v2.z), low(v2.w));
-        lo[i + 384] = make_float4(low(v3.x), low(v3.y), low(v3.z), low(v3.w));
-      }
-      for (; i < n_f4; i += 128) {
-        float4 v = hi[i];
-        lo[i] = make_float4(low(v.x), low(v.y), low(v.z), low(v.w));
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
-      mbar_arrive(bar_lo_done);
-    }
-    mbar_wait(bar_acc, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
-    for (int mt = 0; mt < a.mt; ++mt) {
-      const int m = mt * 128 + quarter * 32 + lane;
-      const int r = m / a.Wp, xc = m % a.Wp;
-      const int gy = y0 + r, gx = x0 + xc;
-      const bool valid = r < a.R && xc < a.Wt && gy < a.H && gx < a.W;
-      float* orow = a.out + (((size_t)n * a.H + gy) * a.W + gx) * a.out_cstride + a.out_coff + co0;
-      for (int c32 = 0; c32 < a.cout_t / 32; ++c32) {
-        uint32_t v[32], vc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * 2 * a.cout_t + c32 * 32), v);
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * 2 * a.cout_t + a.cout_t + c32 * 32), vc);
-        tmem_ld_wait(v, vc);
-        if (valid) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float o[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              int co = co0 + c32 * 32 + 4 * q + u;
-              float f = (__uint_as_float(v[4 * q + u]) + __uint_as_float(vc[4 * q + u])) + a.bias[co];
-              if (a.bn_scale) f = fmaf(f, a.bn_scale[co], a.bn_shift[co]);
-              o[u] = a.relu ? fmaxf(f, 0.f) : f;
-            }
-            *reinterpret_cast<float4*>(orow + c32 * 32 + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
-          }
-        }
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  }
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
-  }
-}
-
-
 // =====================================================================================================================
-// v2: persistent, fully pipelined kernel (one CTA per SM, 16 warps).
+// Persistent, fully pipelined kernel over FLOAT32 activations (one CTA per SM, 16 warps).  It serves
+// `conv_operands = "tf32"` (full float32 range) and float32-activation callers of the fp16-pair arithmetic; the default
+// path of the model is the pair-packed-activation kernel of conv_p16.cu, which has no operand-split pass.
 //   * each CTA walks a static list of (output tile, cout tile) work items;
 //   * hi planes are double buffered (TMA of chunk g+1 overlaps the MMAs of chunk g), so are the a_lo planes written by
 //     the splitter warps, the weight tap stages run through a 3-deep ring fed by their own producer warp;
@@ -267,7 +41,6 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__
 //     (used for narrow maps).
 // Warp roles (the warp scheduler favours high warp ids, so the latency-critical roles sit at the top):
 //   0-7 drain + epilogue | 8-11 a_lo split | 12 plane TMA | 13 weight TMA | 14,15 MMA issue (one M tile each; 14 owns TMEM)
-// Warp roles: 0 plane TMA | 1 weight TMA | 2,3 MMA issue (one M tile each; 2 also owns TMEM) | 4-11 drain + epilogue | 12-15 a_lo split
 // =====================================================================================================================
 namespace v2 {
 
@@ -738,7 +511,7 @@ bool choose(int n_img, int H, int W, int Cout, Cfg* best) {
           if (last >= kPlaneRows) continue;
           k.tiles_x = cdiv(W, Wt), k.tiles_y = cdiv(H, k.R), k.n_ctile = Cout / c;
           k.total = n_img * k.tiles_x * k.tiles_y * k.n_ctile;
-          const double rounds = (double)cdiv(k.total, 148);
+          const double rounds = (double)cdiv(k.total, pcab_sm_count());
           // cost ~ rounds x (MMA time of one item + fixed per-item overhead); one M tile leaves the second issuer idle
           const double cost = rounds * (mt == 2 ? 2.15 : 1.35) + 1e-3 * (double)k.total * mt * 128 / ((double)n_img * H * W * k.n_ctile);
           if (cost < best_cost - 1e-9) best_cost = cost, *best = k, found = true;
@@ -769,77 +542,7 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-struct TileCfg {
-  int cout_t, mt, Wt, Wp, R, plane_rows, nst;
-  size_t smem;
-};
-
-int g_max_stages = 4;
-int g_tile_mode = 1;  // 0: 4 M-tiles, 1 CTA/SM; 1: 2 M-tiles sized for 2 co-resident CTAs/SM (phases of one hide the other's)
-
-bool choose_cfg(int H, int W, int Cout, TileCfg* c) {
-  if (Cout % 32) return false;
-  c->cout_t = Cout <= 64 ? Cout : 64;  // 2 accumulators x 4 M-tiles x 64 columns = the 512 TMEM columns
-  if (Cout % c->cout_t) return false;
-  int Wt;
-  if (g_tile_mode == 0) {
-    c->mt = 4;
-    // widest column tile with Wt + 2 <= 98 that divides W when possible
-    Wt = W <= 96 ? W : 96;
-    for (int cand = 96; cand >= 48; --cand)
-      if (W % cand == 0) {
-        Wt = cand;
-        break;
-      }
-  } else {
-    c->mt = 2;
-    Wt = W <= 24 ? W : 24;
-    for (int cand = 24; cand >= 12; --cand)
-      if (W % cand == 0) {
-        Wt = cand;
-        break;
-      }
-  }
-  c->Wt = Wt;
-  c->Wp = Wt + 2;
-  c->R = (c->mt * 128) / c->Wp;
-  if (c->R > H) c->R = H;
-  if (c->R < 1) return false;
-  int rows = c->mt * 128 + 2 * c->Wp + 2;
-  int box = (c->R + 2) * c->Wp;
-  if (box > rows) rows = box;
-  c->plane_rows = (rows + 7) & ~7;
-  size_t cap = g_tile_mode == 0 ? (size_t)kMaxSmem : (size_t)113 * 1024;
-  for (c->nst = g_max_stages; c->nst >= 2; --c->nst) {  // deepest weight pipeline that fits
-    c->smem = (size_t)2 * c->plane_rows * 128 + (size_t)2 * c->nst * c->cout_t * 128 + 128 + 1024;
-    if (c->smem <= cap) break;
-  }
-  return c->nst >= 2 && c->smem <= cap && c->Wp <= 256 && c->R + 2 <= 256;
-}
-
-int g_base_offset_mode = 0;
-int g_min_hw = 16;
-long long* g_stats = nullptr;
-int g_dbg = 0;
-int g_impl = 2;  // 2: persistent pipelined kernel (v2); 1: the first-generation kernel
-
 }  // namespace
-
-extern "C" int pcab_conv3x3_tc_set_base_offset_mode(int mode) {
-  g_base_offset_mode = mode & 1;
-  g_tile_mode = ((mode >> 1) & 1) ^ 1;  // bit 1 set selects the large 1-CTA/SM tile shape (tuning knob)
-  g_min_hw = (mode & 4) ? 32 : 16;        // bit 2 set: leave maps below 32x32 to the FP32 path
-  g_max_stages = (mode & 8) ? 2 : 4;      // bit 3 set: 2-stage weight pipeline
-  g_impl = (mode & 16) ? 1 : 2;           // bit 4 set: first-generation kernel
-  g_dbg = (mode >> 5) & 31;               // bits 5-7: v2 timing experiments (results are wrong when set)
-  return 0;
-}
-
-// debug: device buffer of 148*16 int64 wait-cycle counters filled by the v2 kernel (null = off)
-extern "C" int pcab_conv3x3_tc_set_stats(long long* device_counters) {
-  g_stats = device_counters;
-  return 0;
-}
 
 // the tile plan the v2 kernel would use: out[0..9] = c, mt, strip, mtx, R, Wt, tiles_x, tiles_y, cout tiles, work items
 extern "C" int pcab_conv3x3_tc_plan(int n_images, int H, int W, int Cout, int* out10) {
@@ -855,13 +558,8 @@ extern "C" int pcab_conv3x3_tc_supported(int n_sources, int c0, int c1, int c2, 
   int cs[3] = {c0, c1, c2};
   for (int s = 0; s < n_sources; ++s)
     if (cs[s] <= 0 || cs[s] % 32) return 0;
-  if (g_impl == 2) {
-    v2::Cfg k;
-    return (H >= 8 && W >= 8 && v2::choose(1, H, W, Cout, &k)) ? 1 : 0;
-  }
-  if (H < g_min_hw || W < g_min_hw) return 0;  // the smallest maps keep the FP32 CUDA-core path (too few tiles for 148 SMs)
-  TileCfg c;
-  return choose_cfg(H, W, Cout, &c) ? 1 : 0;
+  v2::Cfg k;
+  return (H >= 8 && W >= 8 && v2::choose(1, H, W, Cout, &k)) ? 1 : 0;
 }
 
 // floats in the tensor-core weight pack: [2 (hi, lo)][Cout][9 * cin_total]
@@ -929,17 +627,15 @@ int conv3x3_tc_v2(EncodeTiledFn enc, const float* src0, int c0, const float* src
   a.relu = relu, a.out_cstride = out_cstride, a.out_coff = out_coff;
   a.bias = bias, a.bn_scale = bn_scale, a.bn_shift = bn_shift, a.out = out;
   a.wscale_inv = wscale_inv;
-  a.stats = g_stats;
-  a.dbg = g_dbg;
-  static bool configured = false;
-  if (!configured) {
-    PCAB_CUDA(cudaFuncSetAttribute(v2::k_conv3x3_tc2<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::smem_bytes(32)));
-    PCAB_CUDA(cudaFuncSetAttribute(v2::k_conv3x3_tc2<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::smem_bytes(64)));
-    PCAB_CUDA(cudaFuncSetAttribute(v2::k_conv3x3_tc2<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::smem_bytes(32)));
-    PCAB_CUDA(cudaFuncSetAttribute(v2::k_conv3x3_tc2<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::smem_bytes(64)));
-    configured = true;
-  }
-  const int grid = cfg.total < 148 ? cfg.total : 148;
+  a.stats = nullptr;  // per-CTA wait-cycle counters and timing experiments: compiled in, switched on only from a debugger
+  a.dbg = 0;
+  static PcabSmemOnce o32f, o64f, o32h, o64h;
+  PCAB_CUDA(pcab_set_max_smem(v2::k_conv3x3_tc2<32, false>, (int)v2::smem_bytes(32), o32f));
+  PCAB_CUDA(pcab_set_max_smem(v2::k_conv3x3_tc2<64, false>, (int)v2::smem_bytes(64), o64f));
+  PCAB_CUDA(pcab_set_max_smem(v2::k_conv3x3_tc2<32, true>, (int)v2::smem_bytes(32), o32h));
+  PCAB_CUDA(pcab_set_max_smem(v2::k_conv3x3_tc2<64, true>, (int)v2::smem_bytes(64), o64h));
+  const int nsm = pcab_sm_count();
+  const int grid = cfg.total < nsm ? cfg.total : nsm;
   if (cfg.c == 64 && f16)
     v2::k_conv3x3_tc2<64, true><<<grid, v2::kThreads2, v2::smem_bytes(64), stream>>>(maps[0], maps[1], maps[2], maps[3], a);
   else if (cfg.c == 64)
@@ -979,66 +675,6 @@ extern "C" int pcab_conv3x3_tc(const float* src0, int c0, const float* src1, int
     pcab_set_error("pcab_conv3x3_tc: cuTensorMapEncodeTiled unavailable");
     return PCAB_ERR_CUDA;
   }
-  if (g_impl == 2)
-    return conv3x3_tc_v2(enc, src0, c0, src1, c1, src2, c2, temporal_T, weight_tc_packed, bias, bn_scale, bn_shift, relu, out,
-                         n_images, H, W, Cout, out_cstride, out_coff, stream);
-  TileCfg cfg;
-  PCAB_REQUIRE(choose_cfg(H, W, Cout, &cfg), "unsupported shape");
-  PCAB_REQUIRE(out_cstride % 4 == 0 && out_coff % 4 == 0, "output channel layout must be 16B aligned");
-  const float* srcs[3] = {src0, src1, src2};
-  int cs[3] = {c0, c1, c2};
-  int nsrc = src2 ? 3 : (src1 ? 2 : 1);
-  int T = temporal_T > 1 ? temporal_T : 1;
-  if (T > 1) PCAB_REQUIRE(nsrc == 3 && src0 == src1 && src1 == src2, "temporal mode takes the same tensor three times");
-  int cin_total = 0;
-  for (int s = 0; s < nsrc; ++s) cin_total += cs[s];
-
-  CUtensorMap maps[4];
-  for (int s = 0; s < 3; ++s) {
-    int ss = s < nsrc ? s : 0;
-    cuuint64_t dims[4] = {(cuuint64_t)cs[ss], (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_images};
-    cuuint64_t strides[3] = {(cuuint64_t)cs[ss] * 4, (cuuint64_t)W * cs[ss] * 4, (cuuint64_t)H * W * cs[ss] * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)cfg.Wp, (cuuint32_t)(cfg.R + 2), 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&maps[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)srcs[ss], dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      pcab_set_error("pcab_conv3x3_tc: cuTensorMapEncodeTiled(A%d) failed: %d", s, (int)r);
-      return PCAB_ERR_CUDA;
-    }
-  }
-  {
-    cuuint64_t K = (cuuint64_t)9 * cin_total;
-    cuuint64_t dims[2] = {K, (cuuint64_t)2 * Cout};
-    cuuint64_t strides[1] = {K * 4};
-    cuuint32_t box[2] = {32, (cuuint32_t)cfg.cout_t};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&maps[3], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)weight_tc_packed, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      pcab_set_error("pcab_conv3x3_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r);
-      return PCAB_ERR_CUDA;
-    }
-  }
-  TcArgs a;
-  a.nsrc = nsrc;
-  for (int s = 0; s < 3; ++s) a.src_c[s] = cs[s];
-  a.T = T;
-  a.N = n_images, a.H = H, a.W = W, a.Cout = Cout;
-  a.cout_t = cfg.cout_t, a.mt = cfg.mt, a.R = cfg.R, a.Wt = cfg.Wt, a.Wp = cfg.Wp, a.plane_rows = cfg.plane_rows;
-  a.tiles_x = cdiv(W, cfg.Wt), a.tiles_y = cdiv(H, cfg.R);
-  a.relu = relu, a.out_cstride = out_cstride, a.out_coff = out_coff, a.base_offset_mode = g_base_offset_mode;
-  a.nst = cfg.nst;
-  a.bias = bias, a.bn_scale = bn_scale, a.bn_shift = bn_shift, a.out = out;
-  static bool configured = false;
-  if (!configured) {
-    PCAB_CUDA(cudaFuncSetAttribute(k_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    configured = true;
-  }
-  dim3 grid(a.tiles_x * a.tiles_y * n_images, Cout / cfg.cout_t);
-  k_conv3x3_tc<<<grid, kThreads, cfg.smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
-  PCAB_CHECK_LAUNCH("pcab_conv3x3_tc");
-  return PCAB_OK;
+  return conv3x3_tc_v2(enc, src0, c0, src1, c1, src2, c2, temporal_T, weight_tc_packed, bias, bn_scale, bn_shift, relu, out,
+                       n_images, H, W, Cout, out_cstride, out_coff, stream);
 }

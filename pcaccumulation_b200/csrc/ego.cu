@@ -13,6 +13,7 @@
 // one iteration is  r_i = logsumexp_j(A_pad[i][j] - c_j)  followed by  c_j = logsumexp_i(A_pad[i][j] - r_i).
 #include <cub/cub.cuh>
 #include "common.cuh"
+#include "pair16.cuh"
 #include "pcab200.h"
 
 namespace {
@@ -38,6 +39,7 @@ __global__ void k_bg_compact(const int* __restrict__ flag, const int* __restrict
 }
 
 // gather 1024 keypoints per (pair, side): coordinates = pillar mean, features = L2-normalised head output
+template <bool P16>
 __global__ void k_ego_gather(const float* __restrict__ geo, const int* __restrict__ cell2pillar,
                              const float* __restrict__ pillar_mean, const int* __restrict__ bg_cells,
                              const int* __restrict__ frame_off, const int* __restrict__ pair_frames,  // [P][2] src,tgt
@@ -49,8 +51,13 @@ __global__ void k_ego_gather(const float* __restrict__ geo, const int* __restric
     int ps = r / KP;
     int frame = pair_frames[ps];
     int cell = bg_cells[frame_off[frame] + choice[r]];
-    const float* g = geo + (size_t)cell * FD;
-    float a = g[lane], b = g[lane + 32];
+    float a, b;
+    if (P16) {
+      a = p16::load1(geo, (size_t)cell, FD, lane), b = p16::load1(geo, (size_t)cell, FD, lane + 32);
+    } else {
+      const float* g = geo + (size_t)cell * FD;
+      a = g[lane], b = g[lane + 32];
+    }
     float ss = warp_sum(a * a + b * b);
     float nrm = sqrtf(ss);
     feats[(size_t)r * FD + lane] = a / nrm;
@@ -459,7 +466,7 @@ extern "C" size_t pcab_ego_pairs_workspace(int npairs) {
   return al256(f * 4) + al256((size_t)npairs * 3 * 8) + 256;
 }
 
-extern "C" int pcab_ego_pairs(const float* geo_nhwc, const int* cell_to_pillar, const float* pillar_mean,
+extern "C" int pcab_ego_pairs(const float* geo_nhwc, int geo_fmt, const int* cell_to_pillar, const float* pillar_mean,
                               const int* pillar_frame, int n_pillars, const int* bg_cells, const int* frame_off,
                               const int* pair_frames, const int* choice, const float* thr2, int npairs,
                               const float* alpha, const float* beta, int sinkhorn_iters, const float* ego_gt,
@@ -489,8 +496,12 @@ extern "C" int pcab_ego_pairs(const float* geo_nhwc, const int* cell_to_pillar, 
   double* acc = (double*)((char*)workspace + fbytes);
 
   int rows = npairs * 2 * KP;
-  k_ego_gather<<<cdiv((long long)rows * 32, 256), 256, 0, stream>>>(geo_nhwc, cell_to_pillar, pillar_mean, bg_cells,
-                                                                   frame_off, pair_frames, choice, npairs, feats, xyz);
+  if (geo_fmt)
+    k_ego_gather<true><<<cdiv((long long)rows * 32, 256), 256, 0, stream>>>(geo_nhwc, cell_to_pillar, pillar_mean, bg_cells, frame_off,
+                                                                           pair_frames, choice, npairs, feats, xyz);
+  else
+    k_ego_gather<false><<<cdiv((long long)rows * 32, 256), 256, 0, stream>>>(geo_nhwc, cell_to_pillar, pillar_mean, bg_cells, frame_off,
+                                                                            pair_frames, choice, npairs, feats, xyz);
   k_ego_affinity<<<dim3(KP / 64, KP / 64, npairs), 256, 0, stream>>>(feats, alpha, beta, A);
   PCAB_CUDA(cudaMemsetAsync(c, 0, (size_t)npairs * KP * 4, stream));
   for (int it = 0; it < sinkhorn_iters; ++it) {
@@ -502,7 +513,7 @@ extern "C" int pcab_ego_pairs(const float* geo_nhwc, const int* cell_to_pillar, 
   k_ego_kabsch<<<npairs, 1024, 0, stream>>>(xyz, xhat, w, pose_pairs);
   k_ego_pose_gt<<<cdiv(npairs, 32), 32, 0, stream>>>(ego_gt, pair_frames, npairs, pose_gt);
   PCAB_CUDA(cudaMemsetAsync(acc, 0, (size_t)npairs * 3 * 8, stream));
-  k_ego_losses<<<dim3(148, npairs), 256, 0, stream>>>(pillar_mean, pillar_frame, n_pillars, pair_frames, npairs,
+  k_ego_losses<<<dim3(pcab_sm_count(), npairs), 256, 0, stream>>>(pillar_mean, pillar_frame, n_pillars, pair_frames, npairs,
                                                       pose_pairs, pose_gt, acc);
   k_ego_finalize<<<1, 32, 0, stream>>>(pose_pairs, ego_gt, chain_pair, B, T, chain_mode, acc, npairs, ego_est,
                                        ego_gt_out, scalars);

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <type_traits>
 #include "common.cuh"
+#include "pair16.cuh"
 #include "mlp.cuh"
 #include "pcab200.h"
 #include "tc_common.cuh"
@@ -38,10 +39,10 @@ constexpr int kStages = 3;
 constexpr int kChunksPerTile = 13;        // pe2: 1, final_proj / mos0 / off0: 4 each
 constexpr size_t kSmemBytes = 1024 + 2 * (size_t)kPlane + kStages * (size_t)kWStage + 128 + 3 * 128 * 4;
 
-long long* g_head_stats = nullptr;  // debug counters of the kernels in this file (pcab_stpn_head_tc_set_stats)
 
 struct HeadArgs {
   const float* mos_feats;
+  int fmt;  // activation format of mos_feats: 0 = float32 NHWC, 1 = P16 (pair16.cuh)
   int H, W;
   const float* tp;
   const int* pbatch;
@@ -211,9 +212,15 @@ k_stpn_head_tc(const __grid_constant__ CUtensorMap map_w1, const __grid_constant
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qy) : "r"(s_py + 4u * p));
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qb) : "r"(s_pb + 4u * p));
         const mlp::Bilinear bl = mlp::bilinear_border(qx, qy, a.x_abs, a.y_abs, a.H, a.W);
-        const float4* b4 = reinterpret_cast<const float4*>(a.mos_feats + (size_t)qb * a.H * a.W * 64) + q;
-        const float4 t00 = b4[(size_t)bl.o00 * 16], t01 = b4[(size_t)bl.o01 * 16], t10 = b4[(size_t)bl.o10 * 16],
-                     t11 = b4[(size_t)bl.o11 * 16];
+        float4 t00, t01, t10, t11;
+        if (a.fmt) {
+          const size_t fb = (size_t)qb * a.H * a.W;
+          t00 = p16::load4(a.mos_feats, fb + bl.o00, 64, 4 * q), t01 = p16::load4(a.mos_feats, fb + bl.o01, 64, 4 * q);
+          t10 = p16::load4(a.mos_feats, fb + bl.o10, 64, 4 * q), t11 = p16::load4(a.mos_feats, fb + bl.o11, 64, 4 * q);
+        } else {
+          const float4* b4 = reinterpret_cast<const float4*>(a.mos_feats + (size_t)qb * a.H * a.W * 64) + q;
+          t00 = b4[(size_t)bl.o00 * 16], t01 = b4[(size_t)bl.o01 * 16], t10 = b4[(size_t)bl.o10 * 16], t11 = b4[(size_t)bl.o11 * 16];
+        }
         g[it].x = fmaf(t11.x, bl.w11, fmaf(t10.x, bl.w10, fmaf(t01.x, bl.w01, t00.x * bl.w00)));
         g[it].y = fmaf(t11.y, bl.w11, fmaf(t10.y, bl.w10, fmaf(t01.y, bl.w01, t00.y * bl.w00)));
         g[it].z = fmaf(t11.z, bl.w11, fmaf(t10.z, bl.w10, fmaf(t01.z, bl.w01, t00.z * bl.w00)));
@@ -706,13 +713,6 @@ int encode_weights(EncodeTiledFn enc, CUtensorMap* map, const float* w, int rows
 
 }  // namespace
 
-// debug: device buffer of 148*2*8 int64 phase-cycle counters filled by k_stpn_head_tc (null = off).  Per CTA and head half:
-// gather+pe0, wait pe2, pe2 epilogue, wait final_proj, its epilogue, wait head MMA, head epilogue, wait for the last MMA.
-extern "C" int pcab_stpn_head_tc_set_stats(long long* device_counters) {
-  g_head_stats = device_counters;
-  return 0;
-}
-
 // floats in the tensor-core weight packs of the STPN head: pe2 [hi 64 rows; lo 64 rows][32] and
 // [final_proj, mos0, off0] x [hi 128 rows; lo 128 rows][128]   (rows = output channels, K-major)
 extern "C" size_t pcab_stpn_head_tc_pack_floats(int which) { return which == 0 ? (size_t)128 * 32 : (size_t)3 * 256 * 128; }
@@ -720,7 +720,7 @@ extern "C" size_t pcab_stpn_head_tc_pack_floats(int which) { return which == 0 ?
 // Same contract as pcab_stpn_head (points.cu), except that the FP32 pack of that entry point is passed as a HOST pointer
 // (biases, BN, pe0 and the two 128 -> 2 projections are copied from it into the kernel's parameter block); `w1_tc` / `w_tc`
 // are the pre-split K-major device matrices described above.
-extern "C" int pcab_stpn_head_tc(const float* mos_feats_nhwc, int H, int W, const float* transformed_points,
+extern "C" int pcab_stpn_head_tc(const float* mos_feats_nhwc, int feats_fmt, int H, int W, const float* transformed_points,
                                  const int* point_batch, const int* fg_idx, int n_fg, const float* weight_pack_host,
                                  const float* w1_tc, const float* w_tc, float x_abs, float y_abs, float* mos_out,
                                  float* offset_out, cudaStream_t stream) {
@@ -739,15 +739,12 @@ extern "C" int pcab_stpn_head_tc(const float* mos_feats_nhwc, int H, int W, cons
   rc = encode_weights(enc, &m2, w_tc, 3 * 256, 128, 256);
   if (rc != PCAB_OK) return rc;
   HeadArgs a;
-  a.mos_feats = mos_feats_nhwc, a.H = H, a.W = W, a.tp = transformed_points, a.pbatch = point_batch, a.fg_idx = fg_idx;
+  a.mos_feats = mos_feats_nhwc, a.fmt = feats_fmt, a.H = H, a.W = W, a.tp = transformed_points, a.pbatch = point_batch, a.fg_idx = fg_idx;
   a.n_fg = n_fg, a.x_abs = x_abs, a.y_abs = y_abs, a.mos_out = mos_out, a.off_out = offset_out;
   a.n_tiles = cdiv(n_fg, 128);
-  a.stats = g_head_stats;
-  static bool configured = false;
-  if (!configured) {
-    PCAB_CUDA(cudaFuncSetAttribute(k_stpn_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    configured = true;
-  }
+  a.stats = nullptr;  // per-phase cycle counters (debug builds pass a device buffer here)
+  static PcabSmemOnce once;
+  PCAB_CUDA(pcab_set_max_smem(k_stpn_head_tc, (int)kSmemBytes, once));
   HeadConsts k;
   const float* pk = weight_pack_host;
   memcpy(k.pe0w, pk + S_PE0W, sizeof(k.pe0w)), memcpy(k.pe0b, pk + S_PE0B, sizeof(k.pe0b));
@@ -758,7 +755,7 @@ extern "C" int pcab_stpn_head_tc(const float* mos_feats_nhwc, int H, int W, cons
     memcpy(k.ht[i], pk + ht[i], sizeof(k.ht[i])), memcpy(k.h3w[i], pk + h3w[i], sizeof(k.h3w[i]));
     memcpy(k.h3b[i], pk + h3b[i], sizeof(k.h3b[i]));
   }
-  const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
+  const int grid = a.n_tiles < pcab_sm_count() ? a.n_tiles : pcab_sm_count();
   k_stpn_head_tc<<<grid, kNT, kSmemBytes, stream>>>(m1, m2, a, k);
   PCAB_CHECK_LAUNCH("pcab_stpn_head_tc");
   return PCAB_OK;
@@ -788,15 +785,12 @@ int launch_embed(EncodeTiledFn enc, const float* feat, const int* src_idx, const
   if (N2) memcpy(k.b[2], b2, 128 * sizeof(float));
   EmbedArgs a;
   a.feat = feat, a.src_idx = src_idx, a.seg = seg, a.n = n, a.out = out, a.n_tiles = cdiv(n, 128);
-  a.stats = g_head_stats;
-  static bool configured = false;
-  if (!configured) {
-    PCAB_CUDA(cudaFuncSetAttribute(k_embed_tc<K0, N1, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    configured = true;
-  }
+  a.stats = nullptr;  // per-phase cycle counters (debug builds pass a device buffer here)
+  static PcabSmemOnce once;
+  PCAB_CUDA(pcab_set_max_smem(k_embed_tc<K0, N1, N2>, (int)kSmemBytes, once));
   const long long total = (long long)n_seg * 128;
   k_fill_f<<<grid_for(total, 256), 256, 0, stream>>>(out, total, -INFINITY);
-  const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
+  const int grid = a.n_tiles < pcab_sm_count() ? a.n_tiles : pcab_sm_count();
   k_embed_tc<K0, N1, N2><<<grid, kNT, kSmemBytes, stream>>>(m0, m1, m2, a, k);
   k_neg_inf_to_zero<<<grid_for(total, 256), 256, 0, stream>>>(out, total);
   return PCAB_OK;

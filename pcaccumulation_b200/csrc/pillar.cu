@@ -10,6 +10,7 @@
 //   fc_pos W[9][64] b[64] | for blk in 0..2: fc_0 W[64][32] b[32], fc_1 W[32][32] b[32], shortcut W[64][32] |
 //   fc_c W[32][32] b[32]
 #include "common.cuh"
+#include "pair16.cuh"
 #include "pcab200.h"
 
 namespace {
@@ -234,8 +235,9 @@ __global__ void k_fill_neg_inf(float4* __restrict__ a, long long n4) {
 }
 
 // pillar features -> canvas cells (models/pillar_encoder.py:158-172); a pillar without points keeps 0 like torch_scatter
+template <bool P16>
 __global__ void k_canvas_scatter(float4* __restrict__ feats, const int* __restrict__ cell_of_pillar, int m,
-                                 float4* __restrict__ canvas) {
+                                 float* __restrict__ canvas) {
   long long total = (long long)m * 8, stride = (long long)gridDim.x * blockDim.x;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
     const int p = (int)(e >> 3), q = (int)(e & 7);
@@ -244,7 +246,7 @@ __global__ void k_canvas_scatter(float4* __restrict__ feats, const int* __restri
       v = make_float4(0.f, 0.f, 0.f, 0.f);
       feats[e] = v;
     }
-    canvas[(size_t)cell_of_pillar[p] * 8 + q] = v;
+    p16::st4<P16>(canvas, (size_t)cell_of_pillar[p], 32, 4 * q, v);
   }
 }
 
@@ -284,7 +286,8 @@ extern "C" int pcab_pillar_encode(const float* xyz, const int* point_time, const
                                   const int* pstart, const int* coords_zyxt, const int* pillar_cell,
                                   const float* pillar_mean, const float* weight_pack, int n_points, int n_pillars,
                                   const float* range6, const float* voxel_size3, int n_sweeps, float* pillar_feats,
-                                  float* canvas_nhwc, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                                  float* canvas_nhwc, int canvas_fmt, void* workspace, size_t workspace_bytes,
+                                  cudaStream_t stream) {
   PCAB_REQUIRE(workspace_bytes >= pcab_pillar_encode_workspace(n_points, n_pillars), "workspace too small");
   float* net_a = (float*)workspace;
   float* net_b = net_a + (size_t)n_points * 32;
@@ -298,15 +301,12 @@ extern "C" int pcab_pillar_encode(const float* xyz, const int* point_time, const
   g.n_frames = (float)n_sweeps;
   (void)pstart;  // the segment boundaries are recovered from the sorted pillar ids inside the tiles
   const size_t smem = (size_t)(64 * LD + 32 * LD + kBlkSize + 1056) * sizeof(float);
-  static bool cfg = false;
-  if (!cfg) {
-    cudaFuncSetAttribute(k_pfn_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_pfn_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_pfn_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cfg = true;
-  }
+  static PcabSmemOnce once0, once1, once2;
+  PCAB_CUDA(pcab_set_max_smem(k_pfn_tile<0>, (int)smem, once0));
+  PCAB_CUDA(pcab_set_max_smem(k_pfn_tile<1>, (int)smem, once1));
+  PCAB_CUDA(pcab_set_max_smem(k_pfn_tile<2>, (int)smem, once2));
   const int ntiles = (n_points + PT - 1) / PT;
-  const int gp = ntiles < 2 * 148 ? ntiles : 2 * 148;  // persistent: two CTAs (16 warps) per SM
+  const int gp = ntiles < 2 * pcab_sm_count() ? ntiles : 2 * pcab_sm_count();  // persistent: two CTAs (16 warps) per SM
   const long long pool4 = (long long)n_pillars * 8;
   const int gf = grid_for(pool4, 256, 8);
   // pooled vectors ping-pong between `pillar_feats` and the scratch array (each is re-filled with -inf before reuse)
@@ -319,7 +319,10 @@ extern "C" int pcab_pillar_encode(const float* xyz, const int* point_time, const
   k_fill_neg_inf<<<gf, 256, 0, stream>>>((float4*)pillar_feats, pool4);
   k_pfn_tile<2><<<gp, NTP, smem, stream>>>(xyz, point_time, order, p2v, coords_zyxt, pillar_mean, net_b, pooled,
                                            weight_pack, n_points, g, nullptr, pillar_feats);
-  k_canvas_scatter<<<gf, 256, 0, stream>>>((float4*)pillar_feats, pillar_cell, n_pillars, (float4*)canvas_nhwc);
+  if (canvas_fmt)
+    k_canvas_scatter<true><<<gf, 256, 0, stream>>>((float4*)pillar_feats, pillar_cell, n_pillars, canvas_nhwc);
+  else
+    k_canvas_scatter<false><<<gf, 256, 0, stream>>>((float4*)pillar_feats, pillar_cell, n_pillars, canvas_nhwc);
   PCAB_CHECK_LAUNCH("pcab_pillar_encode");
   return PCAB_OK;
 }

@@ -7,6 +7,7 @@
 // torch_scatter segment max / mean calls inside them.
 #include <cub/cub.cuh>
 #include "mlp.cuh"
+#include "pair16.cuh"
 #include "pcab200.h"
 
 namespace {
@@ -29,6 +30,7 @@ __global__ void k_flag_eq(const long long* __restrict__ v, int n, long long valu
 }
 
 // out[j][0..C) = bilinear(feats[frame_of(point)], xy(point)), border padding.  One warp per point.
+template <bool P16>
 __global__ void k_ungrid(const float* __restrict__ feats, int C, int H, int W, const float* __restrict__ xyz,
                          const int* __restrict__ frame_of_point, const int* __restrict__ idx, int k, float x_abs,
                          float y_abs, float* __restrict__ out) {
@@ -37,12 +39,21 @@ __global__ void k_ungrid(const float* __restrict__ feats, int C, int H, int W, c
   for (int j = warp; j < k; j += nwarp) {
     int i = idx ? idx[j] : j;
     mlp::Bilinear bl = mlp::bilinear_border(xyz[3 * i], xyz[3 * i + 1], x_abs, y_abs, H, W);
-    const float* base = feats + (size_t)frame_of_point[i] * H * W * C;
+    const size_t fb = (size_t)frame_of_point[i] * H * W;
+    const float* base = feats + fb * C;
     for (int c = lane; c < C; c += 32) {
-      float v = base[(size_t)bl.o00 * C + c] * bl.w00;
-      v = fmaf(base[(size_t)bl.o01 * C + c], bl.w01, v);
-      v = fmaf(base[(size_t)bl.o10 * C + c], bl.w10, v);
-      v = fmaf(base[(size_t)bl.o11 * C + c], bl.w11, v);
+      float t00, t01, t10, t11;
+      if (P16) {
+        t00 = p16::load1(feats, fb + bl.o00, C, c), t01 = p16::load1(feats, fb + bl.o01, C, c);
+        t10 = p16::load1(feats, fb + bl.o10, C, c), t11 = p16::load1(feats, fb + bl.o11, C, c);
+      } else {
+        t00 = base[(size_t)bl.o00 * C + c], t01 = base[(size_t)bl.o01 * C + c];
+        t10 = base[(size_t)bl.o10 * C + c], t11 = base[(size_t)bl.o11 * C + c];
+      }
+      float v = t00 * bl.w00;
+      v = fmaf(t01, bl.w01, v);
+      v = fmaf(t10, bl.w10, v);
+      v = fmaf(t11, bl.w11, v);
       out[(size_t)j * C + c] = v;
     }
   }
@@ -491,11 +502,16 @@ extern "C" int pcab_select_indices(const int* flags, const long long* values, lo
   return PCAB_OK;
 }
 
-extern "C" int pcab_ungrid(const float* feats_nhwc, int C, int H, int W, const float* xyz, const int* frame_of_point,
+extern "C" int pcab_ungrid(const float* feats_nhwc, int C, int fmt, int H, int W, const float* xyz, const int* frame_of_point,
                            const int* idx, int k, float x_abs, float y_abs, float* out, cudaStream_t stream) {
   if (k <= 0) return PCAB_OK;
-  k_ungrid<<<grid_for((long long)k * 32, 256, 8), 256, 0, stream>>>(feats_nhwc, C, H, W, xyz, frame_of_point, idx, k,
-                                                                   x_abs, y_abs, out);
+  PCAB_REQUIRE(!fmt || C % 32 == 0, "P16 tensors have C % 32 == 0");
+  if (fmt)
+    k_ungrid<true><<<grid_for((long long)k * 32, 256, 8), 256, 0, stream>>>(feats_nhwc, C, H, W, xyz, frame_of_point, idx, k, x_abs,
+                                                                           y_abs, out);
+  else
+    k_ungrid<false><<<grid_for((long long)k * 32, 256, 8), 256, 0, stream>>>(feats_nhwc, C, H, W, xyz, frame_of_point, idx, k, x_abs,
+                                                                            y_abs, out);
   PCAB_CHECK_LAUNCH("pcab_ungrid");
   return PCAB_OK;
 }
@@ -513,11 +529,8 @@ extern "C" int pcab_stpn_head(const float* mos_feats_nhwc, int H, int W, const f
                               float x_abs, float y_abs, float* mos_out, float* offset_out, cudaStream_t stream) {
   if (n_fg <= 0) return PCAB_OK;
   size_t smem = (size_t)(2 * 128 * LDP + mlp::SW_FLOATS + 4 * LDP) * sizeof(float);
-  static bool cfg = false;
-  if (!cfg) {
-    cudaFuncSetAttribute(k_stpn_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cfg = true;
-  }
+  static PcabSmemOnce once;
+  PCAB_CUDA(pcab_set_max_smem(k_stpn_head, (int)smem, once));
   k_stpn_head<<<cdiv(n_fg, PTS), mlp::NT, smem, stream>>>(mos_feats_nhwc, H, W, transformed_points, point_batch, fg_idx,
                                                       n_fg, weight_pack, x_abs, y_abs, mos_out, offset_out);
   PCAB_CHECK_LAUNCH("pcab_stpn_head");
@@ -576,11 +589,8 @@ extern "C" int pcab_tpn_static_embed(const float* mos_feat, const float* geo_fea
                                      int n, int K, const float* pack_motion, const float* pack_geo, float* mos_emb,
                                      float* geo_emb, cudaStream_t stream) {
   size_t smem = (size_t)(2 * 128 * LDP + mlp::SW_FLOATS) * sizeof(float);
-  static bool cfg = false;
-  if (!cfg) {
-    cudaFuncSetAttribute(k_tpn_static_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cfg = true;
-  }
+  static PcabSmemOnce once;
+  PCAB_CUDA(pcab_set_max_smem(k_tpn_static_embed, (int)smem, once));
   k_fill<<<grid_for((long long)K * 128, 256), 256, 0, stream>>>(mos_emb, (long long)K * 128, -INFINITY);
   k_fill<<<grid_for((long long)K * 128, 256), 256, 0, stream>>>(geo_emb, (long long)K * 128, -INFINITY);
   k_tpn_static_embed<<<cdiv(n, PTS), mlp::NT, smem, stream>>>(mos_feat, geo_feat, src_idx, inst, n, pack_motion, pack_geo,
@@ -621,11 +631,8 @@ extern "C" int pcab_tpn_iteration(const float* points, const int* inst, const in
   double* sums = (double*)((char*)workspace + al256p(kt * (128 + 512 + 256 + 128 + 8) * 4));
   PCAB_CUDA(cudaMemsetAsync(sums, 0, kt * 4 * 8, stream));
   size_t smem = (size_t)(2 * 128 * LDP + mlp::SW_FLOATS) * sizeof(float);
-  static bool cfg = false;
-  if (!cfg) {
-    cudaFuncSetAttribute(k_tpn_pos_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cfg = true;
-  }
+  static PcabSmemOnce once;
+  PCAB_CUDA(pcab_set_max_smem(k_tpn_pos_embed, (int)smem, once));
   k_tpn_frame_sums<<<grid_for(n, 256), 256, 0, stream>>>(points, inst, tidx, T, n, sums);
   if (pos_w0_tc) {
     // tensor-core path (csrc/mlp_tc.cu): layer 0 on the CUDA cores, layers 1-2 + the (instance, frame) max on tcgen05

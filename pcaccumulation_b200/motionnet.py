@@ -10,6 +10,7 @@ shared library or a CUDA device ``forward`` raises.
 Internal layout: all BEV tensors are NHWC float32 ``[B*T, Ny, Nx, C]``; points are additionally indexed
 in pillar-sorted order so per-pillar reductions are contiguous ranges.
 """
+import ctypes
 import math
 
 import torch
@@ -198,7 +199,21 @@ class _ConvLayer:
         self.weight = w  # for the tensor-core pack (built lazily)
         self.tc_pack = None
         self.tc_pack16 = None
-        self.tc_ok = {}  # (H, W) -> does the tensor-core kernel take this layer at that map size
+        self.tc_scale16 = None  # power-of-two scale of the fp16-pair weight pack (tc_pack.f16_weight_scale)
+        self.tc_ok = {}  # (H, W, fmt) -> does the tensor-core kernel take this layer at that map size
+
+
+class _MergedConv:
+    """Two 3x3 convolutions over the SAME input run as one layer (output channels concatenated): the first convolutions of
+    the two SegHead2D heads both read ``bev_feats``; merged, the input plane is staged once and the MMA N is 192 + 96."""
+
+    def __init__(self, a, b):
+        import types
+
+        conv = types.SimpleNamespace(weight=torch.cat((a.weight.detach(), b.weight.detach()), 0), bias=torch.cat((a.bias, b.bias)))
+        self.layer = _ConvLayer(conv)
+        self.layer.bn = (torch.cat((a.bn[0], b.bn[0])).contiguous(), torch.cat((a.bn[1], b.bn[1])).contiguous())
+        self.c_first = a.cout
 
 
 class MotionNet(nn.Module):
@@ -229,6 +244,13 @@ class MotionNet(nn.Module):
         # operand format of the tensor-core convolutions: "f16" = fp16 pairs (kind::f16, activations saturate at +-65504),
         # "tf32" = 3xTF32 (kind::tf32, full FP32 range, ~1.3x slower); both keep ~22 significant bits per operand
         self.conv_operands = "f16"
+        # With fp16-pair operands the BEV activations themselves live in the pair-packed P16 format (csrc/pair16.cuh): every
+        # producer writes (h, l) pairs, the convolutions read them straight into the MMA operand.  Values beyond +-65504 would
+        # saturate: the producers count such events and forward() then repeats the scene with conv_operands = "tf32".
+        self.packed_activations = True
+        self.merge_heads = True  # first convolutions of semseg_head / ego_feats_head as one 96-channel layer (P16 path)
+        self._sat = None  # device counter of saturated P16 outputs
+        self._p16_ok = {}
         self.stages = {}  # stage-boundary tensors of the last forward (for stage-wise parity tests)
         self.keep_stages = False
         # stage-wise parity protocol: tensors placed here replace the computed value for the stages
@@ -275,7 +297,8 @@ class MotionNet(nn.Module):
                 W[f"{prefix}d{i}c2"] = _ConvLayer(d.conv2)
             for i, u in enumerate(net.up_convs):
                 co = u.upconv.weight.shape[1]
-                W[f"{prefix}u{i}up"] = (_pack_convT(u.upconv.weight), _v(u.upconv.bias), u.upconv.weight.shape[0], co)
+                W[f"{prefix}u{i}up"] = (_pack_convT(u.upconv.weight), _v(u.upconv.bias), u.upconv.weight.shape[0], co,
+                                        {"weight": u.upconv.weight})
                 W[f"{prefix}u{i}c1"] = _ConvLayer(u.conv1, splits=[co, u.conv1.weight.shape[1] - co])
                 W[f"{prefix}u{i}c2"] = _ConvLayer(u.conv2)
             if final:
@@ -289,6 +312,7 @@ class MotionNet(nn.Module):
         eh = self.ego_feats_head.seg_head
         W["ego0"] = _ConvLayer(eh[0], bn=eh[1])
         W["ego3"] = _ConvLayer(eh[3])
+        W["semego0"] = _MergedConv(W["sem0"], W["ego0"])
         for j, i in enumerate((0, 2, 4, 6)):
             W[f"stpn.c3d{j}"] = _ConvLayer(self.motionhead.init_conv[i], temporal=True)
         mh = self.motionhead
@@ -327,6 +351,31 @@ class MotionNet(nn.Module):
         return W
 
     # ------------------------------------------------------------------------------------------
+    # activation format of the BEV tensors
+    # ------------------------------------------------------------------------------------------
+    def _fmt(self, B, T, Ny, Nx):
+        """1 = P16 (pair-packed fp16, csrc/pair16.cuh) when the tensor-core path with fp16-pair operands is selected and every
+        convolution of both stacks has a tile plan at this grid size; 0 = float32."""
+        if not (self.use_tensor_cores and self.conv_operands == "f16" and self.packed_activations):
+            return 0
+        key = (Ny, Nx)
+        ok = self._p16_ok.get(key)
+        if ok is None:
+            lib = L.lib()
+            ok = Ny % 16 == 0 and Nx % 16 == 0
+            h, w = Ny, Nx
+            for _ in range(5):  # the five resolutions of both UNets; channel counts never matter for the plan's existence
+                ok = ok and bool(lib.pcab_conv3x3_p16_supported(I(1), I(32), I(0), I(0), I(32), I(h), I(w)))
+                h, w = h // 2, w // 2
+            self._p16_ok[key] = ok
+        return 1 if ok else 0
+
+    def _sat_counter(self, dev):
+        if self._sat is None or self._sat.device != dev:
+            self._sat = torch.zeros(1, dtype=torch.int32, device=dev)
+        return self._sat
+
+    # ------------------------------------------------------------------------------------------
     # CUDA-graph replay of fixed launch sequences
     # ------------------------------------------------------------------------------------------
     def _graph_input(self, key, shape, dev):
@@ -358,20 +407,22 @@ class MotionNet(nn.Module):
         slot["graph"], slot["out"] = g, out
         return out
 
-    def _backbone_stack(self, W, B, T, Ny, Nx):
+    def _backbone_stack(self, W, B, T, Ny, Nx, fmt):
         def backbone(x):
-            feats = self._unet(W, "unet.", x, B * T, Ny, Nx, self.cfg["unet"]["depth"], True)
-            return feats, self._conv(W["sem0"], [feats], B * T, Ny, Nx, True)
+            feats = self._unet(W, "unet.", x, B * T, Ny, Nx, self.cfg["unet"]["depth"], True, fmt)
+            if fmt and self.merge_heads:  # [sem0 (32) | ego0 (64)] channels in one tensor
+                return feats, self._conv(W["semego0"].layer, [feats], B * T, Ny, Nx, True, fmt=fmt)
+            return feats, self._conv(W["sem0"], [feats], B * T, Ny, Nx, True, fmt=fmt)
         return backbone
 
-    def _stpn_stack(self, W, B, T, Ny, Nx, dev):
+    def _stpn_stack(self, W, B, T, Ny, Nx, dev, fmt):
         def stpn_stack(x):
             for j in range(4):
-                x = self._conv(W[f"stpn.c3d{j}"], [x], B * T, Ny, Nx, True, T=T)
+                x = self._conv(W[f"stpn.c3d{j}"], [x], B * T, Ny, Nx, True, T=T, fmt=fmt)
             xm = torch.empty(B, Ny, Nx, 32, device=dev)
-            call("pcab_temporal_max", P(x), P(xm), I(B), I(T), I(Ny), I(Nx), I(32), stream())
+            call("pcab_temporal_max", P(x), P(xm), I(B), I(T), I(Ny), I(Nx), I(32), I(fmt), stream())
             del x
-            return self._unet(W, "stpn.", xm, B, Ny, Nx, 5, False)
+            return self._unet(W, "stpn.", xm, B, Ny, Nx, 5, False, fmt)
         return stpn_stack
 
     @torch.no_grad()
@@ -387,10 +438,13 @@ class MotionNet(nn.Module):
         vg = self.cfg["voxel_generator"]
         Nx = int(round((vg["range"][3] - vg["range"][0]) / vg["voxel_size"][0]))
         Ny = int(round((vg["range"][4] - vg["range"][1]) / vg["voxel_size"][1]))
-        B, T, tc = int(batch_size), self.n_sweeps, (self.use_tensor_cores, self.conv_operands)
+        B, T = int(batch_size), self.n_sweeps
+        fmt = self._fmt(B, T, Ny, Nx)
+        tc = (self.use_tensor_cores, self.conv_operands, fmt, self.merge_heads)
         with L.pinned_stream():
             W = self._weights()
-            for name, fn in (("backbone", self._backbone_stack(W, B, T, Ny, Nx)), ("stpn", self._stpn_stack(W, B, T, Ny, Nx, dev))):
+            self._sat_counter(dev)
+            for name, fn in (("backbone", self._backbone_stack(W, B, T, Ny, Nx, fmt)), ("stpn", self._stpn_stack(W, B, T, Ny, Nx, dev, fmt))):
                 key = (name, B, T, Ny, Nx, tc)
                 self._graph_input(key, (B * T, Ny, Nx, 32), dev).zero_()
                 self._run_stack(key, fn, capture=True)
@@ -399,7 +453,7 @@ class MotionNet(nn.Module):
     # ------------------------------------------------------------------------------------------
     # convolution dispatch
     # ------------------------------------------------------------------------------------------
-    def _conv(self, layer, srcs, n_img, H, W_, relu, out=None, T=1):
+    def _conv(self, layer, srcs, n_img, H, W_, relu, out=None, T=1, fmt=0, src0_cstride=0, src0_off=0):
         dev = srcs[0].device
         if out is None:
             out = torch.empty(n_img, H, W_, layer.cout, device=dev, dtype=torch.float32)
@@ -412,33 +466,37 @@ class MotionNet(nn.Module):
         if ev is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        path = "f32"
+        tail = (P(layer.bias), P(scale), P(shift), I(int(relu)), P(out), I(n_img), I(H), I(W_), I(layer.cout))
+        Tl = I(T if layer.temporal else 1)
         tc_ok = False
-        if self.use_tensor_cores:
+        if self.use_tensor_cores and not fmt:
             tc_ok = layer.tc_ok.get((H, W_))
             if tc_ok is None:
                 tc_ok = layer.tc_ok[(H, W_)] = bool(L.lib().pcab_conv3x3_tc_supported(
                     I(len(layer.splits)), I(c[0]), I(c[1]), I(c[2]), I(layer.cout), I(H), I(W_)))
-        if tc_ok and self.conv_operands == "f16":
-            if layer.tc_pack16 is None:
-                from .tc_pack import pack_conv_tc_f16
-                layer.tc_pack16 = pack_conv_tc_f16(layer)
-            from .tc_pack import F16_WEIGHT_SCALE
-            call("pcab_conv3x3_tc_f16", P(s[0]), I(c[0]), P(s[1]), I(c[1]), P(s[2]), I(c[2]), I(T if layer.temporal else 1),
-                 P(layer.tc_pack16), F(1.0 / F16_WEIGHT_SCALE), P(layer.bias), P(scale), P(shift), I(int(relu)), P(out), I(n_img),
-                 I(H), I(W_), I(layer.cout), I(layer.cout), I(0), stream())
+        if (fmt or (tc_ok and self.conv_operands == "f16")) and layer.tc_pack16 is None:
+            from .tc_pack import f16_weight_scale, pack_conv_tc_f16
+            layer.tc_scale16 = f16_weight_scale(layer.weight)
+            layer.tc_pack16 = pack_conv_tc_f16(layer, layer.tc_scale16)
+        if fmt:  # P16 activations in and out (csrc/conv_p16.cu)
+            p0 = ctypes.c_void_p(s[0].data_ptr() + src0_off)
+            call("pcab_conv3x3_p16", p0, I(c[0]), I(src0_cstride), P(s[1]), I(c[1]), P(s[2]), I(c[2]), Tl, P(layer.tc_pack16),
+                 F(1.0 / layer.tc_scale16), *tail, P(self._sat_counter(dev)), stream())
+            path = "tc-p16"
+        elif tc_ok and self.conv_operands == "f16":
+            call("pcab_conv3x3_tc_f16", P(s[0]), I(c[0]), P(s[1]), I(c[1]), P(s[2]), I(c[2]), Tl, P(layer.tc_pack16),
+                 F(1.0 / layer.tc_scale16), *tail, I(layer.cout), I(0), stream())
             path = "tc-f16pair"
         elif tc_ok:
             if layer.tc_pack is None:
                 layer.tc_pack = self._pack_tc(layer)
-            call("pcab_conv3x3_tc", P(s[0]), I(c[0]), P(s[1]), I(c[1]), P(s[2]), I(c[2]), I(T if layer.temporal else 1),
-                 P(layer.tc_pack), P(layer.bias), P(scale), P(shift), I(int(relu)), P(out), I(n_img), I(H), I(W_),
-                 I(layer.cout), I(layer.cout), I(0), stream())
+            call("pcab_conv3x3_tc", P(s[0]), I(c[0]), P(s[1]), I(c[1]), P(s[2]), I(c[2]), Tl, P(layer.tc_pack), *tail,
+                 I(layer.cout), I(0), stream())
             path = "tc"
         else:
-            call("pcab_conv3x3_f32", P(s[0]), I(c[0]), P(s[1]), I(c[1]), P(s[2]), I(c[2]), I(T if layer.temporal else 1),
-                 P(layer.pack), P(layer.bias), P(scale), P(shift), I(int(relu)), P(out), I(n_img), I(H), I(W_),
-                 I(layer.cout), I(layer.cout), I(0), stream())
+            call("pcab_conv3x3_f32", P(s[0]), I(c[0]), P(s[1]), I(c[1]), P(s[2]), I(c[2]), Tl, P(layer.pack), *tail,
+                 I(layer.cout), I(0), stream())
+            path = "f32"
         if ev is not None:
             e1.record()
             if layer.temporal:
@@ -454,29 +512,39 @@ class MotionNet(nn.Module):
         from .tc_pack import pack_conv_tc
         return pack_conv_tc(layer)
 
-    def _unet(self, W, prefix, x, n_img, H, W_, depth, final):
+    def _unet(self, W, prefix, x, n_img, H, W_, depth, final, fmt=0):
         enc = []
         h, w = H, W_
         dev = x.device
         for i in range(depth):
-            x = self._conv(W[f"{prefix}d{i}c1"], [x], n_img, h, w, True)
-            x = self._conv(W[f"{prefix}d{i}c2"], [x], n_img, h, w, True)
+            x = self._conv(W[f"{prefix}d{i}c1"], [x], n_img, h, w, True, fmt=fmt)
+            x = self._conv(W[f"{prefix}d{i}c2"], [x], n_img, h, w, True, fmt=fmt)
             enc.append((x, h, w))
             if i < depth - 1:
                 c = x.shape[-1]
                 pooled = torch.empty(n_img, h // 2, w // 2, c, device=dev, dtype=torch.float32)
-                call("pcab_maxpool2x2", P(x), P(pooled), I(n_img), I(h), I(w), I(c), stream())
+                call("pcab_maxpool2x2", P(x), P(pooled), I(n_img), I(h), I(w), I(c), I(fmt), stream())
                 x, h, w = pooled, h // 2, w // 2
         for i in range(depth - 1):
             skip, sh, sw = enc[-(i + 2)]
-            pack, bias, cin, cout = W[f"{prefix}u{i}up"]
+            up_l = W[f"{prefix}u{i}up"]
+            pack, bias, cin, cout = up_l[:4]
             up = torch.empty(n_img, sh, sw, cout, device=dev, dtype=torch.float32)
-            call("pcab_convT2x2_f32", P(x), P(pack), P(bias), P(up), I(n_img), I(h), I(w), I(cin), I(cout), I(cout), I(0), stream())
+            if fmt:  # ConvTranspose on the tensor cores (1-tap GEMM with 4 x Cout columns, scattered by the output maps)
+                if up_l[4].get("p16") is None:
+                    from .tc_pack import f16_weight_scale, pack_convT_p16
+                    sc = f16_weight_scale(up_l[4]["weight"])
+                    up_l[4]["p16"] = (pack_convT_p16(up_l[4]["weight"], sc), sc)
+                wp, sc = up_l[4]["p16"]
+                call("pcab_convT2x2_p16", P(x), I(cin), P(wp), F(1.0 / sc), P(bias), P(up), I(n_img), I(h), I(w), I(cout),
+                     P(self._sat_counter(dev)), stream())
+            else:
+                call("pcab_convT2x2_f32", P(x), P(pack), P(bias), P(up), I(n_img), I(h), I(w), I(cin), I(cout), I(cout), I(0), stream())
             h, w = sh, sw
-            x = self._conv(W[f"{prefix}u{i}c1"], [up, skip], n_img, h, w, True)
-            x = self._conv(W[f"{prefix}u{i}c2"], [x], n_img, h, w, True)
+            x = self._conv(W[f"{prefix}u{i}c1"], [up, skip], n_img, h, w, True, fmt=fmt)
+            x = self._conv(W[f"{prefix}u{i}c2"], [x], n_img, h, w, True, fmt=fmt)
         if final:
-            x = self._conv(W[f"{prefix}final"], [x], n_img, h, w, False)
+            x = self._conv(W[f"{prefix}final"], [x], n_img, h, w, False, fmt=fmt)
         return x
 
     # ------------------------------------------------------------------------------------------
@@ -566,26 +634,31 @@ class MotionNet(nn.Module):
 
         self._mark("index+stats")
         # 1. pillar encoder -> BEV canvas
-        tc = (self.use_tensor_cores, self.conv_operands)  # part of the graph key: a capture replays the kernels it recorded
+        fmt = self._fmt(B, T, Ny, Nx)  # activation format of the BEV tensors: 1 = P16 pairs, 0 = float32
+        merged = bool(fmt and self.merge_heads)
+        tc = (self.use_tensor_cores, self.conv_operands, fmt, self.merge_heads)  # part of the graph key: a capture replays the kernels it recorded
+        sat = self._sat_counter(dev)
+        if fmt:
+            sat.zero_()
         canvas = self._graph_input(("backbone", B, T, Ny, Nx, tc), (B * T, Ny, Nx, 32), dev)
         canvas.zero_()
         pillar_feats = torch.empty(M, 32, device=dev)
         ws = scratch(size("pcab_pillar_encode_workspace", I(N), I(M)), dev)
         call("pcab_pillar_encode", P(pts), P(ptime), P(order), P(p2v), P(pstart), P(coords_zyxt), P(pillar_cell),
-             P(pillar_mean), P(W["pfn"]), I(N), I(M), rng, vsz, I(self.n_sweeps), P(pillar_feats), P(canvas), P(ws),
+             P(pillar_mean), P(W["pfn"]), I(N), I(M), rng, vsz, I(self.n_sweeps), P(pillar_feats), P(canvas), I(fmt), P(ws),
              Z(ws.numel()), stream())
         del ws
 
         self._mark("pillar_encoder")
         # 2. UNet backbone
-        bev_feats, h = self._run_stack(("backbone", B, T, Ny, Nx, tc), self._backbone_stack(W, B, T, Ny, Nx))
+        bev_feats, h = self._run_stack(("backbone", B, T, Ny, Nx, tc), self._backbone_stack(W, B, T, Ny, Nx, fmt))
 
         self._mark("unet")
         # 3. FG/BG head
         fb_seg = torch.empty(B, T, 2, Ny, Nx, device=dev)
         fb_est = torch.empty(B * T * HW, dtype=torch.int32, device=dev)
-        call("pcab_head2_conv", P(h), I(32), P(W["sem3"][0]), P(W["sem3"][1]), I(B * T), I(Ny), I(Nx), P(fb_seg),
-             P(fb_est), stream())
+        call("pcab_head2_conv", P(h), I(32), I(h.shape[-1]), I(fmt), P(W["sem3"][0]), P(W["sem3"][1]), I(B * T), I(Ny), I(Nx),
+             P(fb_seg), P(fb_est), stream())
         if "fb_est_map" in self.inject:  # [B,T,1,Ny,Nx] or flat: the argmax map the ego head and the gathers consume
             fb_est = self.inject["fb_est_map"].to(dev).reshape(-1).to(torch.int32).contiguous()
         fb_pp = torch.empty(N, 1, dtype=torch.int64, device=dev)
@@ -597,12 +670,16 @@ class MotionNet(nn.Module):
         # 4. ego-motion: the background-pillar counts start their trip to the host before the head convolutions are
         # queued, so the host draws the keypoint permutations while the GPU is busy with them
         prep = self._ego_prepare(cell2pillar, fb_est, M, B, T, Ny, Nx)
-        h = self._conv(W["ego0"], [bev_feats], B * T, Ny, Nx, True)
-        geo = self._conv(W["ego3"], [h], B * T, Ny, Nx, False)
+        if merged:  # channels 32..95 of the merged head tensor are the ego head's hidden layer
+            geo = self._conv(W["ego3"], [h], B * T, Ny, Nx, False, fmt=fmt, src0_cstride=96, src0_off=128)
+        else:
+            h = self._conv(W["ego0"], [bev_feats], B * T, Ny, Nx, True, fmt=fmt)
+            geo = self._conv(W["ego3"], [h], B * T, Ny, Nx, False, fmt=fmt)
         del h
-        self._ego_motion(W, geo, cell2pillar, prep, pillar_mean, pillar_frame, M, ego_gt, B, T, Ny, Nx, results)
+        self._ego_motion(W, geo, cell2pillar, prep, pillar_mean, pillar_frame, M, ego_gt, B, T, Ny, Nx, results, fmt)
         if self.keep_stages:
-            st.update(pillar_mean=pillar_mean, pillar_feats=pillar_feats, bev_feats=bev_feats, geo=geo, fb_est=fb_est)
+            dec = (lambda t: t) if not fmt else _unpack_p16
+            st.update(pillar_mean=pillar_mean, pillar_feats=pillar_feats, bev_feats=dec(bev_feats), geo=dec(geo), fb_est=fb_est)
         del geo
 
         self._mark("ego")
@@ -612,7 +689,7 @@ class MotionNet(nn.Module):
             pose_est = self.inject["ego_motion_est"].to(dev).float().contiguous()
         warped = self._graph_input(("stpn", B, T, Ny, Nx, tc), (B * T, Ny, Nx, 32), dev)
         call("pcab_warp_bev", P(bev_feats), P(pose_est), I(B), I(T), I(Ny), I(Nx), I(32), F(self.resolution[0]),
-             F(self.resolution[1]), F(self.pc_range[0]), F(self.pc_range[1]), P(warped), stream())
+             F(self.resolution[1]), F(self.pc_range[0]), F(self.pc_range[1]), P(warped), I(fmt), stream())
         tp = torch.empty(N, 3, device=dev)
         call("pcab_transform_points", P(pts), P(pframe), P(pose_est), I(N), P(tp), stream())
         results["transformed_points"] = tp
@@ -627,15 +704,16 @@ class MotionNet(nn.Module):
         call("pcab_init_point_outputs", I(N), P(full_mos), P(full_off), stream())
         mos_feats = None
         if n_fg > MIN_POINTS:
-            mos_feats = self._run_stack(("stpn", B, T, Ny, Nx, tc), self._stpn_stack(W, B, T, Ny, Nx, dev))
+            mos_feats = self._run_stack(("stpn", B, T, Ny, Nx, tc), self._stpn_stack(W, B, T, Ny, Nx, dev, fmt))
             if self.use_tensor_cores:
-                call("pcab_stpn_head_tc", P(mos_feats), I(Ny), I(Nx), P(tp), P(pbatch), P(fg_idx), I(n_fg), P(W["stpn_head_host"]),
+                call("pcab_stpn_head_tc", P(mos_feats), I(fmt), I(Ny), I(Nx), P(tp), P(pbatch), P(fg_idx), I(n_fg), P(W["stpn_head_host"]),
                      P(W["stpn_head_tc1"]), P(W["stpn_head_tc"]), F(x_abs), F(y_abs), P(full_mos), P(full_off), stream())
             else:
                 call("pcab_stpn_head", P(mos_feats), I(Ny), I(Nx), P(tp), P(pbatch), P(fg_idx), I(n_fg), P(W["stpn_head"]),
                      F(x_abs), F(y_abs), P(full_mos), P(full_off), stream())
         if self.keep_stages:
-            st.update(warped=warped, mos_feats=mos_feats)
+            dec = (lambda t: t) if not fmt else _unpack_p16
+            st.update(warped=dec(warped), mos_feats=None if mos_feats is None else dec(mos_feats))
         results["mos_est"], results["offset_est"] = full_mos, full_off
         if "mos_est" in self.inject:
             full_mos = self.inject["mos_est"].to(dev).float().contiguous()
@@ -664,9 +742,9 @@ class MotionNet(nn.Module):
                 raise NameError("name 'mos_feats' is not defined")
             bb = torch.empty(n_rec, 32, device=dev)
             mf = torch.empty(n_rec, 64, device=dev)
-            call("pcab_ungrid", P(bev_feats), I(32), I(Ny), I(Nx), P(pts), P(pframe), P(rec_idx), I(n_rec), F(x_abs),
+            call("pcab_ungrid", P(bev_feats), I(32), I(fmt), I(Ny), I(Nx), P(pts), P(pframe), P(rec_idx), I(n_rec), F(x_abs),
                  F(y_abs), P(bb), stream())
-            call("pcab_ungrid", P(mos_feats), I(64), I(Ny), I(Nx), P(tp), P(pbatch), P(rec_idx), I(n_rec), F(x_abs),
+            call("pcab_ungrid", P(mos_feats), I(64), I(fmt), I(Ny), I(Nx), P(tp), P(pbatch), P(rec_idx), I(n_rec), F(x_abs),
                  F(y_abs), P(mf), stream())
             if self.keep_stages:
                 st.update(backbone_feats=bb, motion_feats=mf)
@@ -680,6 +758,8 @@ class MotionNet(nn.Module):
                 "ego_motion_gt": results["ego_motion_gt"]}, results, T)
             call("pcab_scatter_rows3", P(results["sub_rec_est"]), P(rec_idx), I(n_rec), P(rec_est), stream())
         self._mark("tubenet")
+        if fmt:
+            self._deferred.append((("_p16_saturated",), sat))
         if self._deferred:
             vals = torch.cat([t.reshape(-1).float() for _, t in self._deferred]).cpu().tolist()
             i = 0
@@ -687,6 +767,14 @@ class MotionNet(nn.Module):
                 for k in keys:
                     results[k] = vals[i]
                     i += 1
+        if results.pop("_p16_saturated", 0):
+            # an activation left the fp16 range (+-65504) and was clamped: the fp16-pair operands cannot represent this
+            # checkpoint's activations.  Switch this model to the 3xTF32 operands (full float32 range) and redo the scene.
+            import warnings
+
+            warnings.warn("pcaccumulation_b200: BEV activations beyond the fp16 range; switching conv_operands to 'tf32'")
+            self.conv_operands = "tf32"
+            return self._forward(input_dict)
         return results
 
     # ------------------------------------------------------------------------------------------
@@ -709,7 +797,7 @@ class MotionNet(nn.Module):
         ev.record()
         return bg_cells, frame_off, host, ev
 
-    def _ego_motion(self, W, geo, cell2pillar, prep, pillar_mean, pillar_frame, M, ego_gt, B, T, Ny, Nx, results):
+    def _ego_motion(self, W, geo, cell2pillar, prep, pillar_mean, pillar_frame, M, ego_gt, B, T, Ny, Nx, results, fmt=0):
         """models/egomotion.py:387-469.  The host only draws the keypoint permutations (H3 protocol:
         ``torch.randperm`` on the CPU generator, in the reference's order) from ONE readback of the
         per-frame background-pillar counts; everything else is batched over all pairs on the device."""
@@ -762,7 +850,7 @@ class MotionNet(nn.Module):
         gt = torch.empty(B, T, 4, 4, device=dev)
         scalars = torch.empty(4, device=dev)
         ws = scratch(size("pcab_ego_pairs_workspace", I(npairs)), dev)
-        call("pcab_ego_pairs", P(geo), P(cell2pillar), P(pillar_mean), P(pillar_frame), I(M), P(bg_cells), P(frame_off),
+        call("pcab_ego_pairs", P(geo), I(fmt), P(cell2pillar), P(pillar_mean), P(pillar_frame), I(M), P(bg_cells), P(frame_off),
              P(pair_frames_d), P(choice_d), P(thr2_d), I(npairs), P(W["alpha"]), P(W["beta"]),
              I(cfg["pose_estimation"]["sinkhorn_iter"]), P(ego_gt), P(chain_pair_d), I(B), I(T),
              I(1 if mode == "chain" else 0), P(perm), P(pose_pairs), P(est), P(gt), P(scalars), P(ws), Z(ws.numel()),
@@ -966,6 +1054,12 @@ class MotionNet(nn.Module):
             "trans_loss": (torch.norm(gt[:, :3, 3] - rep[:, 4:], p=2, dim=1) * fw).sum() / wsum,
             "inst_est_motion": pose,
         }
+
+
+def _unpack_p16(t):
+    from .tc_pack import unpack_p16
+
+    return unpack_p16(t)
 
 
 class _LazyLossTerms(dict):

@@ -38,14 +38,55 @@ def pack_embed_tc(seq, first=0):
 F16_WEIGHT_SCALE = 256.0  # power of two: keeps the l halves of O(0.01) weights out of the fp16 subnormals
 
 
-def pack_conv_tc_f16(layer):
-    """fp16-pair pack of a 3x3 convolution for ``pcab_conv3x3_tc_f16``: [2 (h, l)][Cout][K/32][64] fp16, the first 32 of every 64
-    = one 32-channel group of the tf32 pack's K order, the rest zero.  h = fp16(s*w), l = fp16(s*w - h)."""
-    k = layer.pack.numel() // layer.cout
-    w = layer.pack.view(k, layer.cout).t().contiguous() * F16_WEIGHT_SCALE  # [Cout][K]
+def f16_weight_scale(w):
+    """Power-of-two scale for the fp16-pair split of a weight tensor: 256 unless that would push max|w| beyond 2^14 (fp16
+    overflows at 65504; a checkpoint with |w| >= 256 must not turn into inf), then the largest power of two that fits."""
+    m = float(w.detach().abs().max()) if w.numel() else 0.0
+    s = F16_WEIGHT_SCALE
+    while m * s > 16384.0 and s > 2.0 ** -24:
+        s *= 0.5
+    return s
+
+
+def pack_rows_f16(rows, scale):
+    """rows [R][K] float32 (K-major, K % 32 == 0) -> fp16 [2 (h, l)][R][K/32][64]: the first 32 of every 64 = one 32-channel
+    group, the rest zero (so a group is one 128-byte swizzle row of the MMA B operand).  h = fp16(s*w), l = fp16(s*w - h)."""
+    r, k = rows.shape
+    w = rows.float() * scale
     h = w.half()
     l = (w - h.float()).half()
-    out = torch.zeros(2, layer.cout, k // 32, 64, dtype=torch.float16, device=w.device)
-    out[0, :, :, :32] = h.view(layer.cout, k // 32, 32)
-    out[1, :, :, :32] = l.view(layer.cout, k // 32, 32)
+    out = torch.zeros(2, r, k // 32, 64, dtype=torch.float16, device=rows.device)
+    out[0, :, :, :32] = h.view(r, k // 32, 32)
+    out[1, :, :, :32] = l.view(r, k // 32, 32)
     return out.contiguous()
+
+
+def pack_conv_tc_f16(layer, scale=F16_WEIGHT_SCALE):
+    """fp16-pair pack of a 3x3 convolution for ``pcab_conv3x3_tc_f16`` / ``pcab_conv3x3_p16``: rows = output channels, K = the
+    tf32 pack's order (per source: tap-major, channel-minor)."""
+    k = layer.pack.numel() // layer.cout
+    return pack_rows_f16(layer.pack.view(k, layer.cout).t().contiguous(), scale)
+
+
+def pack_convT_p16(weight, scale):
+    """ConvTranspose2d(2, stride 2) weight [Cin, Cout, 2, 2] for ``pcab_convT2x2_p16``: GEMM rows (output columns) =
+    (dy*2+dx)*Cout + co, K = Cin."""
+    cin, cout = weight.shape[:2]
+    rows = weight.detach().float().permute(2, 3, 1, 0).reshape(4 * cout, cin).contiguous()
+    return pack_rows_f16(rows, scale)
+
+
+def unpack_p16(t):
+    """Decode a P16 activation tensor (float32-typed storage [..., C], csrc/pair16.cuh) to float32 values h + l."""
+    c = t.shape[-1]
+    h = t.contiguous().view(torch.float16).view(*t.shape[:-1], c // 32, 2, 32)
+    return (h[..., 0, :].float() + h[..., 1, :].float()).reshape(*t.shape[:-1], c)
+
+
+def pack_p16(x):
+    """Encode float32 values [..., C] (C % 32 == 0) as a P16 tensor (float32-typed storage of the same shape)."""
+    c = x.shape[-1]
+    x = x.float().contiguous().view(*x.shape[:-1], c // 32, 32)
+    h = x.clamp(-65504.0, 65504.0).half()
+    l = (x - h.float()).clamp(-65504.0, 65504.0).half()
+    return torch.stack((h, l), -2).contiguous().view(*x.shape[:-2], 2 * c).view(torch.float32)

@@ -207,12 +207,12 @@ def test_convT_maxpool_temporalmax_head2(lib):
     y = torch.randn(3, 32, 10, 14, generator=g)
     outp = torch.empty(3, 5, 7, 32).cuda()
     yd = _nhwc(y).cuda()
-    call("pcab_maxpool2x2", P(yd), P(outp), I(3), I(10), I(14), I(32), stream())
+    call("pcab_maxpool2x2", P(yd), P(outp), I(3), I(10), I(14), I(32), I(0), stream())
     assert torch.equal(outp.cpu(), _nhwc(F.max_pool2d(y, 2, 2)))
     z = torch.randn(2 * 5, 6, 7, 32, generator=g)
     outm = torch.empty(2, 6, 7, 32).cuda()
     zd = z.cuda()
-    call("pcab_temporal_max", P(zd), P(outm), I(2), I(5), I(6), I(7), I(32), stream())
+    call("pcab_temporal_max", P(zd), P(outm), I(2), I(5), I(6), I(7), I(32), I(0), stream())
     assert torch.equal(outm.cpu(), z.view(2, 5, 6, 7, 32).max(1)[0])
     h = torch.randn(2, 32, 13, 17, generator=g)
     w2 = torch.randn(2, 32, 3, 3, generator=g) * 0.1
@@ -221,7 +221,7 @@ def test_convT_maxpool_temporalmax_head2(lib):
     logits = torch.empty(2, 2, 13, 17).cuda()
     am = torch.empty(2 * 13 * 17, dtype=torch.int32).cuda()
     hd, w2d, b2d = _nhwc(h).cuda(), w2.permute(2, 3, 1, 0).contiguous().cuda(), b2.cuda()
-    call("pcab_head2_conv", P(hd), I(32), P(w2d), P(b2d), I(2), I(13), I(17), P(logits), P(am), stream())
+    call("pcab_head2_conv", P(hd), I(32), I(32), I(0), P(w2d), P(b2d), I(2), I(13), I(17), P(logits), P(am), stream())
     assert_close_rel(logits, ref2, 2e-5, "head2")
     assert torch.equal(am.cpu().view(2, 13, 17).long(), logits.cpu().max(1)[1])
 
@@ -588,7 +588,7 @@ def test_stpn_head_tensor_core_matches_fp32_head(fixture_weights, n_fg):
         mos = torch.full((N, 2), 7.0, device="cuda")
         off = torch.full((N, 2), 7.0, device="cuda")
         if tc:
-            call("pcab_stpn_head_tc", P(feats), I(H), I(Wd), P(tp), P(pbatch), P(fg_idx), I(n_fg), P(W["stpn_head_host"]),
+            call("pcab_stpn_head_tc", P(feats), I(0), I(H), I(Wd), P(tp), P(pbatch), P(fg_idx), I(n_fg), P(W["stpn_head_host"]),
                  P(W["stpn_head_tc1"]), P(W["stpn_head_tc"]), F(12.0), F(12.0), P(mos), P(off), stream())
         else:
             call("pcab_stpn_head", P(feats), I(H), I(Wd), P(tp), P(pbatch), P(fg_idx), I(n_fg), P(W["stpn_head"]), F(12.0), F(12.0),
@@ -821,3 +821,198 @@ def test_cluster_evaluator_matches_oracle():
     assert want[8:].sum() > 10 and want[3] + want[7] > 10
     summ = ev.summary()
     assert summ["@0.5"]["tp"].sum() >= summ["@0.9"]["tp"].sum()
+
+
+# -------------------------------------------------------------------------------------------------------------
+# pair-packed (P16) activation path: tcgen05 convolution / ConvTranspose over (h, l) fp16 pairs, and the BEV utilities
+# -------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["single", "concat", "temporal", "small_map", "large_values", "wide128", "merged96", "slice",
+                                  "ragged", "c32_stack"])
+def test_conv3x3_p16_against_float64(lib, case):
+    """pcab_conv3x3_p16 (csrc/conv_p16.cu): P16 in, P16 out, every tile shape (32 / 64 / 96 / 128 output columns per item,
+    strip and flattened tiles, ragged edges), concat and Conv3d formulations, a channel slice of a wider tensor as input --
+    1e-5 of the output scale against float64 on the exactly-decoded inputs (the output's own (h, l) rounding is 2^-22)."""
+    import types
+
+    from pcaccumulation_b200 import motionnet as mn, tc_pack
+    from pcaccumulation_b200._lib import F as Fl, I, P, call, stream
+
+    g = torch.Generator().manual_seed(21)
+    T, relu, bn = 1, 1, True
+    if case == "single":
+        n, cs, cout, H, W = 2, [32], 64, 100, 76
+    elif case == "concat":
+        n, cs, cout, H, W = 2, [64, 32], 32, 40, 56
+    elif case == "temporal":
+        n, cs, cout, H, W, T = 6, [32], 32, 36, 44, 3
+    elif case == "small_map":
+        n, cs, cout, H, W = 1, [128], 128, 9, 9
+    elif case == "wide128":
+        n, cs, cout, H, W, relu, bn = 2, [256], 256, 36, 36, 0, False
+    elif case == "merged96":
+        n, cs, cout, H, W = 1, [32], 96, 64, 48
+    elif case == "slice":
+        n, cs, cout, H, W = 1, [64], 64, 32, 40
+    elif case == "ragged":
+        n, cs, cout, H, W = 1, [32], 32, 37, 21
+    elif case == "c32_stack":
+        n, cs, cout, H, W = 5, [32], 32, 144, 144
+    else:
+        n, cs, cout, H, W = 1, [32], 32, 48, 48
+    scale_in = 3.0e3 if case == "large_values" else 1.0
+    xs = [torch.randn(n, H, W, c, generator=g) * scale_in for c in cs]
+    packed = [tc_pack.pack_p16(x).cuda() for x in xs]
+    xq = [tc_pack.unpack_p16(p.cpu()) for p in packed]  # the values the kernel sees
+    for a, b in zip(xs, xq):
+        assert float((a - b).abs().max()) <= 3e-7 * float(a.abs().max())
+    bias = torch.randn(cout, generator=g)
+    sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    src0_cstride, src0_off = 0, 0
+    if T > 1:
+        w = torch.randn(cout, cs[0], 3, 3, 3, generator=g) * 0.1
+        layer = mn._ConvLayer(types.SimpleNamespace(weight=w.cuda(), bias=bias.cuda()), temporal=True)
+        x5 = xq[0].view(n // T, T, H, W, cs[0]).permute(0, 4, 1, 2, 3).double()
+        ref = F.conv3d(x5, w.double(), bias.double(), padding=1).permute(0, 2, 3, 4, 1).reshape(n, H, W, cout)
+        srcs, c3 = [packed[0]] * 3, [cs[0]] * 3
+    else:
+        w = torch.randn(cout, sum(cs), 3, 3, generator=g) * 0.1
+        layer = mn._ConvLayer(types.SimpleNamespace(weight=w.cuda(), bias=bias.cuda()), splits=cs)
+        x4 = torch.cat(xq, 3).permute(0, 3, 1, 2).double()
+        ref = F.conv2d(x4, w.double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+        srcs, c3 = packed + [None] * (3 - len(packed)), cs + [0] * (3 - len(cs))
+        if case == "slice":  # the 64 input channels are channels 32..95 of a 96-channel tensor
+            wide = torch.randn(n, H, W, 96, generator=g)
+            wide[..., 32:] = xq[0]
+            srcs = [tc_pack.pack_p16(wide).cuda(), None, None]
+            src0_cstride, src0_off = 96, 128
+    if bn:
+        ref = ref * sc.double() + sh.double()
+    if relu:
+        ref = F.relu(ref)
+    assert lib.lib().pcab_conv3x3_p16_supported(I(3 if T > 1 else len(cs)), I(c3[0]), I(c3[1]), I(c3[2]), I(cout), I(H), I(W))
+    scale = tc_pack.f16_weight_scale(layer.weight)
+    pack = tc_pack.pack_conv_tc_f16(layer, scale)
+    out = torch.full((n, H, W, cout), float("nan"), device="cuda")
+    sat = torch.zeros(1, dtype=torch.int32, device="cuda")
+    scd, shd = sc.cuda(), sh.cuda()
+    import ctypes
+    call("pcab_conv3x3_p16", ctypes.c_void_p(srcs[0].data_ptr() + src0_off), I(c3[0]), I(src0_cstride), P(srcs[1]), I(c3[1]), P(srcs[2]),
+         I(c3[2]), I(T), P(pack), Fl(1.0 / scale), P(layer.bias), P(scd if bn else None), P(shd if bn else None), I(relu), P(out),
+         I(n), I(H), I(W), I(cout), P(sat), stream())
+    torch.cuda.synchronize()
+    got = tc_pack.unpack_p16(out.cpu())
+    assert not bool(torch.isnan(got).any())
+    assert int(sat.item()) == 0
+    assert_close_rel(got, ref, 1e-5, f"conv p16 {case}")
+
+
+def test_conv3x3_p16_saturation_is_counted(lib):
+    """Outputs beyond the fp16 range are clamped and COUNTED (the model then switches to the tf32 operands)."""
+    import types
+
+    from pcaccumulation_b200 import motionnet as mn, tc_pack
+    from pcaccumulation_b200._lib import F as Fl, I, P, call, stream
+
+    x = torch.full((1, 16, 16, 32), 3.0e4)
+    w = torch.full((32, 32, 3, 3), 0.5)
+    layer = mn._ConvLayer(types.SimpleNamespace(weight=w.cuda(), bias=torch.zeros(32).cuda()))
+    scale = tc_pack.f16_weight_scale(layer.weight)
+    out = torch.zeros(1, 16, 16, 32, device="cuda")
+    sat = torch.zeros(1, dtype=torch.int32, device="cuda")
+    xp = tc_pack.pack_p16(x).cuda()
+    pack = tc_pack.pack_conv_tc_f16(layer, scale)
+    call("pcab_conv3x3_p16", P(xp), I(32), I(0), P(None), I(0), P(None), I(0), I(1), P(pack), Fl(1.0 / scale), P(layer.bias), P(None),
+         P(None), I(0), P(out), I(1), I(16), I(16), I(32), P(sat), stream())
+    torch.cuda.synchronize()
+    assert int(sat.item()) > 0
+    assert float(tc_pack.unpack_p16(out.cpu()).max()) <= 65504.0 * 1.001
+    # weights beyond 256 do not become inf in the pack
+    big = mn._ConvLayer(types.SimpleNamespace(weight=(w * 2000).cuda(), bias=torch.zeros(32).cuda()))
+    s2 = tc_pack.f16_weight_scale(big.weight)
+    assert s2 < 256.0 and bool(torch.isfinite(tc_pack.pack_conv_tc_f16(big, s2).float()).all())
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 32, 9, 11), (1, 512, 256, 18, 18), (5, 64, 32, 144, 144), (1, 128, 128, 36, 36), (1, 256, 128, 10, 20)])
+def test_convT2x2_p16_against_float64(lib, shape):
+    """pcab_convT2x2_p16: ConvTranspose2d(2, stride 2) as a 1-tap tcgen05 GEMM with 4 x Cout columns, scattered to the four
+    output positions by strided TMA stores."""
+    from pcaccumulation_b200 import tc_pack
+    from pcaccumulation_b200._lib import F as Fl, I, P, call, stream
+
+    n, cin, cout, H, W = shape
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, H, W, cin, generator=g)
+    xp = tc_pack.pack_p16(x).cuda()
+    xq = tc_pack.unpack_p16(xp.cpu())
+    w = torch.randn(cin, cout, 2, 2, generator=g) * 0.1
+    b = torch.randn(cout, generator=g)
+    ref = F.conv_transpose2d(xq.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=2).permute(0, 2, 3, 1)
+    scale = tc_pack.f16_weight_scale(w)
+    pack = tc_pack.pack_convT_p16(w.cuda(), scale)
+    out = torch.full((n, 2 * H, 2 * W, cout), float("nan"), device="cuda")
+    sat = torch.zeros(1, dtype=torch.int32, device="cuda")
+    bd = b.cuda()
+    call("pcab_convT2x2_p16", P(xp), I(cin), P(pack), Fl(1.0 / scale), P(bd), P(out), I(n), I(H), I(W), I(cout), P(sat), stream())
+    torch.cuda.synchronize()
+    got = tc_pack.unpack_p16(out.cpu())
+    assert not bool(torch.isnan(got).any()) and int(sat.item()) == 0
+    assert_close_rel(got, ref, 1e-5, "convT p16")
+
+
+def test_bev_utilities_on_p16_equal_their_float32_versions(lib):
+    """maxpool / temporal max / pose warp / 2-class head / bilinear pickup read and write P16 tensors: same results as the
+    float32 kernels on the decoded values (pooling exactly; the others to the (h, l) rounding of their outputs)."""
+    from pcaccumulation_b200 import tc_pack
+    from pcaccumulation_b200._lib import F as Fl, I, P, call, stream
+
+    g = torch.Generator().manual_seed(9)
+    y = torch.randn(3, 10, 14, 64, generator=g)
+    yp = tc_pack.pack_p16(y).cuda()
+    yq = tc_pack.unpack_p16(yp.cpu()).cuda()
+    o1, o0 = torch.empty(3, 5, 7, 64).cuda(), torch.empty(3, 5, 7, 64).cuda()
+    call("pcab_maxpool2x2", P(yp), P(o1), I(3), I(10), I(14), I(64), I(1), stream())
+    call("pcab_maxpool2x2", P(yq), P(o0), I(3), I(10), I(14), I(64), I(0), stream())
+    assert torch.equal(tc_pack.unpack_p16(o1), o0)
+    z = torch.randn(2 * 5, 6, 7, 32, generator=g)
+    zp = tc_pack.pack_p16(z).cuda()
+    zq = tc_pack.unpack_p16(zp.cpu()).cuda()
+    m1, m0 = torch.empty(2, 6, 7, 32).cuda(), torch.empty(2, 6, 7, 32).cuda()
+    call("pcab_temporal_max", P(zp), P(m1), I(2), I(5), I(6), I(7), I(32), I(1), stream())
+    call("pcab_temporal_max", P(zq), P(m0), I(2), I(5), I(6), I(7), I(32), I(0), stream())
+    assert torch.equal(tc_pack.unpack_p16(m1), m0)
+    # pose warp
+    B, T, H, W = 1, 3, 24, 40
+    bev = torch.randn(B * T, H, W, 32, generator=g)
+    bp = tc_pack.pack_p16(bev).cuda()
+    bq = tc_pack.unpack_p16(bp.cpu()).cuda()
+    pose = torch.eye(4).repeat(B * T, 1, 1)
+    pose[1, :2, 3] = torch.tensor([0.7, -0.4])
+    pose[2, :2, :2] = torch.tensor([[0.9950, -0.0998], [0.0998, 0.9950]])
+    pose = pose.cuda()
+    w1, w0 = torch.empty(B * T, H, W, 32).cuda(), torch.empty(B * T, H, W, 32).cuda()
+    for buf, src, fmt in ((w1, bp, 1), (w0, bq, 0)):
+        call("pcab_warp_bev", P(src), P(pose), I(B), I(T), I(H), I(W), I(32), Fl(0.25), Fl(0.25), Fl(-5.0), Fl(-3.0), P(buf), I(fmt), stream())
+    assert_close_rel(tc_pack.unpack_p16(w1), w0.cpu(), 1e-6, "warp p16")
+    # 2-class head on channels 0..31 of a 96-channel P16 tensor
+    h = torch.randn(2, 13, 17, 96, generator=g)
+    hp = tc_pack.pack_p16(h).cuda()
+    hq = tc_pack.unpack_p16(hp.cpu())[..., :32].contiguous().cuda()
+    w2 = (torch.randn(2, 32, 3, 3, generator=g) * 0.1).permute(2, 3, 1, 0).contiguous().cuda()
+    b2 = torch.randn(2, generator=g).cuda()
+    l1, l0 = torch.empty(2, 2, 13, 17).cuda(), torch.empty(2, 2, 13, 17).cuda()
+    a1, a0 = torch.empty(2 * 13 * 17, dtype=torch.int32).cuda(), torch.empty(2 * 13 * 17, dtype=torch.int32).cuda()
+    call("pcab_head2_conv", P(hp), I(32), I(96), I(1), P(w2), P(b2), I(2), I(13), I(17), P(l1), P(a1), stream())
+    call("pcab_head2_conv", P(hq), I(32), I(32), I(0), P(w2), P(b2), I(2), I(13), I(17), P(l0), P(a0), stream())
+    assert torch.equal(l1, l0) and torch.equal(a1, a0)
+    # bilinear pickup
+    feats = torch.randn(2, 20, 24, 64, generator=g)
+    fp = tc_pack.pack_p16(feats).cuda()
+    fq = tc_pack.unpack_p16(fp.cpu()).cuda()
+    k = 500
+    xyz = ((torch.rand(k, 3, generator=g) * 2 - 1) * torch.tensor([6.5, 6.5, 2.0])).cuda()
+    frame = (torch.rand(k, generator=g) < 0.5).to(torch.int32).cuda()
+    u1, u0 = torch.empty(k, 64).cuda(), torch.empty(k, 64).cuda()
+    for buf, src, fmt in ((u1, fp, 1), (u0, fq, 0)):
+        call("pcab_ungrid", P(src), I(64), I(fmt), I(20), I(24), P(xyz), P(frame), P(None), I(k), Fl(6.0), Fl(6.0), P(buf), stream())
+    torch.cuda.synchronize()
+    assert torch.equal(u1, u0)
