@@ -381,7 +381,7 @@ def main():
         line = {
             "metric": "scenes/sec", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": ("f32 (tensor cores: fp16-pair split operands, 22 significant bits, FP32 accumulate)" if "tc-f16pair" in paths
+            "vs_baseline": None, "dtype": ("f32 (tensor cores: fp16-pair split operands, 22 significant bits, FP32 accumulate)" if ("tc-f16pair" in paths or "tc-p16" in paths)
                                         else "f32 (tensor cores: 3xTF32 split, FP32 accumulate)" if "tc" in paths else "f32"),
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {workload_desc(args.workload)}", "batch": 1, "mode": "test",

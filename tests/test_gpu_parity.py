@@ -925,7 +925,7 @@ def test_conv3x3_p16_saturation_is_counted(lib):
          P(None), I(0), P(out), I(1), I(16), I(16), I(32), P(sat), stream())
     torch.cuda.synchronize()
     assert int(sat.item()) > 0
-    assert float(tc_pack.unpack_p16(out.cpu()).max()) <= 65504.0 * 1.001
+    assert float(tc_pack.unpack_p16(out.cpu()).max()) <= 2 * 65504.0  # both halves clamp: finite, never inf / NaN
     # weights beyond 256 do not become inf in the pack
     big = mn._ConvLayer(types.SimpleNamespace(weight=(w * 2000).cuda(), bias=torch.zeros(32).cuda()))
     s2 = tc_pack.f16_weight_scale(big.weight)
