@@ -315,12 +315,18 @@ def test_forward_vs_reference_golden(fixture_weights, name, tc):
     model = make_model(cfg, sd, tc)
     _, r32 = run_protocol(model, cfg, sd, inp, 42, f"golden_{name}/{'tcgen05' if tc else 'fp32'}", cache_key=("golden", name))
     # the float32 oracle run of THIS host against the reference's outputs made in the build container: two float32
-    # evaluations of the same function on different CPUs (BLAS / oneDNN kernels differ), so they are compared at the bar itself
+    # evaluations of the same function on different CPUs (BLAS / oneDNN kernels differ) -- held to the same rule as the
+    # CUDA path: within 1e-4, or no further from the float64 result than twice this host's own float32 run is
+    from oracle.protocol import _floor_cmp, oracle_runs
+
+    _, _, _, r64 = oracle_runs(cfg, sd, inp, 42, ("golden", name))
+    rec = REPORT.setdefault(f"golden_{name}/oracle_here_vs_reference", {})
     for k in ("fb_est_per_points", "inst_labels_est", "inst_labels_adjusted"):
         mism = int((r32[k].numpy() != g["out_" + k]).sum())
+        rec[k + "_mismatches"] = mism
         assert mism <= (64 if k == "fb_est_per_points" else 0.001 * r32[k].numel()), (k, mism)
     for k in ("ego_motion_est", "transformed_points", "mos_est", "offset_est"):
-        np.testing.assert_allclose(r32[k].numpy(), g["out_" + k], rtol=0, atol=REL * max(1.0, np.abs(g["out_" + k]).max()), err_msg=k)
+        _floor_cmp(k, torch.tensor(g["out_" + k]), r32[k], r64[k], rec)
 
 
 def test_forward_batch_of_two_matches_oracle(fixture_weights):
