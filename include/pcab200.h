@@ -94,10 +94,13 @@ int pcab_conv3x3_tc_f16(const float* src0, int c0, const float* src1, int c1, co
  * pairs and TMA-stores them; weights as for pcab_conv3x3_tc_f16.  src0_cstride: 0, or the channel count of the tensor src0
  * points INTO (src0 = first byte of the first used 32-channel group) -- reads a channel slice of a wider tensor.
  * sat_counter (device, may be NULL) is incremented when an output beyond +-65504 was clamped.
+ * Weights: fp16 [2 (h, l)][columns][Kpad], K dense in the kernel's consumption order -- per source, per 32-channel chunk,
+ * per tap, 32 channels -- zero-padded to a multiple of 64 (tc_pack.pack_conv_p16 / pack_convT_p16), pre-multiplied by
+ * 1/weight_scale_inv (a power of two).
  * pcab_convT2x2_p16: ConvTranspose2d(kernel 2, stride 2) (models/unet.py:24-33) as a 1-tap GEMM with 4*Cout columns on the
- * same pipeline; weights fp16 [2][4*Cout][Cin/32][64], column = (dy*2+dx)*Cout + co. */
+ * same pipeline; column = (dy*2+dx)*Cout + co. */
 int pcab_conv3x3_p16_supported(int n_sources, int c0, int c1, int c2, int Cout, int H, int W);
-int pcab_conv_p16_plan(int n_images, int H, int W, int Cout, int cin_total, int ntaps, int* out12 /* host */);
+int pcab_conv_p16_plan(int n_images, int H, int W, int Cout, int cin_total, int ntaps, int* out13 /* host */);
 int pcab_conv3x3_p16(const void* src0, int c0, int src0_cstride, const void* src1, int c1, const void* src2, int c2,
                      int temporal_T, const void* weight_f16_packed, float weight_scale_inv, const float* bias,
                      const float* bn_scale, const float* bn_shift, int relu, void* out, int n_images, int H, int W, int Cout,

@@ -50,6 +50,10 @@ struct Args {
   int np;             // plane pipeline stages
   uint32_t plane_bytes;
   int ntaps;          // 9 (conv3x3) or 1 (ConvTranspose positions)
+  int resident;       // 1: all weights of the (single) column tile stay in shared memory for the life of the CTA
+  int wslots;         // weight stages in shared memory: all of them (resident) or a ring of kWStages
+  int kg_src[3];      // first K group (32 input channels of one tap, consumption order) of each source
+  int kg_total;
   int relu;
   int cout_real;      // ConvT: output channels of the layer (bias index = column % cout_real); else == Cout
   float wscale_inv;
@@ -104,7 +108,7 @@ k_conv_p16(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w0 = sbase + (uint32_t)a.np * a.plane_bytes;
-  const uint32_t stg0 = w0 + kWStages * kWBytes;
+  const uint32_t stg0 = w0 + (uint32_t)a.wslots * kWBytes;
   const uint32_t stg_bytes = (uint32_t)a.mt * 16384u;  // one 32-channel group of the item's pixels, 128 B per pixel
   const uint32_t bars = stg0 + (uint32_t)(C / 32) * stg_bytes;
   const uint32_t bar_plane_full = bars, bar_plane_free = bars + 32, bar_w_full = bars + 64, bar_w_free = bars + 88,
@@ -161,36 +165,48 @@ k_conv_p16(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
     __syncwarp();
   } else if (warp == 13) {
     // ===================== weight producer =====================
+    // The weight matrix is K-dense in CONSUMPTION order (source, 32-channel chunk, tap): one 128-byte row = two K groups, one
+    // stage = [w_h rows | w_l rows] of a pair of groups.  Resident mode loads every stage once; otherwise the stages an item
+    // touches stream through a ring of kWStages slots.
     if (lane == 0) {
-      int wg = 0;
-      for (int it = blockIdx.x; it < a.total_items; it += gridDim.x) {
-        const Item t = decode_item(a, C, it);
-        int kbase_src = 0;
-        for (int s = 0; s < a.nsrc; ++s) {
-          const int Cs = a.src_c[s];
-          if (src_valid(a, s, t.tframe)) {
-            for (int c0 = 0; c0 < Cs; c0 += 32) {
-              for (int tap = 0; tap < NT; ++tap, ++wg) {
-                const int ws = wg % kWStages;
-                if (wg >= kWStages) mbar_wait(bar_w_free + 8 * ws, (uint32_t)((wg / kWStages) - 1) & 1u);
-                mbar_expect_tx(bar_w_full + 8 * ws, kWBytes);
-                const int k0 = (kbase_src + tap * Cs + c0) * 2;  // fp16 rows: 64 elements per 32-channel group (32 used)
-                tma_load_2d(&map_b, w0 + ws * kWBytes, bar_w_full + 8 * ws, k0, t.co0);
-                tma_load_2d(&map_b, w0 + ws * kWBytes + C * 128u, bar_w_full + 8 * ws, k0, a.Cout + t.co0);
-              }
+      if (a.resident) {
+        const int nst = (a.kg_total + 1) >> 1;
+        mbar_expect_tx(bar_w_full, (uint32_t)nst * kWBytes);
+        for (int j = 0; j < nst; ++j) {
+          tma_load_2d(&map_b, w0 + (uint32_t)j * kWBytes, bar_w_full, 64 * j, 0);
+          tma_load_2d(&map_b, w0 + (uint32_t)j * kWBytes + C * 128u, bar_w_full, 64 * j, a.Cout);
+        }
+      } else {
+        int wc = 0;
+        for (int it = blockIdx.x; it < a.total_items; it += gridDim.x) {
+          const Item t = decode_item(a, C, it);
+          int prev_j = -1;
+          for (int s = 0; s < a.nsrc; ++s) {
+            if (!src_valid(a, s, t.tframe)) continue;
+            const int ng = (a.src_c[s] / 32) * NT;
+            for (int kg = a.kg_src[s]; kg < a.kg_src[s] + ng; ++kg) {
+              const int j = kg >> 1;
+              if (j == prev_j) continue;
+              prev_j = j;
+              const int ws = wc % kWStages;
+              if (wc >= kWStages) mbar_wait(bar_w_free + 8 * ws, (uint32_t)((wc / kWStages) - 1) & 1u);
+              mbar_expect_tx(bar_w_full + 8 * ws, kWBytes);
+              tma_load_2d(&map_b, w0 + ws * kWBytes, bar_w_full + 8 * ws, 64 * j, t.co0);
+              tma_load_2d(&map_b, w0 + ws * kWBytes + C * 128u, bar_w_full + 8 * ws, 64 * j, a.Cout + t.co0);
+              ++wc;
             }
           }
-          kbase_src += NT * Cs;
         }
       }
     }
     __syncwarp();
   } else if (warp >= 14) {
     // ===================== MMA issuers =====================
-    // warp 14 owns M tile 0, warp 15 M tile 1 (disjoint accumulators: no ordering between them).  One elected lane runs
-    // a whole chunk; for the 9-tap convolution the tap loop is unrolled (weight stage and parity are literals).
+    // warp 14 owns M tile 0, warp 15 M tile 1 (disjoint accumulators: no ordering between them).  The whole warp runs the
+    // loop with warp-uniform state; the tcgen05 instructions themselves are issued by one fixed lane.
     const int mi = warp - 14;
     if (mi < a.mt) {
+      const bool leader = elect_one();
       const uint32_t idesc_base = (1u << 4) | ((128u >> 4) << 24);  // D = F32, A = B = F16, K-major both, M = 128
       const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * C) >> 3) << 17);
       const uint32_t idesc1 = idesc_base | ((uint32_t)(C >> 3) << 17);
@@ -203,28 +219,43 @@ k_conv_p16(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
       const uint32_t wp8 = (uint32_t)a.Wp * 8u;
       const uint32_t a_base = lbo | (((sbase & 0x3FFFF) >> 4) + tile_off16);
       const uint32_t b_base = lbo | ((w0 & 0x3FFFF) >> 4);
-      int g = 0, wg = 0;
+      int g = 0, wc = 0;
+      if (a.resident) {
+        mbar_wait(bar_w_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       for (int it = blockIdx.x; it < a.total_items; it += gridDim.x) {
         const Item t = decode_item(a, C, it);
-        const int nchunks = item_chunks(a, t.tframe);
-        for (int ci = 0; ci < nchunks; ++ci, ++g) {
-          const int st = g & 1, ps = g % a.np;
-          mbar_wait(bar_plane_full + 8 * ps, (uint32_t)(g / a.np) & 1u);
-          if (g >= 2) mbar_wait(bar_acc_empty + 8 * st, (uint32_t)((g >> 1) - 1) & 1u);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (elect_one()) {
+        int prev_j = -1, slot = 0;
+        for (int s = 0; s < a.nsrc; ++s) {
+          if (!src_valid(a, s, t.tframe)) continue;
+          for (int c0 = 0, kg0 = a.kg_src[s]; c0 < a.src_c[s]; c0 += 32, kg0 += NT, ++g) {
+            const int st = g & 1, ps = g % a.np;
+            mbar_wait(bar_plane_full + 8 * ps, (uint32_t)(g / a.np) & 1u);
+            if (g >= 2) mbar_wait(bar_acc_empty + 8 * st, (uint32_t)((g >> 1) - 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t ap = a_base + (uint32_t)ps * (a.plane_bytes >> 4);
             const uint32_t tmem_d = tmem_base + (uint32_t)(st * a.mt * 2 * C + mi * 2 * C);
-            if (NT == 9) {
-              const uint32_t wpar = (uint32_t)g;  // weight stage `tap % 3` is in its (3g + tap/3)-th use
 #pragma unroll
-              for (int tap = 0; tap < 9; ++tap) {
-                static_assert(kWStages == 3, "the unrolled tap loop assumes a 3-deep weight ring");
-                const int ws = tap % 3;
-                mbar_wait(bar_w_full + 8 * ws, (wpar + (uint32_t)(tap / 3)) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t shift16 = (uint32_t)(tap / 3) * wp8 + (uint32_t)(tap % 3) * 8u;
-                const uint32_t b16 = b_base + (uint32_t)ws * (kWBytes >> 4);
+            for (int tap = 0; tap < NT; ++tap) {
+              const int kg = kg0 + tap;
+              uint32_t bst;
+              if (a.resident) {
+                bst = b_base + (uint32_t)(kg >> 1) * (kWBytes >> 4);
+              } else {
+                const int j = kg >> 1;
+                if (j != prev_j) {  // first group of a new weight stage: release the previous slot, wait for the next one
+                  if (prev_j >= 0 && leader) umma_commit(bar_w_free + 8 * slot);
+                  slot = wc % kWStages;
+                  mbar_wait(bar_w_full + 8 * slot, (uint32_t)(wc / kWStages) & 1u);
+                  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                  ++wc, prev_j = j;
+                }
+                bst = b_base + (uint32_t)slot * (kWBytes >> 4);
+              }
+              const uint32_t b16 = bst + (uint32_t)(kg & 1) * 4u;  // second group of the pair: bytes 64-127 of the rows
+              const uint32_t shift16 = NT == 9 ? (uint32_t)(tap / 3) * wp8 + (uint32_t)(tap % 3) * 8u : 0u;
+              if (leader) {
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk) {
                   const uint64_t dah = desc_hi_a | (ap + shift16 + 2u * kk);       // bytes 0-63 of a row: a_h
@@ -233,29 +264,17 @@ k_conv_p16(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
                   umma_f16(tmem_d, dah, db, idesc2, (tap == 0 && kk == 0) ? 0u : 1u);  // [a_h*w_h | a_h*w_l]
                   umma_f16(tmem_d + (uint32_t)C, dal, db, idesc1, 1u);                // += a_l*w_h into the second half
                 }
-                umma_commit(bar_w_free + 8 * ws);
               }
-            } else {
-              const int ws = wg % kWStages;
-              mbar_wait(bar_w_full + 8 * ws, (uint32_t)(wg / kWStages) & 1u);
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t b16 = b_base + (uint32_t)ws * (kWBytes >> 4);
-#pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const uint64_t dah = desc_hi_a | (ap + 2u * kk);
-                const uint64_t dal = desc_hi_a | (ap + 4u + 2u * kk);
-                const uint64_t db = desc_hi_b | (b16 + 2u * kk);
-                umma_f16(tmem_d, dah, db, idesc2, kk == 0 ? 0u : 1u);
-                umma_f16(tmem_d + (uint32_t)C, dal, db, idesc1, 1u);
-              }
-              umma_commit(bar_w_free + 8 * ws);
             }
-            umma_commit(bar_plane_free + 8 * ps);
-            umma_commit(bar_acc_full + 8 * st);
+            if (leader) {
+              umma_commit(bar_plane_free + 8 * ps);
+              umma_commit(bar_acc_full + 8 * st);
+            }
+            __syncwarp();
           }
-          __syncwarp();
-          wg += NT;
         }
+        if (!a.resident && prev_j >= 0 && leader) umma_commit(bar_w_free + 8 * slot);
+        __syncwarp();
       }
     }
   } else if (warp < 4 * NG) {
@@ -388,7 +407,7 @@ k_conv_p16(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
 // host side: tile plan, tensor maps, launch
 // --------------------------------------------------------------------------------------------------------------------
 struct Cfg {
-  int c, mt, strip, mtx, R, Wt, Wp, tiles_x, tiles_y, n_ctile, total, np, plane_rows;
+  int c, mt, strip, mtx, R, Wt, Wp, tiles_x, tiles_y, n_ctile, total, np, plane_rows, resident, wslots;
   size_t smem;
 };
 
@@ -396,15 +415,20 @@ struct Cfg {
 // time at 128 B/clk (A 4 KB per MMA, B 32 N bytes)
 int mma_clk(int c) { return c == 32 ? 88 : (c == 64 ? 112 : (c == 96 ? 144 : 192)); }
 
-size_t smem_bytes(int c, int mt, int np, int plane_rows) {
-  return 1024 + (size_t)np * plane_rows * 128 + (size_t)kWStages * 2 * c * 128 + (size_t)(c / 32) * mt * 16384 + 256;
+size_t smem_bytes(int c, int mt, int np, int plane_rows, int wslots) {
+  return 1024 + (size_t)np * plane_rows * 128 + (size_t)wslots * 2 * c * 128 + (size_t)(c / 32) * mt * 16384 + 256;
 }
 
-// pick (columns per item, tile shape) with the lowest modelled time over the SMs of the device
+// pick (columns per item, tile shape, resident / streamed weights) with the lowest modelled time over the SMs of the device.
+// nchunks: 32-channel input chunks per item (all sources); the model charges every chunk its MMA time (shared-memory
+// operand bound below N = 128), the shared-memory write time of what TMA brings in, and the L2 -> SM bandwidth of that
+// traffic summed over the SMs (~6 KB/clk chip-wide): re-streaming the weights for every 128-pixel item is what bounds the
+// wide column tiles unless the weights stay resident.
 bool choose(int n_img, int H, int W, int Cout, int nchunks, int ntaps, Cfg* best) {
   if (Cout % 32) return false;
   const int halo = ntaps == 9 ? 1 : 0;
   const int nsm = pcab_sm_count();
+  const int kg2 = (nchunks * ntaps + 1) / 2;  // weight stages (pairs of K groups) of one column tile
   double best_cost = 1e30;
   bool found = false;
   const int cands[4] = {128, 96, 64, 32};
@@ -416,31 +440,42 @@ bool choose(int n_img, int H, int W, int Cout, int nchunks, int ntaps, Cfg* best
       for (int mt = 1; mt <= mt_max; ++mt) {
         for (int mtx = 1; mtx <= (strip ? mt : 1); ++mtx) {
           for (int Wt = (strip ? 8 * mtx : 6); Wt <= (strip ? 8 * mtx : 41); ++Wt) {
-            Cfg k;
-            k.c = c, k.mt = mt, k.strip = strip, k.mtx = mtx, k.Wt = Wt, k.Wp = Wt + 2 * halo;
-            if (strip) {
-              k.R = 16 * (mt / mtx);
-            } else {
-              k.R = (mt * 128) / k.Wp;
-              if (k.R > H) k.R = H;
-              if (Wt > W) continue;
+            for (int resident = 0; resident <= 1; ++resident) {
+              Cfg k;
+              k.c = c, k.mt = mt, k.strip = strip, k.mtx = mtx, k.Wt = Wt, k.Wp = Wt + 2 * halo;
+              k.n_ctile = Cout / c;
+              if (resident && k.n_ctile != 1) continue;
+              if (strip) {
+                k.R = 16 * (mt / mtx);
+              } else {
+                k.R = (mt * 128) / k.Wp;
+                if (k.R > H) k.R = H;
+                if (Wt > W) continue;
+              }
+              if (k.R < 1 || k.R + 2 * halo > 256) continue;
+              // last plane row a (shifted) view can touch, and the rows the TMA box fills
+              const int last = strip ? ((k.R - 1 + 2 * halo) * k.Wp + (Wt - 8) + 2 * halo + 7) : (mt * 128 - 1 + 2 * halo * k.Wp + 2 * halo);
+              int rows = (k.R + 2 * halo) * k.Wp;
+              if (last + 1 > rows) rows = last + 1;
+              k.plane_rows = (rows + 7) & ~7;
+              k.resident = resident, k.wslots = resident ? kg2 : kWStages;
+              k.np = 4;
+              while (k.np >= 2 && smem_bytes(c, mt, k.np, k.plane_rows, k.wslots) > (size_t)kMaxSmem) --k.np;
+              if (k.np < 2) continue;
+              k.smem = smem_bytes(c, mt, k.np, k.plane_rows, k.wslots);
+              k.tiles_x = cdiv(W, Wt), k.tiles_y = cdiv(H, k.R);
+              k.total = n_img * k.tiles_x * k.tiles_y * k.n_ctile;
+              const double rounds = (double)cdiv(k.total, nsm);
+              const double mma = (double)mt * 2 * ntaps * mma_clk(c);
+              const double tma_bytes = (double)(k.R + 2 * halo) * k.Wp * 128 + (resident ? 0.0 : (double)ntaps * 2 * c * 64);
+              const int busy = k.total < nsm ? k.total : nsm;
+              double chunk = mma + tma_bytes / 128.0;
+              const double l2 = tma_bytes * busy / 6000.0;
+              if (l2 > chunk) chunk = l2;
+              const double item = (double)nchunks * (chunk + 250.0) + 1200.0 + 400.0 * mt * (c / 32);
+              const double cost = rounds * item * (k.np >= 3 ? 1.0 : 1.03) + (resident ? (double)kg2 * 2 * c * 128 / 64.0 : 0.0);
+              if (cost < best_cost - 1e-9) best_cost = cost, *best = k, found = true;
             }
-            if (k.R < 1 || k.R + 2 * halo > 256) continue;
-            // last plane row a (shifted) view can touch, and the rows the TMA box fills
-            const int last = strip ? ((k.R - 1 + 2 * halo) * k.Wp + (Wt - 8) + 2 * halo + 7) : (mt * 128 - 1 + 2 * halo * k.Wp + 2 * halo);
-            int rows = (k.R + 2 * halo) * k.Wp;
-            if (last + 1 > rows) rows = last + 1;
-            k.plane_rows = (rows + 7) & ~7;
-            k.np = 4;
-            while (k.np >= 2 && smem_bytes(c, mt, k.np, k.plane_rows) > (size_t)kMaxSmem) --k.np;
-            if (k.np < 2) continue;
-            k.smem = smem_bytes(c, mt, k.np, k.plane_rows);
-            k.tiles_x = cdiv(W, Wt), k.tiles_y = cdiv(H, k.R), k.n_ctile = Cout / c;
-            k.total = n_img * k.tiles_x * k.tiles_y * k.n_ctile;
-            const double rounds = (double)cdiv(k.total, nsm);
-            const double item = (double)nchunks * ((double)mt * 2 * ntaps * mma_clk(c) + 250.0) + 1200.0 + 400.0 * mt * (c / 32);
-            const double cost = rounds * item * (k.np >= 3 ? 1.0 : 1.04);
-            if (cost < best_cost - 1e-9) best_cost = cost, *best = k, found = true;
           }
         }
       }
@@ -528,8 +563,9 @@ int run(const void* src0, int c0, int src0_cstride, const void* src1, int c1, co
     }
   }
   {
-    // fp16 [2 * cols rows][2K]: per 32-channel group of the K order 32 values + 32 zeros (128 B rows in the box)
-    cuuint64_t K = (cuuint64_t)ntaps * cin_total * 2;
+    // fp16 [2 * cols rows][Kpad]: K dense in consumption order (source, 32-channel chunk, tap), padded to a multiple of 64;
+    // a box = C rows x 64 elements = the (h or l) half of one weight stage
+    cuuint64_t K = (cuuint64_t)((ntaps * (cin_total / 32) + 1) / 2) * 64;
     cuuint64_t dims[2] = {K, (cuuint64_t)2 * cols};
     cuuint64_t strides[1] = {K * 2};
     cuuint32_t box[2] = {64u, (cuuint32_t)cfg.c};
@@ -557,6 +593,9 @@ int run(const void* src0, int c0, int src0_cstride, const void* src1, int c1, co
   a.tiles_x = cfg.tiles_x, a.tiles_y = cfg.tiles_y, a.n_ctile = cfg.n_ctile, a.total_items = cfg.total;
   a.np = cfg.np, a.plane_bytes = (uint32_t)cfg.plane_rows * 128u;
   a.ntaps = ntaps, a.relu = relu, a.cout_real = cout_layer, a.wscale_inv = weight_scale_inv;
+  a.resident = cfg.resident, a.wslots = cfg.wslots;
+  a.kg_total = 0;
+  for (int s = 0; s < 3; ++s) a.kg_src[s] = a.kg_total, a.kg_total += s < nsrc ? (cs[s] / 32) * ntaps : 0;
   a.bias = bias, a.bn_scale = bn_scale, a.bn_shift = bn_shift, a.sat_counter = sat_counter;
   int rc;
   if (ntaps == 9) {
@@ -586,14 +625,14 @@ extern "C" int pcab_conv3x3_p16_supported(int n_sources, int c0, int c1, int c2,
   return (H >= 8 && W >= 8 && choose(1, H, W, Cout, 1, 9, &k)) ? 1 : 0;
 }
 
-// the tile plan: out[0..11] = columns per item, mt, strip, mtx, R, Wt, tiles_x, tiles_y, column tiles, work items, plane stages,
-// dynamic shared memory bytes
-extern "C" int pcab_conv_p16_plan(int n_images, int H, int W, int Cout, int cin_total, int ntaps, int* out12) {
+// the tile plan: out[0..12] = columns per item, mt, strip, mtx, R, Wt, tiles_x, tiles_y, column tiles, work items, plane stages,
+// dynamic shared memory bytes, weights resident
+extern "C" int pcab_conv_p16_plan(int n_images, int H, int W, int Cout, int cin_total, int ntaps, int* out13) {
   Cfg k;
   PCAB_REQUIRE(ntaps == 9 || ntaps == 1, "ntaps is 9 (conv3x3) or 1 (ConvTranspose2x2)");
   PCAB_REQUIRE(choose(n_images, H, W, ntaps == 9 ? Cout : 4 * Cout, cin_total / 32, ntaps, &k), "unsupported shape");
-  int v[12] = {k.c, k.mt, k.strip, k.mtx, k.R, k.Wt, k.tiles_x, k.tiles_y, k.n_ctile, k.total, k.np, (int)k.smem};
-  for (int i = 0; i < 12; ++i) out12[i] = v[i];
+  int v[13] = {k.c, k.mt, k.strip, k.mtx, k.R, k.Wt, k.tiles_x, k.tiles_y, k.n_ctile, k.total, k.np, (int)k.smem, k.resident};
+  for (int i = 0; i < 13; ++i) out13[i] = v[i];
   return PCAB_OK;
 }
 

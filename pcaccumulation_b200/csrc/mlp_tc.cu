@@ -203,6 +203,43 @@ k_stpn_head_tc(const __grid_constant__ CUtensorMap map_w1, const __grid_constant
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int ctid = (int)threadIdx.x;  // 0..255
+      if (a.fmt) {
+        // P16 feature map: work item = (point, 8-channel block): one 16-byte load of the h halves and one of the l halves per
+        // tap (the 8 lanes of a point still cover whole 256-byte pixels), g[2*it], g[2*it+1] = channels 8*q8 .. 8*q8+7
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int e = it * 256 + ctid, p = e >> 3, q8 = e & 7;
+          float qx, qy;
+          int qb;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qx) : "r"(s_px + 4u * p));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qy) : "r"(s_py + 4u * p));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qb) : "r"(s_pb + 4u * p));
+          const mlp::Bilinear bl = mlp::bilinear_border(qx, qy, a.x_abs, a.y_abs, a.H, a.W);
+          const char* base = reinterpret_cast<const char*>(a.mos_feats) + (size_t)qb * a.H * a.W * 256 + (q8 >> 2) * 128 + (q8 & 3) * 16;
+          const int offs[4] = {bl.o00, bl.o01, bl.o10, bl.o11};
+          const float wts[4] = {bl.w00, bl.w01, bl.w10, bl.w11};
+          uint4 hh[4], ll[4];
+#pragma unroll
+          for (int tp_ = 0; tp_ < 4; ++tp_) {
+            hh[tp_] = *reinterpret_cast<const uint4*>(base + (size_t)offs[tp_] * 256);
+            ll[tp_] = *reinterpret_cast<const uint4*>(base + (size_t)offs[tp_] * 256 + 64);
+          }
+          float r8[8];
+#pragma unroll
+          for (int tp_ = 0; tp_ < 4; ++tp_) {
+            const uint32_t hw_[4] = {hh[tp_].x, hh[tp_].y, hh[tp_].z, hh[tp_].w}, lw_[4] = {ll[tp_].x, ll[tp_].y, ll[tp_].z, ll[tp_].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 v = p16::join2(hw_[u], lw_[u]);
+              r8[2 * u] = tp_ == 0 ? v.x * wts[0] : fmaf(v.x, wts[tp_], r8[2 * u]);
+              r8[2 * u + 1] = tp_ == 0 ? v.y * wts[0] : fmaf(v.y, wts[tp_], r8[2 * u + 1]);
+            }
+          }
+          g[2 * it] = make_float4(r8[0], r8[1], r8[2], r8[3]);
+          g[2 * it + 1] = make_float4(r8[4], r8[5], r8[6], r8[7]);
+        }
+        return;
+      }
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int e = it * 256 + ctid, p = e >> 4, q = e & 15;
@@ -212,15 +249,8 @@ k_stpn_head_tc(const __grid_constant__ CUtensorMap map_w1, const __grid_constant
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(qy) : "r"(s_py + 4u * p));
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qb) : "r"(s_pb + 4u * p));
         const mlp::Bilinear bl = mlp::bilinear_border(qx, qy, a.x_abs, a.y_abs, a.H, a.W);
-        float4 t00, t01, t10, t11;
-        if (a.fmt) {
-          const size_t fb = (size_t)qb * a.H * a.W;
-          t00 = p16::load4(a.mos_feats, fb + bl.o00, 64, 4 * q), t01 = p16::load4(a.mos_feats, fb + bl.o01, 64, 4 * q);
-          t10 = p16::load4(a.mos_feats, fb + bl.o10, 64, 4 * q), t11 = p16::load4(a.mos_feats, fb + bl.o11, 64, 4 * q);
-        } else {
-          const float4* b4 = reinterpret_cast<const float4*>(a.mos_feats + (size_t)qb * a.H * a.W * 64) + q;
-          t00 = b4[(size_t)bl.o00 * 16], t01 = b4[(size_t)bl.o01 * 16], t10 = b4[(size_t)bl.o10 * 16], t11 = b4[(size_t)bl.o11 * 16];
-        }
+        const float4* b4 = reinterpret_cast<const float4*>(a.mos_feats + (size_t)qb * a.H * a.W * 64) + q;
+        const float4 t00 = b4[(size_t)bl.o00 * 16], t01 = b4[(size_t)bl.o01 * 16], t10 = b4[(size_t)bl.o10 * 16], t11 = b4[(size_t)bl.o11 * 16];
         g[it].x = fmaf(t11.x, bl.w11, fmaf(t10.x, bl.w10, fmaf(t01.x, bl.w01, t00.x * bl.w00)));
         g[it].y = fmaf(t11.y, bl.w11, fmaf(t10.y, bl.w10, fmaf(t01.y, bl.w01, t00.y * bl.w00)));
         g[it].z = fmaf(t11.z, bl.w11, fmaf(t10.z, bl.w10, fmaf(t01.z, bl.w01, t00.z * bl.w00)));
@@ -236,8 +266,10 @@ k_stpn_head_tc(const __grid_constant__ CUtensorMap map_w1, const __grid_constant
         const int ctid = (int)threadIdx.x;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int e = it * 256 + ctid, p = e >> 4, q = e & 15;
-          put4(a_hi, a_lo, p, 64 + 4 * q, g[it].x, g[it].y, g[it].z, g[it].w);
+          // float32 map: item (point e >> 4, channels 4 * (e & 15)); P16 map: g[2j], g[2j+1] = item (point, channels 8 * q8 ..)
+          const int e = a.fmt ? (it >> 1) * 256 + ctid : it * 256 + ctid;
+          const int p = a.fmt ? e >> 3 : e >> 4, c = a.fmt ? 8 * (e & 7) + 4 * (it & 1) : 4 * (e & 15);
+          put4(a_hi, a_lo, p, 64 + c, g[it].x, g[it].y, g[it].z, g[it].w);
         }
       }
       // ---- positional encoding layer 0 (3 -> 32, ReLU) on the CUDA cores: this thread's 16 hidden channels -> A channels 16h ..

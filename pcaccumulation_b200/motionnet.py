@@ -199,6 +199,7 @@ class _ConvLayer:
         self.weight = w  # for the tensor-core pack (built lazily)
         self.tc_pack = None
         self.tc_pack16 = None
+        self.p16_pack = None  # K-dense fp16-pair pack of the P16 kernel (tc_pack.pack_conv_p16)
         self.tc_scale16 = None  # power-of-two scale of the fp16-pair weight pack (tc_pack.f16_weight_scale)
         self.tc_ok = {}  # (H, W, fmt) -> does the tensor-core kernel take this layer at that map size
 
@@ -474,13 +475,18 @@ class MotionNet(nn.Module):
             if tc_ok is None:
                 tc_ok = layer.tc_ok[(H, W_)] = bool(L.lib().pcab_conv3x3_tc_supported(
                     I(len(layer.splits)), I(c[0]), I(c[1]), I(c[2]), I(layer.cout), I(H), I(W_)))
-        if (fmt or (tc_ok and self.conv_operands == "f16")) and layer.tc_pack16 is None:
-            from .tc_pack import f16_weight_scale, pack_conv_tc_f16
+        if (fmt or (tc_ok and self.conv_operands == "f16")) and layer.tc_scale16 is None:
+            from .tc_pack import f16_weight_scale
             layer.tc_scale16 = f16_weight_scale(layer.weight)
+        if fmt and layer.p16_pack is None:
+            from .tc_pack import pack_conv_p16
+            layer.p16_pack = pack_conv_p16(layer, layer.tc_scale16)
+        if not fmt and tc_ok and self.conv_operands == "f16" and layer.tc_pack16 is None:
+            from .tc_pack import pack_conv_tc_f16
             layer.tc_pack16 = pack_conv_tc_f16(layer, layer.tc_scale16)
         if fmt:  # P16 activations in and out (csrc/conv_p16.cu)
             p0 = ctypes.c_void_p(s[0].data_ptr() + src0_off)
-            call("pcab_conv3x3_p16", p0, I(c[0]), I(src0_cstride), P(s[1]), I(c[1]), P(s[2]), I(c[2]), Tl, P(layer.tc_pack16),
+            call("pcab_conv3x3_p16", p0, I(c[0]), I(src0_cstride), P(s[1]), I(c[1]), P(s[2]), I(c[2]), Tl, P(layer.p16_pack),
                  F(1.0 / layer.tc_scale16), *tail, P(self._sat_counter(dev)), stream())
             path = "tc-p16"
         elif tc_ok and self.conv_operands == "f16":

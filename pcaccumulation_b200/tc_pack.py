@@ -68,12 +68,37 @@ def pack_conv_tc_f16(layer, scale=F16_WEIGHT_SCALE):
     return pack_rows_f16(layer.pack.view(k, layer.cout).t().contiguous(), scale)
 
 
+def pack_rows_f16_dense(rows, scale):
+    """rows [R][K] float32 (K % 32 == 0, already in the kernel's consumption order) -> fp16 [2 (h, l)][R][Kpad], Kpad = K rounded
+    up to a multiple of 64 (two 32-channel K groups per 128-byte row of the MMA B operand).  h = fp16(s*w), l = fp16(s*w - h)."""
+    r, k = rows.shape
+    kp = (k + 63) // 64 * 64
+    w = rows.float() * scale
+    h = w.half()
+    l = (w - h.float()).half()
+    out = torch.zeros(2, r, kp, dtype=torch.float16, device=rows.device)
+    out[0, :, :k] = h
+    out[1, :, :k] = l
+    return out.contiguous()
+
+
+def pack_conv_p16(layer, scale):
+    """Weight pack of ``pcab_conv3x3_p16``: rows = output channels; K in consumption order: per source, per 32-channel chunk,
+    per tap (ky*3+kx), 32 channels.  ``layer.pack`` holds per source [9][C_s][Cout]."""
+    cols, off = [], 0
+    for cs in layer.splits:
+        blk = layer.pack[off:off + 9 * cs * layer.cout].view(9, cs // 32, 32, layer.cout)
+        cols.append(blk.permute(1, 0, 2, 3).reshape(9 * cs, layer.cout))  # [chunk][tap][32] x Cout
+        off += 9 * cs * layer.cout
+    return pack_rows_f16_dense(torch.cat(cols, 0).t().contiguous(), scale)
+
+
 def pack_convT_p16(weight, scale):
     """ConvTranspose2d(2, stride 2) weight [Cin, Cout, 2, 2] for ``pcab_convT2x2_p16``: GEMM rows (output columns) =
     (dy*2+dx)*Cout + co, K = Cin."""
     cin, cout = weight.shape[:2]
     rows = weight.detach().float().permute(2, 3, 1, 0).reshape(4 * cout, cin).contiguous()
-    return pack_rows_f16(rows, scale)
+    return pack_rows_f16_dense(rows, scale)
 
 
 def unpack_p16(t):

@@ -897,7 +897,7 @@ def test_conv3x3_p16_against_float64(lib, case):
         ref = F.relu(ref)
     assert lib.lib().pcab_conv3x3_p16_supported(I(3 if T > 1 else len(cs)), I(c3[0]), I(c3[1]), I(c3[2]), I(cout), I(H), I(W))
     scale = tc_pack.f16_weight_scale(layer.weight)
-    pack = tc_pack.pack_conv_tc_f16(layer, scale)
+    pack = tc_pack.pack_conv_p16(layer, scale)
     out = torch.full((n, H, W, cout), float("nan"), device="cuda")
     sat = torch.zeros(1, dtype=torch.int32, device="cuda")
     scd, shd = sc.cuda(), sh.cuda()
@@ -926,7 +926,7 @@ def test_conv3x3_p16_saturation_is_counted(lib):
     out = torch.zeros(1, 16, 16, 32, device="cuda")
     sat = torch.zeros(1, dtype=torch.int32, device="cuda")
     xp = tc_pack.pack_p16(x).cuda()
-    pack = tc_pack.pack_conv_tc_f16(layer, scale)
+    pack = tc_pack.pack_conv_p16(layer, scale)
     call("pcab_conv3x3_p16", P(xp), I(32), I(0), P(None), I(0), P(None), I(0), I(1), P(pack), Fl(1.0 / scale), P(layer.bias), P(None),
          P(None), I(0), P(out), I(1), I(16), I(16), I(32), P(sat), stream())
     torch.cuda.synchronize()
@@ -935,7 +935,7 @@ def test_conv3x3_p16_saturation_is_counted(lib):
     # weights beyond 256 do not become inf in the pack
     big = mn._ConvLayer(types.SimpleNamespace(weight=(w * 2000).cuda(), bias=torch.zeros(32).cuda()))
     s2 = tc_pack.f16_weight_scale(big.weight)
-    assert s2 < 256.0 and bool(torch.isfinite(tc_pack.pack_conv_tc_f16(big, s2).float()).all())
+    assert s2 < 256.0 and bool(torch.isfinite(tc_pack.pack_conv_p16(big, s2).float()).all())
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 32, 9, 11), (1, 512, 256, 18, 18), (5, 64, 32, 144, 144), (1, 128, 128, 36, 36), (1, 256, 128, 10, 20)])
