@@ -95,6 +95,34 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "chamfer.npz"), xyz1=a.numpy(), xyz2=b.numpy(), dist1=d1.numpy(), dist2=d2.numpy(),
                         idx1=i1.numpy(), idx2=i2.numpy(), g1=g1.numpy(), g2=g2.numpy(), grad1=ga.numpy(), grad2=gb.numpy())
     print("chamfer golden written")
+    alignment_golden(ns)
+
+
+def alignment_golden(ns):
+    """tests/golden/alignment.npz: the reference's BaseModel.align_frames / get_alignment_errors (models/tpointnet.py:95-163)."""
+    import importlib
+
+    tp = importlib.import_module("models.tpointnet")
+    bm = tp.BaseModel(ref_loader.reference_config("waymo", "test", None))
+    g = np.random.default_rng(12)
+    n = 6000
+    pts = torch.tensor(g.uniform(-30, 30, (n, 3)).astype(np.float32))
+    t = torch.tensor(g.integers(0, 5, n))
+
+    def pose(a, tx, ty):
+        P = np.eye(4, dtype=np.float32)
+        c, s = np.cos(a), np.sin(a)
+        P[:2, :2] = [[c, -s], [s, c]]
+        P[0, 3], P[1, 3] = tx, ty
+        return P
+
+    est = torch.tensor(np.stack([pose(0.01 * i, 0.3 * i, 0.1 * i) for i in range(5)]))
+    gt = torch.tensor(np.stack([pose(0.011 * i, 0.31 * i, 0.09 * i) for i in range(5)]))
+    cd, l2 = bm.get_alignment_errors(pts, t, est, gt)
+    al = bm.align_frames(pts, t, est)
+    np.savez_compressed(os.path.join(GOLD, "alignment.npz"), points=pts.numpy(), time=t.numpy(), est=est.numpy(), gt=gt.numpy(),
+                        chamfer=np.array([float(cd)]), l2=np.array([float(l2)]), aligned=al.numpy())
+    print("alignment golden written", float(cd), float(l2))
 
 
 if __name__ == "__main__":

@@ -266,6 +266,8 @@ class MotionNet(nn.Module):
         # launches from Python per scene).  Their inputs are persistent buffers; their outputs are rewritten by the next forward.
         self.use_graphs = True
         self._graphs = {}
+        self.flop_acc = None  # when a dict: algorithmic FLOPs of the tensor-core launches per stack name (bench roofline)
+        self._flop_key = None
 
     # ------------------------------------------------------------------------------------------
     def _pack_key(self):
@@ -392,7 +394,17 @@ class MotionNet(nn.Module):
         is fragile), never implicitly."""
         slot = self._graphs[key]
         if slot.get("key") is not self._packed_key:  # first use, or a new weight pack drops the capture
+            if slot.get("graph") is not None:
+                import warnings
+
+                warnings.warn("pcaccumulation_b200: weights changed after warmup(); the captured CUDA graphs are dropped and "
+                              "the convolution stacks run kernel by kernel until warmup() is called again")
             slot.update(graph=None, out=None, key=self._packed_key)
+        if self.flop_acc is not None:  # accounting pass: eager, FLOPs of this stack's launches summed under its name
+            self._flop_key = key[0]
+            out = fn(slot["in"])
+            self._flop_key = None
+            return out
         if not (self.use_graphs and self.conv_events is None):
             return fn(slot["in"])
         if slot["graph"] is not None:
@@ -425,6 +437,23 @@ class MotionNet(nn.Module):
             del x
             return self._unet(W, "stpn.", xm, B, Ny, Nx, 5, False, fmt)
         return stpn_stack
+
+    def time_conv_stacks(self, reps=20):
+        """CUDA-event time (ms per replay) of the captured graphs of the two convolution stacks, replayed back to back on the
+        current stream over whatever their static inputs hold: the tensor-core convolutions with no host in the loop."""
+        out = {}
+        for key, slot in self._graphs.items():
+            if slot.get("graph") is None:
+                continue
+            slot["graph"].replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                slot["graph"].replay()
+            e1.record()
+            e1.synchronize()
+            out[key[0]] = e0.elapsed_time(e1) / reps
+        return out
 
     @torch.no_grad()
     def warmup(self, batch_size=1):
@@ -503,12 +532,20 @@ class MotionNet(nn.Module):
             call("pcab_conv3x3_f32", P(s[0]), I(c[0]), P(s[1]), I(c[1]), P(s[2]), I(c[2]), Tl, P(layer.pack), *tail,
                  I(layer.cout), I(0), stream())
             path = "f32"
-        if ev is not None:
-            e1.record()
+        if self.flop_acc is not None or ev is not None:
             if layer.temporal:
                 taps = 9 * layer.splits[0] * (3 * T - 2) * (n_img // T)
             else:
                 taps = 9 * sum(layer.splits) * n_img
+            if self.flop_acc is not None:
+                k = self._flop_key or "outside_graphs"
+                acc = self.flop_acc.setdefault(k, {"flops": 0.0, "launches": 0, "bytes": 0.0})
+                acc["flops"] += 2.0 * taps * layer.cout * H * W_
+                acc["launches"] += 1
+                cin_r = (sum(layer.splits) if not layer.temporal else layer.splits[0]) * n_img
+                acc["bytes"] += 4.0 * H * W_ * (cin_r + layer.cout * n_img) + 2.0 * 9 * sum(layer.splits) * layer.cout * 2
+        if ev is not None:
+            e1.record()
             cin_read = (sum(layer.splits) if not layer.temporal else layer.splits[0]) * n_img
             nbytes = 4.0 * H * W_ * (cin_read + layer.cout * n_img) + 4.0 * 9 * sum(layer.splits) * layer.cout
             ev.append((e0, e1, 2.0 * taps * layer.cout * H * W_, path, nbytes))
@@ -544,6 +581,11 @@ class MotionNet(nn.Module):
                 wp, sc = up_l[4]["p16"]
                 call("pcab_convT2x2_p16", P(x), I(cin), P(wp), F(1.0 / sc), P(bias), P(up), I(n_img), I(h), I(w), I(cout),
                      P(self._sat_counter(dev)), stream())
+                if self.flop_acc is not None:
+                    acc = self.flop_acc.setdefault(self._flop_key or "outside_graphs", {"flops": 0.0, "launches": 0, "bytes": 0.0})
+                    acc["flops"] += 2.0 * 4 * cin * cout * n_img * h * w
+                    acc["launches"] += 1
+                    acc["bytes"] += 4.0 * n_img * h * w * (cin + 4 * cout) + 2.0 * 4 * cin * cout * 2
             else:
                 call("pcab_convT2x2_f32", P(x), P(pack), P(bias), P(up), I(n_img), I(h), I(w), I(cin), I(cout), I(cout), I(0), stream())
             h, w = sh, sw

@@ -175,14 +175,14 @@ class ScenePipeline:
         torch.cuda.synchronize(self.device)
         self._pool = ThreadPoolExecutor(max_workers=self.depth, thread_name_prefix="pcab-scene")
 
-    def load_state_dict(self, state_dict):
+    def load_state_dict(self, state_dict, batch_size=1):
         """Load the weights into every slot and capture its CUDA graphs (single-threaded: the workers are idle)."""
         for r, stream in self._slots:
             r.model.load_state_dict(state_dict)
             with torch.cuda.stream(stream):
-                r.warmup()
+                r.warmup(batch_size)
 
-    def _work(self, points4, num_points, ego, seed, out, host):
+    def _work(self, points4, num_points, ego, seed, out, host, post=None):
         runner, stream = self._free.get()
         try:
             torch.cuda.set_device(self.device)
@@ -192,18 +192,24 @@ class ScenePipeline:
                 done = torch.cuda.Event()
                 if host:
                     res = runner.run_host(points4, num_points, ego_motion_gt_host=ego, out=out, copy_stream=runner.copy_stream)[0]
+                    if post is not None:  # the completion event then covers the post-processing on this stream too
+                        post(res)
+                        runner.copy_stream.wait_stream(stream)
                     done.record(runner.copy_stream)
                 else:
                     res = runner.run_device(points4, num_points, ego_motion_gt=ego)
+                    if post is not None:
+                        post(res)
                     done.record(stream)
             return res, done
         finally:
             self._free.put((runner, stream))
 
-    def submit(self, points4, num_points, ego=None, seed=None, out=None, host=False):
+    def submit(self, points4, num_points, ego=None, seed=None, out=None, host=False, post=None):
         """Queue one scene; returns a future of ``(results, cuda_event)``.  The results live on the slot's stream:
-        wait for the event (``event.synchronize()`` or ``stream.wait_event``) before reading them."""
-        return self._pool.submit(self._work, points4, num_points, ego, seed, out, host)
+        wait for the event (``event.synchronize()`` or ``stream.wait_event``) before reading them.  ``post(results)``: optional
+        callable run on the slot's thread and stream right after the forward (e.g. the Chamfer alignment errors)."""
+        return self._pool.submit(self._work, points4, num_points, ego, seed, out, host, post)
 
     def close(self):
         self._pool.shutdown(wait=True)

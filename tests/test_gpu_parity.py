@@ -443,6 +443,27 @@ def test_chamfer_vs_oracle_sizes_and_ties(n, m):
     assert np.array_equal(g1.cpu().numpy(), d1) and np.array_equal(g2.cpu().numpy(), d2)
 
 
+def test_alignment_errors_match_reference_golden():
+    """BaseModel.align_frames / get_chamfer_distance / get_alignment_errors (models/tpointnet.py:95-163) against outputs of the
+    UNMODIFIED reference (tests/golden/alignment.npz, oracle/make_golden.py:alignment_golden)."""
+    from pcaccumulation_b200 import config
+    from pcaccumulation_b200.alignment import BaseModel
+
+    g = np.load(os.path.join(GOLDEN, "alignment.npz"))
+    bm = BaseModel(config.workload_config("C1"))
+    pts, t = torch.tensor(g["points"]).cuda(), torch.tensor(g["time"]).cuda()
+    est, gt = torch.tensor(g["est"]).cuda(), torch.tensor(g["gt"]).cuda()
+    al = bm.align_frames(pts, t, est)
+    assert float((al.cpu() - torch.tensor(g["aligned"])).abs().max()) <= 4e-6
+    cd, l2 = bm.get_alignment_errors(pts, t, est, gt)
+    assert abs(float(cd) - float(g["chamfer"][0])) <= 1e-5 * float(g["chamfer"][0])
+    assert abs(float(l2) - float(g["l2"][0])) <= 1e-5 * float(g["l2"][0])
+    # gradient flows to the estimated poses' points through the Chamfer kernel
+    p = pts.clone().requires_grad_(True)
+    bm.get_chamfer_distance(p, bm.align_frames(pts, t, gt), torch.full((pts.shape[0],), 1.0 / pts.shape[0], device="cuda")).backward()
+    assert bool(torch.isfinite(p.grad).all()) and float(p.grad.abs().sum()) > 0
+
+
 def test_chamfer_nuscenes_sized_properties():
     """C3-sized clouds (350k x 350k): identical sets -> zero distance and identity argmin; symmetry under swap."""
     from pcaccumulation_b200.chamfer_distance import chamfer_with_indices
