@@ -279,8 +279,8 @@ class Arm:
             depth = len(self.out_bufs) // N_SCENES
             out = self.out_bufs[k * depth + (i // N_SCENES) % depth]
             return self.pipe.submit(self.host_pts[k], self.nums[k], ego=self.host_ego[k], seed=1000 + i, out=out, host=True,
-                                    post=self.post(k))
-        return self.pipe.submit(self.dev_pts[k], self.nums[k], ego=self.dev_ego[k], seed=1000 + i, post=self.post(k))
+                                    post=self.post(k), keep_results=False)
+        return self.pipe.submit(self.dev_pts[k], self.nums[k], ego=self.dev_ego[k], seed=1000 + i, post=self.post(k), keep_results=False)
 
     def serial(self, i):
         torch.manual_seed(1000 + i)

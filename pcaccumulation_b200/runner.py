@@ -182,7 +182,7 @@ class ScenePipeline:
             with torch.cuda.stream(stream):
                 r.warmup(batch_size)
 
-    def _work(self, points4, num_points, ego, seed, out, host, post=None):
+    def _work(self, points4, num_points, ego, seed, out, host, post=None, keep=True):
         runner, stream = self._free.get()
         try:
             torch.cuda.set_device(self.device)
@@ -201,15 +201,17 @@ class ScenePipeline:
                     if post is not None:
                         post(res)
                     done.record(stream)
-            return res, done
+            return (res if keep else None), done
         finally:
             self._free.put((runner, stream))
 
-    def submit(self, points4, num_points, ego=None, seed=None, out=None, host=False, post=None):
+    def submit(self, points4, num_points, ego=None, seed=None, out=None, host=False, post=None, keep_results=True):
         """Queue one scene; returns a future of ``(results, cuda_event)``.  The results live on the slot's stream:
         wait for the event (``event.synchronize()`` or ``stream.wait_event``) before reading them.  ``post(results)``: optional
-        callable run on the slot's thread and stream right after the forward (e.g. the Chamfer alignment errors)."""
-        return self._pool.submit(self._work, points4, num_points, ego, seed, out, host, post)
+        callable run on the slot's thread and stream right after the forward (e.g. the Chamfer alignment errors).
+        ``keep_results=False`` returns ``(None, event)``: the device tensors of the scene go back to the allocator at once
+        (a long queue of futures otherwise pins every scene's outputs)."""
+        return self._pool.submit(self._work, points4, num_points, ego, seed, out, host, post, keep_results)
 
     def close(self):
         self._pool.shutdown(wait=True)

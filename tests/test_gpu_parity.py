@@ -314,19 +314,31 @@ def test_forward_vs_reference_golden(fixture_weights, name, tc):
     sd = fixture_weights(cfg)
     model = make_model(cfg, sd, tc)
     _, r32 = run_protocol(model, cfg, sd, inp, 42, f"golden_{name}/{'tcgen05' if tc else 'fp32'}", cache_key=("golden", name))
-    # the float32 oracle run of THIS host against the reference's outputs made in the build container: two float32
-    # evaluations of the same function on different CPUs (BLAS / oneDNN kernels differ) -- held to the same rule as the
-    # CUDA path: within 1e-4, or no further from the float64 result than twice this host's own float32 run is
-    from oracle.protocol import _floor_cmp, oracle_runs
+    # The float32 oracle run of THIS host against the reference's outputs made in the build container: two float32 evaluations
+    # of the same function on different CPUs (BLAS / oneDNN kernels differ).  Each is within the float32 floor of the exact
+    # result -- the floor of the build container is stored in the golden (oracle/make_golden.py) -- so they are within two
+    # floors of each other (or within the 1e-4 bar).  Stages downstream of the pose start from the golden's own pose.
+    from oracle import oracle
 
-    _, _, _, r64 = oracle_runs(cfg, sd, inp, 42, ("golden", name))
     rec = REPORT.setdefault(f"golden_{name}/oracle_here_vs_reference", {})
+
+    def two_floors(k, here, scale_floor=2.0):
+        ref = torch.tensor(g["out_" + k]).double()
+        err, scale = float((here.double() - ref).abs().max()), max(1.0, float(ref.abs().max()))
+        tol = max(REL * scale, scale_floor * float(g["floor_" + k][0]))
+        rec[k] = {"err": err / scale, "tol": tol / scale}
+        assert err <= tol, (k, err, tol)
+
     for k in ("fb_est_per_points", "inst_labels_est", "inst_labels_adjusted"):
         mism = int((r32[k].numpy() != g["out_" + k]).sum())
         rec[k + "_mismatches"] = mism
         assert mism <= (64 if k == "fb_est_per_points" else 0.001 * r32[k].numel()), (k, mism)
-    for k in ("ego_motion_est", "transformed_points", "mos_est", "offset_est"):
-        _floor_cmp(k, torch.tensor(g["out_" + k]), r32[k], r64[k], rec)
+    for k in ("ego_motion_est", "transformed_points"):
+        two_floors(k, r32[k])
+    torch.manual_seed(42)
+    staged = oracle.OracleMotionNet(cfg, sd, inject={"ego_motion_est": torch.tensor(g["out_ego_motion_est"])}).forward(inp)
+    for k in ("mos_est", "offset_est"):
+        two_floors(k, staged[k])
 
 
 def test_forward_batch_of_two_matches_oracle(fixture_weights):
