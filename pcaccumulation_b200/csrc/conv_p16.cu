@@ -117,6 +117,10 @@ k_conv_p16(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   uint32_t tmem_cols = 32;
   while (tmem_cols < 4u * a.mt * C) tmem_cols <<= 1;  // 2 stages x mt tiles x [main C | corr C]
+  // Programmatic dependent launch: the next kernel of the stream may be scheduled now (its barrier / TMEM / descriptor
+  // set-up then overlaps this kernel's tail on SMs that are already idle); it waits for THIS grid to complete before it
+  // touches global memory (griddepcontrol.wait below does the same for us against our predecessor).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(bar_plane_full + 8 * i, 1), mbar_init(bar_plane_free + 8 * i, a.mt);
@@ -139,6 +143,7 @@ k_conv_p16(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the producer of our inputs (and of the buffers we overwrite) is done
 
   constexpr int HALO = (NT == 9) ? 1 : 0;
   const uint32_t box_bytes = (uint32_t)(a.R + 2 * HALO) * a.Wp * 128u;
@@ -522,7 +527,13 @@ int launch(const Cfg& cfg, const CUtensorMap* maps, const Args& a, cudaStream_t 
   PCAB_CUDA(pcab_set_max_smem(k_conv_p16<C, NT>, kMaxSmem, once));
   const int nsm = pcab_sm_count();
   const int grid = cfg.total < nsm ? cfg.total : nsm;
-  k_conv_p16<C, NT><<<grid, kThreads, cfg.smem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], a);
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid), lc.blockDim = dim3(kThreads), lc.dynamicSmemBytes = cfg.smem, lc.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr, lc.numAttrs = 1;
+  PCAB_CUDA(cudaLaunchKernelEx(&lc, k_conv_p16<C, NT>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], a));
   return PCAB_OK;
 }
 

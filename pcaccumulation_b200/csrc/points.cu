@@ -290,28 +290,64 @@ __global__ void k_tpn_regressor_input(const float* __restrict__ geo_emb, const f
   }
 }
 
-// generic small dense layer: one thread per (row, out)
-__global__ void k_linear_rows(const float* __restrict__ X, int R, int IN, int OUT, const float* __restrict__ W,
-                              const float* __restrict__ b, const float* __restrict__ scale,
-                              const float* __restrict__ shift, int relu, float* __restrict__ Y) {
-  long long total = (long long)R * OUT;
-  long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
-    int r = (int)(e / OUT), o = (int)(e % OUT);
-    const float* x = X + (size_t)r * IN;
-    float a = 0.f;
-    const float* w = W + o;
+// The three layers of the TubeNet regressor (512 -> 256 -> BN -> ReLU -> 128 -> BN -> ReLU -> 7) for RR rows per CTA in one
+// launch: the hidden rows stay in shared memory and every weight element is read once per CTA (coalesced over the output
+// index).  Each output is one rounding sequence: fmaf over ascending k from 0, + bias, BN fmaf, ReLU.
+constexpr int RR = 4;
+__global__ void __launch_bounds__(256) k_regressor(const float* __restrict__ X, int R, const float* __restrict__ W0,
+                                                   const float* __restrict__ b0, const float* __restrict__ s0,
+                                                   const float* __restrict__ t0, const float* __restrict__ W1,
+                                                   const float* __restrict__ b1, const float* __restrict__ s1,
+                                                   const float* __restrict__ t1, const float* __restrict__ W2,
+                                                   const float* __restrict__ b2, float* __restrict__ Y) {
+  __shared__ __align__(16) float sx[RR][512];
+  __shared__ __align__(16) float h0[RR][256];
+  __shared__ __align__(16) float h1[RR][128];
+  const int r0 = blockIdx.x * RR, tid = threadIdx.x;
+  for (int e = tid; e < RR * 128; e += 256) {
+    const int r = e >> 7, q = e & 127;
+    reinterpret_cast<float4*>(sx[r])[q] = r0 + r < R ? reinterpret_cast<const float4*>(X + (size_t)(r0 + r) * 512)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  {
+    float a[RR] = {};
+    const float* w = W0 + tid;
 #pragma unroll 1
-    for (int k0 = 0; k0 < IN; k0 += 16) {  // IN is a multiple of 16 for every layer of the regressor
-      float xv[16], wv[16];
+    for (int k0 = 0; k0 < 512; k0 += 16) {
+      float wv[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) xv[u] = x[k0 + u], wv[u] = w[(size_t)(k0 + u) * OUT];  // 32 independent loads in flight
+      for (int u = 0; u < 16; ++u) wv[u] = w[(size_t)(k0 + u) * 256];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) a = fmaf(xv[u], wv[u], a);
+      for (int u = 0; u < 16; ++u)
+#pragma unroll
+        for (int r = 0; r < RR; ++r) a[r] = fmaf(sx[r][k0 + u], wv[u], a[r]);
     }
-    a += b[o];
-    if (scale) a = fmaf(a, scale[o], shift[o]);
-    Y[e] = relu ? fmaxf(a, 0.f) : a;
+#pragma unroll
+    for (int r = 0; r < RR; ++r) h0[r][tid] = fmaxf(fmaf(a[r] + b0[tid], s0[tid], t0[tid]), 0.f);
+  }
+  __syncthreads();
+  if (tid < 128) {
+    float a[RR] = {};
+    const float* w = W1 + tid;
+#pragma unroll 1
+    for (int k0 = 0; k0 < 256; k0 += 16) {
+      float wv[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) wv[u] = w[(size_t)(k0 + u) * 128];
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+#pragma unroll
+        for (int r = 0; r < RR; ++r) a[r] = fmaf(h0[r][k0 + u], wv[u], a[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < RR; ++r) h1[r][tid] = fmaxf(fmaf(a[r] + b1[tid], s1[tid], t1[tid]), 0.f);
+  }
+  __syncthreads();
+  if (tid < RR * 7) {
+    const int r = tid / 7, o = tid % 7;
+    float a = 0.f;
+    for (int k = 0; k < 128; ++k) a = fmaf(h1[r][k], W2[k * 7 + o], a);
+    if (r0 + r < R) Y[(size_t)(r0 + r) * 7 + o] = a + b2[o];
   }
 }
 
@@ -659,10 +695,8 @@ extern "C" int pcab_tpn_iteration(const float* points, const int* inst, const in
   const float* t1 = s1 + 128;
   const float* W2 = t1 + 128;
   const float* b2 = W2 + 128 * 7;
-  k_linear_rows<<<grid_for((long long)kt * 256, 256), 256, 0, stream>>>(X, (int)kt, 512, 256, W0, b0, s0, t0, 1, H0);
-  k_linear_rows<<<grid_for((long long)kt * 128, 256), 256, 0, stream>>>(H0, (int)kt, 256, 128, W1, b1, s1, t1, 1, H1);
-  k_linear_rows<<<grid_for((long long)kt * 7, 256), 256, 0, stream>>>(H1, (int)kt, 128, 7, W2, b2, nullptr, nullptr, 0,
-                                                                      rep_out ? rep_out : rep);
+  (void)H0, (void)H1;  // (hidden rows of the regressor now stay in shared memory)
+  k_regressor<<<cdiv(kt, RR), 256, 0, stream>>>(X, (int)kt, W0, b0, s0, t0, W1, b1, s1, t1, W2, b2, rep_out ? rep_out : rep);
   k_tpn_pose<<<grid_for((long long)kt, 128), 128, 0, stream>>>(rep_out ? rep_out : rep, sums, (int)kt, T,
                                                                pose_centered_out, pose_out);
   PCAB_CHECK_LAUNCH("pcab_tpn_iteration");

@@ -102,32 +102,57 @@ __global__ void k_segment_starts(const int* __restrict__ keys_sorted, int n, int
 }
 
 // one thread per pillar, sequential in stream order -> bit-identical to a CPU scatter_add
-__global__ void k_pillar_stats(const float* __restrict__ xyz, const long long* __restrict__ fb_labels,
-                               const int* __restrict__ order, const int* __restrict__ pstart, int m,
-                               float* __restrict__ pillar_mean, int* __restrict__ fb_sub) {
-  int stride = gridDim.x * blockDim.x;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < m; p += stride) {
-    int s = pstart[p], e = pstart[p + 1];
+// 8 lanes per pillar: the lanes fetch eight points of the pillar at once (the gathers through `order` are what the time goes
+// into), lane 0 of the group then adds them in stream order from registers -- the same sequential rounding sequence as
+// a CPU scatter_add, so the means stay bit-identical to the reference's.
+__global__ void __launch_bounds__(256) k_pillar_stats(const float* __restrict__ xyz, const long long* __restrict__ fb_labels,
+                                                      const int* __restrict__ order, const int* __restrict__ pstart, int m,
+                                                      float* __restrict__ pillar_mean, int* __restrict__ fb_sub) {
+  const int sub = threadIdx.x & 7;
+  const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);
+  const int groups = (gridDim.x * blockDim.x) >> 3;
+  const int m8 = (m + 7) & ~7;  // (every lane of a warp runs the same number of iterations: the shuffles below are warp-wide)
+  for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; p < m8; p += groups) {
+    const bool live = p < m;
+    const int s = live ? pstart[p] : 0, e = live ? pstart[p + 1] : 0;
     float sx = 0.f, sy = 0.f, sz = 0.f;
     long long mx = 0;
     bool any = false;
-    for (int j = s; j < e; ++j) {
-      int i = order[j];
-      sx = __fadd_rn(sx, xyz[3 * i + 0]);
-      sy = __fadd_rn(sy, xyz[3 * i + 1]);
-      sz = __fadd_rn(sz, xyz[3 * i + 2]);
-      if (fb_labels) {
-        long long v = fb_labels[i];
-        mx = any ? (v > mx ? v : mx) : v;
+    const int iters = (e - s + 7) >> 3;
+    int max_iters = iters;
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) max_iters = max(max_iters, __shfl_xor_sync(0xffffffffu, max_iters, o));
+    for (int it = 0; it < max_iters; ++it) {
+      const int j = s + 8 * it + sub;
+      float x = 0.f, y = 0.f, z = 0.f;
+      long long v = 0;
+      if (j < e) {
+        const int i = order[j];
+        x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        if (fb_labels) v = fb_labels[i];
       }
-      any = true;
+      const int cnt = min(8, e - (s + 8 * it));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xk = __shfl_sync(0xffffffffu, x, (threadIdx.x & 24) + k), yk = __shfl_sync(0xffffffffu, y, (threadIdx.x & 24) + k),
+                    zk = __shfl_sync(0xffffffffu, z, (threadIdx.x & 24) + k);
+        const long long vk = __shfl_sync(0xffffffffu, v, (threadIdx.x & 24) + k);
+        if (k < cnt) {
+          sx = __fadd_rn(sx, xk), sy = __fadd_rn(sy, yk), sz = __fadd_rn(sz, zk);
+          mx = any ? (vk > mx ? vk : mx) : vk;
+          any = true;
+        }
+      }
     }
-    int cnt = e - s;
-    float c = (float)(cnt > 0 ? cnt : 1);
-    pillar_mean[3 * p + 0] = __fdiv_rn(sx, c);
-    pillar_mean[3 * p + 1] = __fdiv_rn(sy, c);
-    pillar_mean[3 * p + 2] = __fdiv_rn(sz, c);
-    if (fb_sub) fb_sub[p] = (int)mx;
+    (void)gmask;
+    if (live && sub == 0) {
+      const int cnt = e - s;
+      const float c = (float)(cnt > 0 ? cnt : 1);
+      pillar_mean[3 * p + 0] = __fdiv_rn(sx, c);
+      pillar_mean[3 * p + 1] = __fdiv_rn(sy, c);
+      pillar_mean[3 * p + 2] = __fdiv_rn(sz, c);
+      if (fb_sub) fb_sub[p] = (int)mx;
+    }
   }
 }
 
@@ -218,8 +243,8 @@ extern "C" int pcab_pillar_index(const int* p2v, int n_points, int n_pillars, in
 extern "C" int pcab_pillar_stats(const float* xyz, const long long* fb_labels, const int* order, const int* pstart,
                                  int n_pillars, float* pillar_mean, int* fb_sub, cudaStream_t stream) {
   const int B = 128;
-  k_pillar_stats<<<grid_for(n_pillars, B), B, 0, stream>>>(xyz, fb_labels, order, pstart, n_pillars, pillar_mean,
-                                                            fb_sub);
+  k_pillar_stats<<<grid_for((long long)n_pillars * 8, 256, 16), 256, 0, stream>>>(xyz, fb_labels, order, pstart, n_pillars,
+                                                                                 pillar_mean, fb_sub);
   PCAB_CHECK_LAUNCH("pcab_pillar_stats");
   return PCAB_OK;
 }
