@@ -63,6 +63,16 @@ int pcab_pillar_encode(const float* xyz, const int* point_time, const int* order
                        float* canvas_nhwc /* zero-filled by the caller */, int canvas_fmt, void* workspace,
                        size_t workspace_bytes, pcab_stream_t stream);
 
+/* the same encoder on the tensor cores (tcgen05, fp16-pair operands; csrc/pillar.cu:pfn_tc): w_tc = 3 stage blobs of fp16
+ * [fc_0 64x64 | [shortcut|fc_1] 2x64x64 | fc_pos 128x64 or fc_c 64x64 (+pad)] with rows = [h rows; l rows] (tc_pack.pack_pfn_tc),
+ * bias_tc = per stage b0[32] b1[32] bx[64] (device), scales_inv9 = per stage 1/scale of the three matrices (HOST) */
+int pcab_pillar_encode_tc(const float* xyz, const int* point_time, const int* order, const int* p2v, const int* coords_zyxt,
+                          const int* pillar_cell, const float* pillar_mean, const void* w_tc, const float* bias_tc,
+                          const float* scales_inv9 /* host */, int n_points, int n_pillars, const float* range6 /* host */,
+                          const float* voxel_size3 /* host */, int n_sweeps, float* pillar_feats /* [M,32] */,
+                          float* canvas_nhwc /* zero-filled by the caller */, int canvas_fmt, void* workspace,
+                          size_t workspace_bytes, pcab_stream_t stream);
+
 /* ---- convolutions: models/unet.py:11-113, models/stpn.py:13-22,80 ---------------------------------------- */
 /* FP32 CUDA-core path; sources accumulate into one output (concat / temporal 3x3x3) */
 int pcab_conv3x3_f32(const float* src0, int c0, const float* src1, int c1, const float* src2, int c2, int temporal_T,

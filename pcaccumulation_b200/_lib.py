@@ -44,7 +44,7 @@ SIZE_T_FUNCS = [
 SYMBOLS = [
     "pcab_last_error", "pcab_version", "pcab_voxelize_workspace", "pcab_voxelize", "pcab_pillar_index_workspace",
     "pcab_pillar_index", "pcab_pillar_stats", "pcab_pillar_cells", "pcab_pfn_pack_size",
-    "pcab_pillar_encode_workspace", "pcab_pillar_encode", "pcab_conv3x3_f32", "pcab_convT2x2_f32", "pcab_maxpool2x2",
+    "pcab_pillar_encode_workspace", "pcab_pillar_encode", "pcab_pillar_encode_tc", "pcab_conv3x3_f32", "pcab_convT2x2_f32", "pcab_maxpool2x2",
     "pcab_temporal_max", "pcab_conv3x3_tc_supported", "pcab_conv3x3_tc_plan", "pcab_conv3x3_tc_pack_floats", "pcab_conv3x3_tc", "pcab_conv3x3_tc_f16",
     "pcab_conv3x3_p16_supported", "pcab_conv_p16_plan", "pcab_conv3x3_p16", "pcab_convT2x2_p16",
     "pcab_head2_conv", "pcab_fb_per_point", "pcab_canvases", "pcab_warp_bev", "pcab_transform_points",

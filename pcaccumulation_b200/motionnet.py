@@ -249,6 +249,7 @@ class MotionNet(nn.Module):
         # producer writes (h, l) pairs, the convolutions read them straight into the MMA operand.  Values beyond +-65504 would
         # saturate: the producers count such events and forward() then repeats the scene with conv_operands = "tf32".
         self.packed_activations = True
+        self.pfn_tensor_cores = True  # pillar encoder on tcgen05 (fp16-pair operands) when use_tensor_cores
         self.merge_heads = True  # first convolutions of semseg_head / ego_feats_head as one 96-channel layer (P16 path)
         self._sat = None  # device counter of saturated P16 outputs
         self._p16_ok = {}
@@ -293,6 +294,9 @@ class MotionNet(nn.Module):
         parts += [_t(pe.fc_c.weight), _v(pe.fc_c.bias)]
         W["pfn"] = torch.cat(parts).contiguous()
         assert W["pfn"].numel() == L.lib().pcab_pfn_pack_size()
+        from .tc_pack import pack_pfn_tc
+        blob, bias_tc, inv = pack_pfn_tc(pe)
+        W["pfn_tc"] = (blob, bias_tc, host_floats(inv))
 
         def unet_layers(net, prefix, final):
             for i, d in enumerate(net.down_convs):
@@ -692,9 +696,15 @@ class MotionNet(nn.Module):
         canvas.zero_()
         pillar_feats = torch.empty(M, 32, device=dev)
         ws = scratch(size("pcab_pillar_encode_workspace", I(N), I(M)), dev)
-        call("pcab_pillar_encode", P(pts), P(ptime), P(order), P(p2v), P(pstart), P(coords_zyxt), P(pillar_cell),
-             P(pillar_mean), P(W["pfn"]), I(N), I(M), rng, vsz, I(self.n_sweeps), P(pillar_feats), P(canvas), I(fmt), P(ws),
-             Z(ws.numel()), stream())
+        if self.use_tensor_cores and self.pfn_tensor_cores:
+            blob, bias_tc, inv9 = W["pfn_tc"]
+            call("pcab_pillar_encode_tc", P(pts), P(ptime), P(order), P(p2v), P(coords_zyxt), P(pillar_cell), P(pillar_mean), P(blob),
+                 P(bias_tc), inv9, I(N), I(M), rng, vsz, I(self.n_sweeps), P(pillar_feats), P(canvas), I(fmt), P(ws), Z(ws.numel()),
+                 stream())
+        else:
+            call("pcab_pillar_encode", P(pts), P(ptime), P(order), P(p2v), P(pstart), P(coords_zyxt), P(pillar_cell),
+                 P(pillar_mean), P(W["pfn"]), I(N), I(M), rng, vsz, I(self.n_sweeps), P(pillar_feats), P(canvas), I(fmt), P(ws),
+                 Z(ws.numel()), stream())
         del ws
 
         self._mark("pillar_encoder")

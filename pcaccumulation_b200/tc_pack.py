@@ -115,3 +115,42 @@ def pack_p16(x):
     h = x.clamp(-65504.0, 65504.0).half()
     l = (x - h.float()).clamp(-65504.0, 65504.0).half()
     return torch.stack((h, l), -2).contiguous().view(*x.shape[:-2], 2 * c).view(torch.float32)
+
+
+def pack_pfn_tc(pe):
+    """Tensor-core packs of the pillar encoder (csrc/pillar.cu:pfn_tc) from the reference's ``PillarFeatureNet`` parameters
+    (models/pillar_encoder.py:59-95).  Returns (fp16 blob [3 stages][20480], float32 bias [3][128], 9 host floats 1/scale)."""
+    def hl(w, scale, rows, width=64):
+        """[out, in] float32 -> [h rows (rows); l rows (rows)] x width fp16 (zero padded)."""
+        out = torch.zeros(2, rows, width, dtype=torch.float16, device=w.device)
+        x = w.detach().float() * scale
+        h = x.half()
+        out[0, : w.shape[0], : w.shape[1]] = h
+        out[1, : w.shape[0], : w.shape[1]] = (x - h.float()).half()
+        return out.reshape(-1)
+
+    dev = pe.fc_pos.weight.device
+    blobs, biases, inv = [], [], []
+    for s, blk in enumerate(pe.blocks):
+        s0 = f16_weight_scale(blk.fc_0.weight)
+        s1 = min(f16_weight_scale(blk.shortcut.weight), f16_weight_scale(blk.fc_1.weight))
+        w0 = hl(blk.fc_0.weight, s0, 32)                                   # K groups 0, 1 of the block input
+        w1a = hl(blk.shortcut.weight, s1, 32)                              # stage 0 of [Ws | W1]: K groups 0, 1
+        w1b = hl(blk.fc_1.weight, s1, 32)                                  # stage 1: K group 2 (+ 32 zeros)
+        bx = torch.zeros(64, device=dev)
+        if s == 0:
+            sx = f16_weight_scale(pe.fc_pos.weight)
+            wx = hl(pe.fc_pos.weight, sx, 64)
+            bx = pe.fc_pos.bias.detach().float()
+        elif s == 2:
+            sx = f16_weight_scale(pe.fc_c.weight)
+            wx = torch.cat((hl(pe.fc_c.weight, sx, 32), torch.zeros(64 * 64, dtype=torch.float16, device=dev)))
+            bx[:32] = pe.fc_c.bias.detach().float()
+        else:
+            sx, wx = 1.0, torch.zeros(128 * 64, dtype=torch.float16, device=dev)
+        blobs.append(torch.cat((w0, w1a, w1b, wx)))
+        biases.append(torch.cat((blk.fc_0.bias.detach().float(), blk.fc_1.bias.detach().float(), bx)))
+        inv += [1.0 / s0, 1.0 / s1, 1.0 / sx]
+    blob = torch.stack(blobs).contiguous()
+    assert blob.shape == (3, 20480)
+    return blob, torch.stack(biases).contiguous(), inv
