@@ -308,11 +308,18 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the short C3 / C4 / C5 measurements of the default run")
     ap.add_argument("--no-tc", action="store_true", help="force the FP32 CUDA-core convolution path")
     ap.add_argument("--operands", default=None, choices=["f16", "tf32"], help="operand format of the tensor-core convolutions")
-    ap.add_argument("--in-flight", type=int, default=4, help="independent scenes kept in flight per GPU (1 = serial)")
+    ap.add_argument("--in-flight", type=int, default=0,
+                    help="independent scenes kept in flight per GPU (1 = serial; 0 = auto: 4, or 3 when the rank has fewer than 6 host cores)")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.in_flight <= 0:
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        args.in_flight = 4 if cores // max(1, env_int("LOCAL_WORLD_SIZE", world)) >= 6 else 3
     if args.warmup < 3:
         print(f"bench.py: --warmup {args.warmup} raised to 3 (timing rules)", file=sys.stderr)
         args.warmup = 3

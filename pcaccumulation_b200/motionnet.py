@@ -609,6 +609,29 @@ class MotionNet(nn.Module):
             e.record()
             self.stage_marks.append((name, e))
 
+    def _select_async(self, n, dev, flags=None, values=None, value=0):
+        """Like ``_select`` but the count travels to a pinned host buffer asynchronously: returns (idx buffer, wait) where
+        ``wait()`` blocks until the count has arrived and returns (idx[:k], k).  Issued early, the wait is free."""
+        idx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        if n > 0:
+            ws = scratch(size("pcab_select_workspace", I(n)), dev)
+            call("pcab_select_indices", P(flags), P(values), L.L(value), I(n), P(idx), P(cnt), P(ws), Z(ws.numel()), stream())
+        if getattr(self, "_pin_ints", None) is None:  # pinned staging for small readbacks (allocated once: cudaHostAlloc is slow)
+            self._pin_ints, self._pin_next = torch.empty(16, dtype=torch.int32).pin_memory(), 0
+        host = self._pin_ints[self._pin_next:self._pin_next + 1]
+        self._pin_next = (self._pin_next + 1) % 16
+        host.copy_(cnt, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+
+        def wait():
+            ev.synchronize()
+            k = int(host[0])
+            return idx[:k], k
+
+        return wait
+
     def _select(self, n, dev, flags=None, values=None, value=0):
         idx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -723,6 +746,12 @@ class MotionNet(nn.Module):
         call("pcab_fb_per_point", P(fb_est), P(pillar_cell), P(p2v), I(N), P(fb_pp), stream())
         results["fb_seg_est"] = fb_seg
         results["fb_est_per_points"] = fb_pp
+        # foreground selection (models/motionnet.py:213-221): issued now, its count is read after the STPN stack is queued
+        if self.mode in ("train", "val"):
+            fg_flags = ((fb64 == 1) | (fb_pp[:, 0] == 1)).to(torch.int32)
+            fg_wait = self._select_async(N, dev, flags=fg_flags)
+        else:
+            fg_wait = self._select_async(N, dev, values=fb_pp, value=1)
 
         self._mark("fb_head")
         # 4. ego-motion: the background-pillar counts start their trip to the host before the head convolutions are
@@ -752,17 +781,22 @@ class MotionNet(nn.Module):
         call("pcab_transform_points", P(pts), P(pframe), P(pose_est), I(N), P(tp), stream())
         results["transformed_points"] = tp
 
-        if self.mode in ("train", "val"):
-            fg_flags = ((fb64 == 1) | (fb_pp[:, 0] == 1)).to(torch.int32)
-            fg_idx, n_fg = self._select(N, dev, flags=fg_flags)
-        else:
-            fg_idx, n_fg = self._select(N, dev, values=fb_pp, value=1)
         full_mos = torch.empty(N, 2, device=dev)
         full_off = torch.empty(N, 2, device=dev)
         call("pcab_init_point_outputs", I(N), P(full_mos), P(full_off), stream())
-        mos_feats = None
-        if n_fg > MIN_POINTS:
-            mos_feats = self._run_stack(("stpn", B, T, Ny, Nx, tc), self._stpn_stack(W, B, T, Ny, Nx, dev, fmt))
+        # The Conv3d + STPN-UNet stack does not depend on WHICH points are foreground, only the guard `count > MIN_POINTS`
+        # (models/motionnet.py:222) does: with a captured graph it is queued before the count is read (the readback then
+        # costs nothing); its output is dropped in the rare scene that fails the guard.
+        stack_key = ("stpn", B, T, Ny, Nx, tc)
+        early = self.use_graphs and self.conv_events is None and self.flop_acc is None and \
+            self._graphs.get(stack_key, {}).get("graph") is not None and self._graphs[stack_key].get("key") is self._packed_key
+        mos_feats = self._run_stack(stack_key, self._stpn_stack(W, B, T, Ny, Nx, dev, fmt)) if early else None
+        fg_idx, n_fg = fg_wait()
+        if n_fg <= MIN_POINTS:
+            mos_feats = None
+        else:
+            if not early:
+                mos_feats = self._run_stack(stack_key, self._stpn_stack(W, B, T, Ny, Nx, dev, fmt))
             if self.use_tensor_cores:
                 call("pcab_stpn_head_tc", P(mos_feats), I(fmt), I(Ny), I(Nx), P(tp), P(pbatch), P(fg_idx), I(n_fg), P(W["stpn_head_host"]),
                      P(W["stpn_head_tc1"]), P(W["stpn_head_tc"]), F(x_abs), F(y_abs), P(full_mos), P(full_off), stream())
