@@ -115,6 +115,10 @@ int pcab_conv3x3_p16(const void* src0, int c0, int src0_cstride, const void* src
                      int temporal_T, const void* weight_f16_packed, float weight_scale_inv, const float* bias,
                      const float* bn_scale, const float* bn_shift, int relu, void* out, int n_images, int H, int W, int Cout,
                      unsigned int* sat_counter, pcab_stream_t stream);
+/* Conv3d 3x3x3 (32 -> 32 channels; models/stpn.py:13-22) with the temporal taps fused into the MMA N dimension: every input
+ * frame is staged once and feeds output frames f-1, f, f+1; weights fp16 [2][96 = (kt 2,1,0) x 32][320] (tc_pack.pack_conv3d_fused_p16) */
+int pcab_conv3d_p16(const void* src, int T, const void* weight_f16_packed, float weight_scale_inv, const float* bias, int relu,
+                    void* out, int n_images /* B*T */, int H, int W, unsigned int* sat_counter, pcab_stream_t stream);
 int pcab_convT2x2_p16(const void* in, int Cin, const void* weight_f16_packed, float weight_scale_inv, const float* bias,
                       void* out /* [n,2H,2W,Cout] P16 */, int n_images, int H, int W, int Cout, unsigned int* sat_counter,
                       pcab_stream_t stream);

@@ -46,7 +46,7 @@ SYMBOLS = [
     "pcab_pillar_index", "pcab_pillar_stats", "pcab_pillar_cells", "pcab_pfn_pack_size",
     "pcab_pillar_encode_workspace", "pcab_pillar_encode", "pcab_pillar_encode_tc", "pcab_conv3x3_f32", "pcab_convT2x2_f32", "pcab_maxpool2x2",
     "pcab_temporal_max", "pcab_conv3x3_tc_supported", "pcab_conv3x3_tc_plan", "pcab_conv3x3_tc_pack_floats", "pcab_conv3x3_tc", "pcab_conv3x3_tc_f16",
-    "pcab_conv3x3_p16_supported", "pcab_conv_p16_plan", "pcab_conv3x3_p16", "pcab_convT2x2_p16",
+    "pcab_conv3x3_p16_supported", "pcab_conv_p16_plan", "pcab_conv3x3_p16", "pcab_conv3d_p16", "pcab_convT2x2_p16",
     "pcab_head2_conv", "pcab_fb_per_point", "pcab_canvases", "pcab_warp_bev", "pcab_transform_points",
     "pcab_bg_compact_workspace", "pcab_bg_compact", "pcab_ego_pairs_workspace", "pcab_ego_pairs",
     "pcab_select_workspace", "pcab_select_indices", "pcab_ungrid", "pcab_stpn_head_pack_size",

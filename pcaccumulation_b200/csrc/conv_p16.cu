@@ -408,6 +408,245 @@ k_conv_p16(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   }
 }
 
+// =====================================================================================================================
+// Conv3d 3x3x3 (32 -> 32 channels, models/stpn.py:13-22) with the TEMPORAL taps fused into the MMA N dimension.
+// The generic kernel runs a Conv3d as three 2-D K-slices per output frame: every input plane is staged and streamed
+// through the tensor core three times with N = 64 + 32, where the MMAs are bound by the shared-memory reads of A.
+// Here a CTA owns a 128-pixel tile of ONE scene for all T frames: input frame f is staged once and multiplied against
+// [W(kt=2); W(kt=1); W(kt=0)] (N = 96), i.e. it contributes to output frames f-1, f, f+1 at once.  The accumulators of the
+// output frames form two rings of eight 32-column blocks in TMEM (main sums at columns 0..255, correction sums at
+// 256..511; output frame g lives in block (g+1) % 8), the three products are three N = 96 MMAs on a 96-column window
+// of those rings (split in two at the ring wrap), and an output frame is drained, stored and its block zeroed again as soon
+// as the input frame after it has been consumed.  A read per algorithmic MAC drops 3x, the MMAs come close to math bound.
+// Warp roles (512 threads): 0-7 drain + epilogue | 12 plane TMA | 13 weights (once) | 14 MMA issue.
+// =====================================================================================================================
+struct Args3d {
+  int B, T, H, W;
+  int tiles_x, tiles_y, total_items;
+  int np;
+  uint32_t plane_bytes;
+  int relu;
+  float wscale_inv;
+  const float* bias;
+  unsigned int* sat_counter;
+};
+
+constexpr uint32_t kW3dStage = 192u * 128u;  // one pair of taps: [w_h rows of kt = 2, 1, 0 | w_l rows of kt = 2, 1, 0] x 128 B
+constexpr int kW3dStages = 5;                // nine taps, two per 128-byte row
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv3d_p16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+             const __grid_constant__ CUtensorMap map_o, Args3d a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w0 = sbase + (uint32_t)a.np * a.plane_bytes;
+  const uint32_t stg0 = w0 + kW3dStages * kW3dStage;
+  const uint32_t bars = stg0 + 16384u;
+  const uint32_t bar_plane_full = bars, bar_plane_free = bars + 32, bar_w_full = bars + 64, bar_fd = bars + 72, bar_fc = bars + 88,
+                 tmem_slot = bars + 104;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(bar_plane_full + 8 * i, 1), mbar_init(bar_plane_free + 8 * i, 1);
+    mbar_init(bar_w_full, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_fd + 8 * i, 1), mbar_init(bar_fc + 8 * i, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 14) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 12 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_o)) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+  // every accumulator block starts at zero (all MMAs accumulate): the epilogue warps clear the 512 columns once
+  if (warp < 8) {
+    const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 256u;
+#pragma unroll 1
+    for (int c = 0; c < 256; c += 16)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(t0 + c), "r"(0u) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  constexpr int Wp = 10, R = 16;  // strip tile: 8 x 16 output pixels, halo plane 10 x 18
+  const uint32_t box_bytes = 18u * Wp * 128u;
+  auto item_of = [&](int it, int& b, int& x0, int& y0) {
+    const int tx = it % a.tiles_x, ty = (it / a.tiles_x) % a.tiles_y;
+    b = it / (a.tiles_x * a.tiles_y), x0 = tx * 8, y0 = ty * R;
+  };
+
+  if (warp == 12) {
+    // ===================== plane producer: one halo plane per input frame =====================
+    if (lane == 0) {
+      int g = 0;
+      for (int it = blockIdx.x; it < a.total_items; it += gridDim.x) {
+        int b, x0, y0;
+        item_of(it, b, x0, y0);
+        for (int f = 0; f < a.T; ++f, ++g) {
+          const int ps = g % a.np;
+          if (g >= a.np) mbar_wait(bar_plane_free + 8 * ps, (uint32_t)((g / a.np) - 1) & 1u);
+          mbar_expect_tx(bar_plane_full + 8 * ps, box_bytes);
+          tma_load_4d(&map_a, sbase + (uint32_t)ps * a.plane_bytes, bar_plane_full + 8 * ps, 0, x0 - 1, y0 - 1, b * a.T + f);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 13) {
+    // ===================== weights: resident for the life of the CTA =====================
+    if (lane == 0) {
+      mbar_expect_tx(bar_w_full, kW3dStages * kW3dStage);
+      for (int j = 0; j < kW3dStages; ++j) tma_load_2d(&map_b, w0 + (uint32_t)j * kW3dStage, bar_w_full, 64 * j, 0);
+    }
+    __syncwarp();
+  } else if (warp == 14) {
+    // ===================== MMA issue =====================
+    const bool leader = elect_one();
+    const uint32_t idesc_base = (1u << 4) | ((128u >> 4) << 24);  // D = F32, A = B = F16, K-major both, M = 128
+    auto idesc = [&](uint32_t n) { return idesc_base | ((n >> 3) << 17); };
+    const uint64_t desc_hi_a = (uint64_t)((uint32_t)Wp * 8u | (1u << 14) | (2u << 29)) << 32;  // strip: 8-row groups are image rows
+    const uint64_t desc_hi_b = (uint64_t)(64u | (1u << 14) | (2u << 29)) << 32;
+    const uint32_t lbo = 1u << 16;
+    const uint32_t a_base = lbo | ((sbase & 0x3FFFF) >> 4);
+    const uint32_t b_base = lbo | ((w0 & 0x3FFFF) >> 4);
+    mbar_wait(bar_w_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    int F = 0;  // global frame counter of this CTA
+    for (int it = blockIdx.x; it < a.total_items; it += gridDim.x) {
+      for (int f = 0; f < a.T; ++f, ++F) {
+        const int ps = F % a.np, sl = F & 1;
+        mbar_wait(bar_plane_full + 8 * ps, (uint32_t)(F / a.np) & 1u);
+        // back-pressure: the epilogue has finished the duties of frame F-2 (of F-1 at the start of an item: the previous
+        // item's last output blocks are drained and cleared before any of them is accumulated into again)
+        if (F >= 2) mbar_wait(bar_fc + 8 * sl, (uint32_t)((F >> 1) - 1) & 1u);
+        if (f == 0 && F >= 1) mbar_wait(bar_fc + 8 * (sl ^ 1), (uint32_t)((F - 1) >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ap = a_base + (uint32_t)ps * (a.plane_bytes >> 4);
+        const int j0 = f & 7;  // ring block of output frame f-1; the window is blocks j0, j0+1, j0+2 (mod 8)
+        if (leader) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t shift16 = (uint32_t)(tap / 3) * (Wp * 8u) + (uint32_t)(tap % 3) * 8u;
+            const uint32_t bst = b_base + (uint32_t)(tap >> 1) * (kW3dStage >> 4) + (uint32_t)(tap & 1) * 4u;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t dah = desc_hi_a | (ap + shift16 + 2u * kk), dal = desc_hi_a | (ap + shift16 + 4u + 2u * kk);
+              // B rows: [0, 96) = w_h of kt = 2, 1, 0 ; [96, 192) = w_l of kt = 2, 1, 0  (128 B per row: 8 x 16 B)
+              const uint32_t bh = bst + 2u * kk, bl = bst + 96u * 8u + 2u * kk;
+              auto three = [&](uint32_t col, uint32_t row_off, uint32_t n) {
+                const uint32_t ro = row_off * 8u;
+                umma_f16(tmem_base + col, dah, desc_hi_b | (bh + ro), idesc(n), 1u);          // main ring  += a_h . w_h
+                umma_f16(tmem_base + 256u + col, dah, desc_hi_b | (bl + ro), idesc(n), 1u);   // corr ring  += a_h . w_l
+                umma_f16(tmem_base + 256u + col, dal, desc_hi_b | (bh + ro), idesc(n), 1u);   // corr ring  += a_l . w_h
+              };
+              if (j0 <= 5) {
+                three(32u * j0, 0u, 96u);
+              } else if (j0 == 6) {
+                three(192u, 0u, 64u);
+                three(0u, 64u, 32u);
+              } else {
+                three(224u, 0u, 32u);
+                three(0u, 32u, 64u);
+              }
+            }
+          }
+          umma_commit(bar_plane_free + 8 * ps);
+          umma_commit(bar_fd + 8 * sl);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== drain + epilogue =====================
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int m = quarter * 32 + lane;
+    const uint32_t srow = (uint32_t)m, sw = srow & 7u;  // strip tile: staging row = TMEM lane ((m >> 3) * 8 + (m & 7))
+    bool stored = false, sat = false;
+    int F = 0;
+    auto clear_block = [&](int j) {
+      const uint32_t t = tmem_base + lane_addr + 32u * j + 16u * half;
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(t), "r"(0u) : "memory");
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(t + 256u), "r"(0u) : "memory");
+    };
+    for (int it = blockIdx.x; it < a.total_items; it += gridDim.x) {
+      int b, x0, y0;
+      item_of(it, b, x0, y0);
+      auto finalize = [&](int g) {  // output frame g is complete: bias / ReLU -> pairs -> staging -> TMA store; clear its block
+        const int j = (g + 1) & 7;
+        uint32_t vm[16], vc[16];
+        tmem_ld16(tmem_base + lane_addr + 32u * j + 16u * half, vm);
+        tmem_ld16(tmem_base + lane_addr + 256u + 32u * j + 16u * half, vc);
+        tmem_ld_wait16(vm, vc);
+        clear_block(j);
+        if (threadIdx.x == 0 && stored) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int cb = 16 * half + 8 * q;
+          float o[8];
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + cb)), b1 = __ldg(reinterpret_cast<const float4*>(a.bias + cb + 4));
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            o[u] = fmaf(__uint_as_float(vm[8 * q + u]) + __uint_as_float(vc[8 * q + u]), a.wscale_inv, bb[u]);
+            if (a.relu) o[u] = fmaxf(o[u], 0.f);
+            sat |= !(fabsf(o[u]) <= 65504.f);
+          }
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) p16::split2(o[2 * u], o[2 * u + 1], h[u], l[u]);
+          const uint32_t row_addr = stg0 + srow * 128u, ch = (uint32_t)cb >> 3;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((ch ^ sw) << 4)), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + (((4u + ch) ^ sw) << 4)), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (threadIdx.x == 0) {
+          tma_store_4d(&map_o, stg0, 0, x0, y0, b * a.T + g);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          stored = true;
+        }
+      };
+      for (int f = 0; f < a.T; ++f, ++F) {
+        const int sl = F & 1;
+        mbar_wait(bar_fd + 8 * sl, (uint32_t)(F >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (f == 0)
+          clear_block(0);  // the block of "output frame -1" only collected the kt = 2 products of frame 0
+        else
+          finalize(f - 1);
+        if (f == a.T - 1) {
+          finalize(a.T - 1);
+          clear_block((a.T + 1) & 7);  // "output frame T"
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(bar_fc + 8 * sl);
+      }
+    }
+    if (sat && a.sat_counter) atomicAdd(a.sat_counter, 1u);
+    if (threadIdx.x == 0 && stored) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 14) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // --------------------------------------------------------------------------------------------------------------------
 // host side: tile plan, tensor maps, launch
 // --------------------------------------------------------------------------------------------------------------------
@@ -653,6 +892,53 @@ extern "C" int pcab_conv3x3_p16(const void* src0, int c0, int src0_cstride, cons
                                 unsigned int* sat_counter, cudaStream_t stream) {
   return run(src0, c0, src0_cstride, src1, c1, src2, c2, temporal_T, weight_f16_packed, weight_scale_inv, bias, bn_scale, bn_shift, relu,
              out, n_images, H, W, Cout, 9, sat_counter, stream);
+}
+
+// Conv3d 3x3x3, 32 -> 32 channels, temporal taps fused into the MMA N dimension (k_conv3d_p16).  weight: fp16 [2 (h, l)][96 rows =
+// (kt = 2, 1, 0) x 32 output channels][320] (nine taps x 32 input channels, K dense, padded to 320; tc_pack.pack_conv3d_fused_p16).
+extern "C" int pcab_conv3d_p16(const void* src, int T, const void* weight_f16_packed, float weight_scale_inv, const float* bias, int relu,
+                               void* out, int n_images, int H, int W, unsigned int* sat_counter, cudaStream_t stream) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    pcab_set_error("pcab_conv3d_p16: cuTensorMapEncodeTiled unavailable");
+    return PCAB_ERR_CUDA;
+  }
+  PCAB_REQUIRE(T >= 2 && n_images % T == 0 && H >= 8 && W >= 8, "n_images = B * T, T >= 2, maps of at least 8 x 8");
+  PCAB_REQUIRE(((uintptr_t)src & 127) == 0 && ((uintptr_t)out & 127) == 0 && ((uintptr_t)bias & 15) == 0, "alignment");
+  CUtensorMap ma, mb, mo;
+  if (!encode_act(enc, &ma, src, 32, 32, W, H, n_images, 10, 18) || !encode_act(enc, &mo, out, 32, 32, W, H, n_images, 8, 16)) {
+    pcab_set_error("pcab_conv3d_p16: cuTensorMapEncodeTiled(activations) failed");
+    return PCAB_ERR_CUDA;
+  }
+  {
+    cuuint64_t dims[2] = {320, 192};
+    cuuint64_t strides[1] = {640};
+    cuuint32_t box[2] = {64u, 192u};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)weight_f16_packed, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      pcab_set_error("pcab_conv3d_p16: cuTensorMapEncodeTiled(B) failed");
+      return PCAB_ERR_CUDA;
+    }
+  }
+  Args3d a;
+  a.B = n_images / T, a.T = T, a.H = H, a.W = W;
+  a.tiles_x = cdiv(W, 8), a.tiles_y = cdiv(H, 16), a.total_items = a.B * a.tiles_x * a.tiles_y;
+  a.np = 3, a.plane_bytes = 184u * 128u;
+  a.relu = relu, a.wscale_inv = weight_scale_inv, a.bias = bias, a.sat_counter = sat_counter;
+  const size_t smem = 1024 + (size_t)a.np * a.plane_bytes + (size_t)kW3dStages * kW3dStage + 16384 + 256;
+  static PcabSmemOnce once;
+  PCAB_CUDA(pcab_set_max_smem(k_conv3d_p16, (int)smem, once));
+  const int nsm = pcab_sm_count();
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(a.total_items < nsm ? a.total_items : nsm), lc.blockDim = dim3(kThreads), lc.dynamicSmemBytes = smem, lc.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr, lc.numAttrs = 1;
+  PCAB_CUDA(cudaLaunchKernelEx(&lc, k_conv3d_p16, ma, mb, mo, a));
+  PCAB_CHECK_LAUNCH("pcab_conv3d_p16");
+  return PCAB_OK;
 }
 
 extern "C" int pcab_convT2x2_p16(const void* in, int Cin, const void* weight_f16_packed, float weight_scale_inv, const float* bias,

@@ -200,6 +200,7 @@ class _ConvLayer:
         self.tc_pack = None
         self.tc_pack16 = None
         self.p16_pack = None  # K-dense fp16-pair pack of the P16 kernel (tc_pack.pack_conv_p16)
+        self.p16_pack3d = None  # Conv3d with fused temporal taps (tc_pack.pack_conv3d_fused_p16)
         self.tc_scale16 = None  # power-of-two scale of the fp16-pair weight pack (tc_pack.f16_weight_scale)
         self.tc_ok = {}  # (H, W, fmt) -> does the tensor-core kernel take this layer at that map size
 
@@ -249,6 +250,7 @@ class MotionNet(nn.Module):
         # producer writes (h, l) pairs, the convolutions read them straight into the MMA operand.  Values beyond +-65504 would
         # saturate: the producers count such events and forward() then repeats the scene with conv_operands = "tf32".
         self.packed_activations = True
+        self.fuse_conv3d = True  # Conv3d 3x3x3 with the temporal taps in the MMA N dimension (P16 path)
         self.pfn_tensor_cores = True  # pillar encoder on tcgen05 (fp16-pair operands) when use_tensor_cores
         self.merge_heads = True  # first convolutions of semseg_head / ego_feats_head as one 96-channel layer (P16 path)
         self._sat = None  # device counter of saturated P16 outputs
@@ -474,7 +476,7 @@ class MotionNet(nn.Module):
         Ny = int(round((vg["range"][4] - vg["range"][1]) / vg["voxel_size"][1]))
         B, T = int(batch_size), self.n_sweeps
         fmt = self._fmt(B, T, Ny, Nx)
-        tc = (self.use_tensor_cores, self.conv_operands, fmt, self.merge_heads)
+        tc = (self.use_tensor_cores, self.conv_operands, fmt, self.merge_heads, self.fuse_conv3d)
         with L.pinned_stream():
             W = self._weights()
             self._sat_counter(dev)
@@ -511,13 +513,21 @@ class MotionNet(nn.Module):
         if (fmt or (tc_ok and self.conv_operands == "f16")) and layer.tc_scale16 is None:
             from .tc_pack import f16_weight_scale
             layer.tc_scale16 = f16_weight_scale(layer.weight)
-        if fmt and layer.p16_pack is None:
+        if fmt and layer.p16_pack is None and not (layer.temporal and self.fuse_conv3d and layer.cout == 32 and layer.splits[0] == 32):
             from .tc_pack import pack_conv_p16
             layer.p16_pack = pack_conv_p16(layer, layer.tc_scale16)
         if not fmt and tc_ok and self.conv_operands == "f16" and layer.tc_pack16 is None:
             from .tc_pack import pack_conv_tc_f16
             layer.tc_pack16 = pack_conv_tc_f16(layer, layer.tc_scale16)
-        if fmt:  # P16 activations in and out (csrc/conv_p16.cu)
+        if fmt and layer.temporal and self.fuse_conv3d and layer.cout == 32 and layer.splits[0] == 32:
+            # Conv3d with the temporal taps fused into the MMA N dimension (one pass over every input frame)
+            if layer.p16_pack3d is None:
+                from .tc_pack import pack_conv3d_fused_p16
+                layer.p16_pack3d = pack_conv3d_fused_p16(layer.weight, layer.tc_scale16)
+            call("pcab_conv3d_p16", P(s[0]), I(T), P(layer.p16_pack3d), F(1.0 / layer.tc_scale16), P(layer.bias), I(int(relu)), P(out),
+                 I(n_img), I(H), I(W_), P(self._sat_counter(dev)), stream())
+            path = "tc-p16"
+        elif fmt:  # P16 activations in and out (csrc/conv_p16.cu)
             p0 = ctypes.c_void_p(s[0].data_ptr() + src0_off)
             call("pcab_conv3x3_p16", p0, I(c[0]), I(src0_cstride), P(s[1]), I(c[1]), P(s[2]), I(c[2]), Tl, P(layer.p16_pack),
                  F(1.0 / layer.tc_scale16), *tail, P(self._sat_counter(dev)), stream())
@@ -711,7 +721,7 @@ class MotionNet(nn.Module):
         # 1. pillar encoder -> BEV canvas
         fmt = self._fmt(B, T, Ny, Nx)  # activation format of the BEV tensors: 1 = P16 pairs, 0 = float32
         merged = bool(fmt and self.merge_heads)
-        tc = (self.use_tensor_cores, self.conv_operands, fmt, self.merge_heads)  # part of the graph key: a capture replays the kernels it recorded
+        tc = (self.use_tensor_cores, self.conv_operands, fmt, self.merge_heads, self.fuse_conv3d)  # part of the graph key: a capture replays the kernels it recorded
         sat = self._sat_counter(dev)
         if fmt:
             sat.zero_()

@@ -93,6 +93,16 @@ def pack_conv_p16(layer, scale):
     return pack_rows_f16_dense(torch.cat(cols, 0).t().contiguous(), scale)
 
 
+def pack_conv3d_fused_p16(weight, scale):
+    """Conv3d weight [32, 32, 3 (kt), 3, 3] for ``pcab_conv3d_p16`` (temporal taps fused into the MMA N dimension): rows =
+    (kt = 2, 1, 0) x output channel -- input frame f feeds output frames f-1, f, f+1 through kt = 2, 1, 0 --, K = tap (ky*3+kx)
+    x input channel, dense, padded to 320."""
+    cout, cin = weight.shape[:2]
+    assert cout == 32 and cin == 32
+    rows = torch.cat([weight.detach().float()[:, :, kt].permute(0, 2, 3, 1).reshape(cout, 9 * cin) for kt in (2, 1, 0)], 0)
+    return pack_rows_f16_dense(rows.contiguous(), scale)
+
+
 def pack_convT_p16(weight, scale):
     """ConvTranspose2d(2, stride 2) weight [Cin, Cout, 2, 2] for ``pcab_convT2x2_p16``: GEMM rows (output columns) =
     (dy*2+dx)*Cout + co, K = Cin."""

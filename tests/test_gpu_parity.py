@@ -947,6 +947,36 @@ def test_conv3x3_p16_against_float64(lib, case):
     assert_close_rel(got, ref, 1e-5, f"conv p16 {case}")
 
 
+@pytest.mark.parametrize("shape", [(1, 5, 48, 40), (2, 3, 37, 21), (1, 10, 32, 32), (1, 2, 16, 24)])
+def test_conv3d_fused_p16_against_float64(lib, shape):
+    """pcab_conv3d_p16: Conv3d 3x3x3 with the temporal taps fused into the MMA N dimension (accumulator rings in TMEM, ring wrap
+    at T > 6, ragged tiles, B > 1) against float64 on the exactly-decoded input."""
+    from pcaccumulation_b200 import tc_pack
+    from pcaccumulation_b200._lib import F as Fl, I, P, call, stream
+
+    B, T, H, W = shape
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B * T, H, W, 32, generator=g)
+    xp = tc_pack.pack_p16(x).cuda()
+    xq = tc_pack.unpack_p16(xp.cpu())
+    w = torch.randn(32, 32, 3, 3, 3, generator=g) * 0.1
+    bias = torch.randn(32, generator=g)
+    x5 = xq.view(B, T, H, W, 32).permute(0, 4, 1, 2, 3).double()
+    ref = F.relu(F.conv3d(x5, w.double(), bias.double(), padding=1)).permute(0, 2, 3, 4, 1).reshape(B * T, H, W, 32)
+    scale = tc_pack.f16_weight_scale(w)
+    pack = tc_pack.pack_conv3d_fused_p16(w.cuda(), scale)
+    assert pack.shape == (2, 96, 320)
+    out = torch.full((B * T, H, W, 32), float("nan"), device="cuda")
+    sat = torch.zeros(1, dtype=torch.int32, device="cuda")
+    bd = bias.cuda()
+    for _ in range(2):  # twice: the second launch starts from whatever the first left in TMEM / shared memory
+        call("pcab_conv3d_p16", P(xp), I(T), P(pack), Fl(1.0 / scale), P(bd), I(1), P(out), I(B * T), I(H), I(W), P(sat), stream())
+    torch.cuda.synchronize()
+    got = tc_pack.unpack_p16(out.cpu())
+    assert not bool(torch.isnan(got).any()) and int(sat.item()) == 0
+    assert_close_rel(got, ref, 1e-5, "conv3d fused p16")
+
+
 def test_conv3x3_p16_saturation_is_counted(lib):
     """Outputs beyond the fp16 range are clamped and COUNTED (the model then switches to the tf32 operands)."""
     import types
