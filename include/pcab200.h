@@ -209,6 +209,15 @@ int pcab_tpn_pos_l0(const float* points, const int* inst, const int* tidx, int n
 int pcab_apply_seg_pose(const float* points, const int* seg, const float* pose, int n, float* out,
                         pcab_stream_t stream);
 int pcab_scatter_rows3(const float* src, const int* idx, int k, float* dst, pcab_stream_t stream);
+/* models/motionnet.py:246-258: the TubeNet inputs of the selected points (labels, batch / time index, coordinates, motion labels) */
+int pcab_tpn_gather(const int* idx, int k, const long long* inst, const int* point_batch, const int* point_time,
+                    const float* points, const long long* sd_labels, long long* inst_out, long long* batch_out,
+                    long long* time_out, float* points_out, long long* mos_out, pcab_stream_t stream);
+/* models/alignnet.py:9-38 (test mode): out[t] = pose_gt[t] @ inv(pose_est[t]) */
+int pcab_pose_error(const float* pose_gt, const float* pose_est, int T, float* out /* [T,4,4] */, pcab_stream_t stream);
+/* models/alignnet.py:271-279: out2 = {inst_l2_error, dynamic_inst_l2_error}; scratch4 = four doubles */
+int pcab_inst_errors(const float* rec_est, const float* rec_gt, const long long* time_idx, const long long* mos_labels, int n,
+                     double* scratch4, float* out2, pcab_stream_t stream);
 
 /* ---- data front-end: libs/dataset.py:163-207 steps 2-4 (crop, ground removal) ------------- */
 size_t pcab_prep_points_workspace(int n_points);

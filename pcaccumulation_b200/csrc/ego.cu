@@ -281,8 +281,15 @@ __global__ void __launch_bounds__(1024) k_ego_kabsch(const float* __restrict__ x
     for (int c = 0; c < 3; ++c) C[r][c] = block_sum(a[r] * wn * b[c], sh);
   if (i == 0) {
     double R[3][3];
-    kabsch_rotation(C, R);
     float* P = pose + (size_t)p * 16;
+    bool finite = true;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) finite &= isfinite(C[r][c]);
+    if (!finite) {  // torch.svd raises on a non-finite covariance: R = I, t = 0 (toolbox/register_utils.py:295-304)
+      for (int k = 0; k < 16; ++k) P[k] = (k % 5 == 0) ? 1.f : 0.f;
+      return;
+    }
+    kabsch_rotation(C, R);
     for (int r = 0; r < 3; ++r) {
       for (int c = 0; c < 3; ++c) P[4 * r + c] = (float)R[r][c];
       double t = mean[3 + r] - ((double)(float)R[r][0] * mean[0] + (double)(float)R[r][1] * mean[1] +

@@ -712,6 +712,100 @@ extern "C" int pcab_apply_seg_pose(const float* points, const int* seg, const fl
   return PCAB_OK;
 }
 
+namespace {
+// TubeNet inputs of the selected points in one pass (replaces six boolean-mask gathers of models/motionnet.py:246-258)
+__global__ void k_tpn_gather(const int* __restrict__ idx, int k, const long long* __restrict__ inst, const int* __restrict__ pbatch,
+                             const int* __restrict__ ptime, const float* __restrict__ tp, const long long* __restrict__ sd,
+                             long long* __restrict__ o_inst, long long* __restrict__ o_batch, long long* __restrict__ o_time,
+                             float* __restrict__ o_tp, long long* __restrict__ o_mos) {
+  int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < k; j += stride) {
+    const int i = idx[j];
+    o_inst[j] = inst[i], o_batch[j] = pbatch[i], o_time[j] = ptime[i], o_mos[j] = sd[i];
+    o_tp[3 * j] = tp[3 * i], o_tp[3 * j + 1] = tp[3 * i + 1], o_tp[3 * j + 2] = tp[3 * i + 2];
+  }
+}
+
+// general 4x4 inverse in double (Gauss-Jordan, partial pivoting) and G[t] = gt[t] @ inv(est[t])  (models/alignnet.py:9-38)
+__global__ void k_pose_error(const float* __restrict__ gt, const float* __restrict__ est, int T, float* __restrict__ out) {
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    double a[4][8];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) a[i][j] = est[16 * t + 4 * i + j], a[i][4 + j] = (i == j);
+    for (int c = 0; c < 4; ++c) {
+      int piv = c;
+      for (int r = c + 1; r < 4; ++r)
+        if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+      for (int j = 0; j < 8; ++j) {
+        const double tmp = a[c][j];
+        a[c][j] = a[piv][j], a[piv][j] = tmp;
+      }
+      const double d = a[c][c];
+      for (int j = 0; j < 8; ++j) a[c][j] /= d;
+      for (int r = 0; r < 4; ++r)
+        if (r != c) {
+          const double f = a[r][c];
+          for (int j = 0; j < 8; ++j) a[r][j] -= f * a[c][j];
+        }
+    }
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        double v = 0;
+        for (int k = 0; k < 4; ++k) v += (double)gt[16 * t + 4 * i + k] * a[k][4 + j];
+        out[16 * t + 4 * i + j] = (float)v;
+      }
+  }
+}
+
+// sums for inst_l2_error / dynamic_inst_l2_error (models/alignnet.py:271-279): acc = {sum l2 w, sum w, sum l2 wm, sum wm}
+__global__ void k_inst_errors(const float* __restrict__ a, const float* __restrict__ b, const long long* __restrict__ tidx,
+                              const long long* __restrict__ mos, int n, double* __restrict__ acc) {
+  double s[4] = {0, 0, 0, 0};
+  int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float dx = a[3 * i] - b[3 * i], dy = a[3 * i + 1] - b[3 * i + 1], dz = a[3 * i + 2] - b[3 * i + 2];
+    const float l2 = sqrtf(dx * dx + dy * dy + dz * dz);
+    const bool w = tidx[i] > 0, wm = w && mos[i] == 1;
+    if (w) s[0] += l2, s[1] += 1.0;
+    if (wm) s[2] += l2, s[3] += 1.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    s[k] = warp_sum_d(s[k]);
+    if ((threadIdx.x & 31) == 0 && s[k] != 0.0) atomicAdd(acc + k, s[k]);
+  }
+}
+__global__ void k_inst_errors_final(const double* __restrict__ acc, float* __restrict__ out2) {
+  out2[0] = (float)(acc[0] / (acc[1] + 1e-20));
+  out2[1] = (float)(acc[2] / (acc[3] + 1e-20));
+}
+}  // namespace
+
+extern "C" int pcab_tpn_gather(const int* idx, int k, const long long* inst, const int* point_batch, const int* point_time,
+                               const float* points, const long long* sd_labels, long long* inst_out, long long* batch_out,
+                               long long* time_out, float* points_out, long long* mos_out, cudaStream_t stream) {
+  if (k <= 0) return PCAB_OK;
+  k_tpn_gather<<<grid_for(k, 256), 256, 0, stream>>>(idx, k, inst, point_batch, point_time, points, sd_labels, inst_out, batch_out,
+                                                     time_out, points_out, mos_out);
+  PCAB_CHECK_LAUNCH("pcab_tpn_gather");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_pose_error(const float* pose_gt, const float* pose_est, int T, float* out, cudaStream_t stream) {
+  k_pose_error<<<1, 32, 0, stream>>>(pose_gt, pose_est, T, out);
+  PCAB_CHECK_LAUNCH("pcab_pose_error");
+  return PCAB_OK;
+}
+
+extern "C" int pcab_inst_errors(const float* rec_est, const float* rec_gt, const long long* time_idx, const long long* mos_labels, int n,
+                                double* scratch4, float* out2, cudaStream_t stream) {
+  PCAB_CUDA(cudaMemsetAsync(scratch4, 0, 4 * sizeof(double), stream));
+  if (n > 0) k_inst_errors<<<grid_for(n, 256), 256, 0, stream>>>(rec_est, rec_gt, time_idx, mos_labels, n, scratch4);
+  k_inst_errors_final<<<1, 1, 0, stream>>>(scratch4, out2);
+  PCAB_CHECK_LAUNCH("pcab_inst_errors");
+  return PCAB_OK;
+}
+
 extern "C" int pcab_scatter_rows3(const float* src, const int* idx, int k, float* dst, cudaStream_t stream) {
   if (k <= 0) return PCAB_OK;
   k_scatter_rows3<<<grid_for(k, 256), 256, 0, stream>>>(src, idx, k, dst);

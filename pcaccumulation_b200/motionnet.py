@@ -850,13 +850,20 @@ class MotionNet(nn.Module):
                  F(y_abs), P(mf), stream())
             if self.keep_stages:
                 st.update(backbone_feats=bb, motion_feats=mf)
-            ridx = rec_idx.long()
+            g_inst = torch.empty(n_rec, dtype=torch.int64, device=dev)
+            g_batch = torch.empty(n_rec, dtype=torch.int64, device=dev)
+            g_time = torch.empty(n_rec, dtype=torch.int64, device=dev)
+            g_mos = torch.empty(n_rec, dtype=torch.int64, device=dev)
+            g_tp = torch.empty(n_rec, 3, device=dev)
+            sd64 = input_dict["sd_labels"].reshape(-1).to(torch.int64).contiguous()
+            call("pcab_tpn_gather", P(rec_idx), I(n_rec), P(inst_labels), P(pbatch), P(ptime), P(tp), P(sd64), P(g_inst), P(g_batch),
+                 P(g_time), P(g_tp), P(g_mos), stream())
             self._alignnet(W, {
-                "inst_labels": inst_labels[ridx], "batch_idx": pbatch[ridx].long(), "time_idx": ptime[ridx].long(),
+                "inst_labels": g_inst, "batch_idx": g_batch, "time_idx": g_time,
                 "n_inst_max": n_inst_max if self.mode == "test" else 0,
-                "transformed_points": tp[ridx],
+                "transformed_points": g_tp,
                 "backbone_feats": bb, "motion_feats": mf, "inst_motion_gt": input_dict["inst_motion_gt"],
-                "mos_labels": input_dict["sd_labels"][ridx, 0].long(), "ego_motion_est": results["ego_motion_est"],
+                "mos_labels": g_mos, "ego_motion_est": results["ego_motion_est"],
                 "ego_motion_gt": results["ego_motion_gt"]}, results, T)
             call("pcab_scatter_rows3", P(results["sub_rec_est"]), P(rec_idx), I(n_rec), P(rec_est), stream())
         self._mark("tubenet")
@@ -1005,7 +1012,8 @@ class MotionNet(nn.Module):
             # upstream builds ONE identity motion list entry for the whole batch (alignnet.py:190-192), so every instance's
             # "GT" is the ego-pose error of scene 0 per frame and instance ids are not offset per scene
             K0 = inp["n_inst_max"] + 1
-            G = (ego_gt[0] @ torch.linalg.inv(ego_est[0])).contiguous()  # [T,4,4]
+            G = torch.empty(T, 4, 4, device=dev)
+            call("pcab_pose_error", P(ego_gt[0].contiguous()), P(ego_est[0].contiguous()), I(T), P(G), stream())
             motion_all = None
         else:
             inst_motion_gt = [m.to(dev).float() for m in inp["inst_motion_gt"]]
@@ -1110,10 +1118,9 @@ class MotionNet(nn.Module):
             call("pcab_apply_seg_pose", P(tp), P(t32), P(G), I(n_points), P(rec_gt), stream())
         else:
             call("pcab_apply_seg_pose", P(tp), P(seg32), P(motion_kept.contiguous()), I(n_points), P(rec_gt), stream())
-        l2 = torch.norm(rec_est - rec_gt, p=2, dim=1)
-        w = t_idx > 0
-        wm = (mos_labels == 1) & w
-        errs = torch.stack(((l2 * w).sum() / (w.sum() + 1e-20), (l2 * wm).sum() / (wm.sum() + 1e-20)))
+        errs = torch.empty(2, device=dev)
+        acc4 = torch.empty(4, dtype=torch.float64, device=dev)
+        call("pcab_inst_errors", P(rec_est), P(rec_gt), P(t_idx), P(mos_labels.contiguous()), I(n_points), P(acc4), P(errs), stream())
         self._deferred.append((("inst_l2_error", "dynamic_inst_l2_error"), errs))
         results["inst_labels_adjusted"] = inst_labels
         results["inst_pose_est"] = final
