@@ -140,6 +140,8 @@ int pcab_transform_points(const float* xyz, const int* point_frame, const float*
 size_t pcab_bg_compact_workspace(long long n_cells);
 int pcab_bg_compact(const int* cell_to_pillar, const int* fb_est, int n_frames, int H, int W, int* bg_cells,
                     int* frame_off /* [n_frames+1] */, void* workspace, size_t workspace_bytes, pcab_stream_t stream);
+/* models/egomotion.py:451-455: out2 = {ego_rot_error, ego_trans_error} of [B,T,4,4] poses (recomputed after the ICP refinement) */
+int pcab_ego_pose_errors(const float* ego_est, const float* ego_gt, int B, int T, float* out2, pcab_stream_t stream);
 size_t pcab_ego_pairs_workspace(int npairs);
 int pcab_ego_pairs(const float* geo_nhwc /* [B*T,H,W,64] */, int geo_fmt, const int* cell_to_pillar, const float* pillar_mean,
                    const int* pillar_frame, int n_pillars, const int* bg_cells, const int* frame_off,
@@ -249,6 +251,31 @@ int pcab_chamfer_forward(const float* xyz1, const float* xyz2, int B, int n, int
 int pcab_chamfer_backward(const float* xyz1, const float* xyz2, int B, int n, int m, const float* grad_dist1,
                           const float* grad_dist2, const int* idx1, const int* idx2, float* grad_xyz1,
                           float* grad_xyz2, pcab_stream_t stream);
+
+/* same results with every pair evaluated (the formulation of chamfer_distance.cu:6-136); workspace as pcab_chamfer_workspace */
+int pcab_chamfer_forward_brute(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1, float* dist2,
+                               int* idx1, int* idx2, void* workspace, size_t workspace_bytes, pcab_stream_t stream);
+/* One direction of that search (chamfer_distance.cpp:59-84, nnsearch) through the exact uniform-grid search: dist / idx of the
+ * nearest target of every query, bit-identical to the brute force (lowest index wins ties).  max_dist > 0 bounds the search
+ * (the KD-tree hybrid search of Open3D's registration, models/egomotion.py:21): dist = NaN, idx = -1 where no target lies
+ * strictly within max_dist; max_dist <= 0 = unbounded. */
+size_t pcab_nn_workspace(int n_queries, int n_targets);
+int pcab_nn_search(const float* queries, int n_queries, const float* targets, int n_targets, float max_dist, float* dist,
+                   int* idx, void* workspace, size_t workspace_bytes, pcab_stream_t stream);
+
+/* ---- ICP refinement: models/egomotion.py:9-28,360-384 (model.ego_icp) and
+ *      models/alignnet.py:54-112 (model.tpointnet_icp), i.e. open3d registration_icp(src, tgt, max_dist, init,
+ *      TransformationEstimationPointToPoint(), ICPConvergenceCriteria(max_iteration)) ------------------------------------
+ * n_problems independent registrations in one call.  src_problem[i] (NULL = all 0; < 0 = ignored) assigns source point i to
+ * a problem; tgt_group[j] / problem_group[p] (both NULL = one group) restrict problem p to the targets of its group.
+ * init_pose [P,4,4] (NULL = identity) is the starting transformation; pose_out [P,4,4] = total transformation (update_k ...
+ * update_1 init); stats [P,3] = fitness, inlier rmse, updates applied (may be NULL).  rel_fitness / rel_rmse = Open3D's
+ * ICPConvergenceCriteria defaults 1e-6. */
+size_t pcab_icp_workspace(int n_targets, int n_problems);
+int pcab_icp_point_to_point(const float* src, const int* src_problem, int n_src, const float* tgt, const int* tgt_group, int n_tgt,
+                            const int* problem_group, int n_problems, const float* init_pose, float max_dist, int max_iter,
+                            float rel_fitness, float rel_rmse, float* pose_out, float* stats, void* workspace,
+                            size_t workspace_bytes, pcab_stream_t stream);
 
 #ifdef __cplusplus
 }

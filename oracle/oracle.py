@@ -179,6 +179,56 @@ def kabsch(x1, x2, weights, eps=1e-7):
     return rot, trans
 
 
+def icp_point_to_point(src, tgt, max_dist, init=None, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6):
+    """open3d.pipelines.registration.registration_icp(src, tgt, max_dist, init, TransformationEstimationPointToPoint(),
+    ICPConvergenceCriteria(max_iteration=max_iter)) as the reference calls it (models/egomotion.py:9-28, models/alignnet.py:
+    79-83).  Open3D (unpinned by the reference, README "open3d") is NOT installed here and not vendored: PARITY UNPINNED for
+    this function -- it restates the published algorithm of Open3D's RegistrationICP (cpp/open3d/pipelines/registration/
+    Registration.cpp): correspondences = nearest target strictly within max_dist (KD-tree hybrid search, max_nn = 1);
+    fitness = #correspondences / #source, inlier_rmse = sqrt(mean squared distance); per iteration the update is
+    Eigen::umeyama(source, target, with_scaling=false) over the correspondence set (identity when it is empty), applied to
+    the source in float64; stop when both |d fitness| < 1e-6 and |d rmse| < 1e-6.  Returns (T[4,4] float64, fitness, rmse)."""
+    from scipy.spatial import cKDTree
+
+    src = np.asarray(src, dtype=np.float64).reshape(-1, 3)
+    tgt = np.asarray(tgt, dtype=np.float64).reshape(-1, 3)
+    T = np.eye(4) if init is None else np.asarray(init, dtype=np.float64).copy()
+    if len(src) == 0 or len(tgt) == 0:
+        return T, 0.0, 0.0
+    tree = cKDTree(tgt)
+    pts = src @ T[:3, :3].T + T[:3, 3]
+
+    def correspondences(p):
+        d, j = tree.query(p, k=1)
+        ok = d < max_dist
+        n = int(ok.sum())
+        return ok, j, (n / len(p), float(np.sqrt((d[ok] ** 2).sum() / n)) if n else 0.0)
+
+    def umeyama(a, b):
+        ma, mb = a.mean(0), b.mean(0)
+        cov = (b - mb).T @ (a - ma) / len(a)
+        U, _, Vt = np.linalg.svd(cov)
+        S = np.eye(3)
+        if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+            S[2, 2] = -1
+        R = U @ S @ Vt
+        out = np.eye(4)
+        out[:3, :3], out[:3, 3] = R, mb - R @ ma
+        return out
+
+    ok, j, (fit, rmse) = correspondences(pts)
+    for _ in range(max_iter):
+        upd = umeyama(pts[ok], tgt[j[ok]]) if ok.any() else np.eye(4)
+        T = upd @ T
+        pts = pts @ upd[:3, :3].T + upd[:3, 3]
+        ok, j, (fit2, rmse2) = correspondences(pts)
+        done = abs(fit - fit2) < rel_fitness and abs(rmse - rmse2) < rel_rmse
+        fit, rmse = fit2, rmse2
+        if done:
+            break
+    return T, fit, rmse
+
+
 def relative_pose(tsfm_src, tsfm_tgt):
     """toolbox/register_utils.py:184-197 (waymo / nuscene branch): inv(T_tgt) @ T_src."""
     return torch.linalg.solve(tsfm_tgt, tsfm_src)
@@ -430,7 +480,7 @@ class OracleMotionNet:
         pose[:3, 3] = t[0][:, 0]
         return pose, perm
 
-    def ego_motion(self, geo, fb_est, occ_map, pts_mean_map, ego_gt, results):
+    def ego_motion(self, geo, fb_est, occ_map, pts_mean_map, ego_gt, results, raw=None):
         """models/egomotion.py:387-469 with the sequence strategies of :195-357."""
         B, T, C, Ny, Nx = geo.shape
         freq = self.cfg["data"]["freq"]
@@ -474,6 +524,18 @@ class OracleMotionNet:
                     perm_list.append(perm)
                     chained_est.append(pose)
                     chained_gt.append(pose_gt)
+            if self.cfg["model"]["ego_icp"]:  # models/egomotion.py:360-384,439-441: raw background points, frame 0 = anchor
+                points, time_indice, fb_pp = raw
+                pe = self.cfg["pose_estimation"]
+                sel0 = (time_indice[:, 0] == b) & (time_indice[:, 1] == 0) & (fb_pp[:, 0] == 0)
+                anchor_pts = points[sel0].double().numpy()
+                refined = [eye]
+                for t in range(1, T):
+                    sel = (time_indice[:, 0] == b) & (time_indice[:, 1] == t) & (fb_pp[:, 0] == 0)
+                    init = chained_est[-T:][t].float().numpy()
+                    Tm, _, _ = icp_point_to_point(points[sel].double().numpy(), anchor_pts, pe["icp_threshold"], init, pe["icp_max_iter"])
+                    refined.append(torch.tensor(Tm).float())
+                chained_est[-T:] = refined
         est, gtp = torch.stack(chained_est), torch.stack(chained_gt)
         rot_err = rotation_error(est[:, :3, :3], gtp[:, :3, :3]).mean().item()
         trans_err = torch.norm(est[:, :3, 3].unsqueeze(-1) - gtp[:, :3, 3].unsqueeze(-1), dim=(1, 2)).mean().item()
@@ -686,6 +748,7 @@ class OracleMotionNet:
             p_time, p_idx = t_idx, torch.arange(n_points).long()
         p_bb, p_mf = inp["backbone_feats"][p_idx], inp["motion_feats"][p_idx]
         p_inst, p_mos, p_pts = inst_labels[p_idx], mos_labels[p_idx], tp[p_idx]
+        p_pts0 = p_pts.clone()
         results["tpointnet_loss_terms"] = {}
         final = None
         for it in range(self.cfg["tpointnet"]["n_iterations"]):
@@ -700,6 +763,20 @@ class OracleMotionNet:
             motion = motion.view(K, T, 4, 4)
             final = c if final is None else torch.matmul(c, final)
         final = final.view(K, T, 4, 4)
+        if self.cfg["model"]["tpointnet_icp"]:  # models/alignnet.py:54-112,264-266
+            rec = reconstruct_sequence(p_pts0, p_time, p_inst, final, T)
+            thr = self.cfg["tpointnet"]["icp_threshold"]
+            final = final.clone()
+            for k in range(K):
+                sel = p_inst == k
+                pk, tk = rec[sel].double().numpy(), p_time[sel].numpy()
+                assert tk.min() == 0
+                anchor_pts = pk[tk == 0]
+                ref = []
+                for t in range(T):
+                    cur = pk[tk == t]
+                    ref.append(icp_point_to_point(cur, anchor_pts, thr, None, 50)[0] if (t != 0 and len(cur)) else np.eye(4))
+                final[k] = torch.matmul(torch.tensor(np.array(ref)).to(final.dtype), final[k])
         rec_est = reconstruct_sequence(inp["transformed_points"], t_idx, inst_labels, final, T)
         rec_gt = reconstruct_sequence(inp["transformed_points"], t_idx, inst_labels, inst_motion_gt, T)
         l2 = torch.norm(rec_est - rec_gt, p=2, dim=1)
@@ -763,7 +840,7 @@ class OracleMotionNet:
         geo = self.seghead2d(bev_feats, "ego_feats_head")
         geo = geo / torch.norm(geo, p=2, dim=1, keepdim=True)
         st["geo_feats"] = geo
-        self.ego_motion(geo.view(B, T, -1, Ny, Nx), fb_est, occ_map, mean_map, ego_gt, results)
+        self.ego_motion(geo.view(B, T, -1, Ny, Nx), fb_est, occ_map, mean_map, ego_gt, results, raw=(pts, time_indice, fb_pp))
 
         pose_est = results["ego_motion_est"].to(self.dt)
         if "ego_motion_est" in self.inject:

@@ -3,7 +3,7 @@
 Forward and backward run as sm_100a kernels behind ``pcab_chamfer_forward`` / ``pcab_chamfer_backward``."""
 import torch
 
-from ._lib import I, P, Z, call, scratch, size, stream
+from ._lib import F, I, P, Z, call, scratch, size, stream
 
 
 class ChamferDistanceFunction(torch.autograd.Function):
@@ -46,8 +46,9 @@ class ChamferDistance(torch.nn.Module):
         return ChamferDistanceFunction.apply(xyz1, xyz2)
 
 
-def chamfer_with_indices(xyz1, xyz2):
-    """(dist1, dist2, idx1, idx2) -- the indices the reference keeps in ctx.saved_tensors."""
+def chamfer_with_indices(xyz1, xyz2, brute=False):
+    """(dist1, dist2, idx1, idx2) -- the indices the reference keeps in ctx.saved_tensors.  ``brute`` evaluates every pair
+    (the reference kernel's formulation) instead of the exact grid search; the results are bit-identical."""
     xyz1 = xyz1.contiguous().float()
     xyz2 = xyz2.contiguous().float()
     B, n, _ = xyz1.shape
@@ -58,6 +59,19 @@ def chamfer_with_indices(xyz1, xyz2):
     idx1 = torch.empty(B, n, dtype=torch.int32, device=dev)
     idx2 = torch.empty(B, m, dtype=torch.int32, device=dev)
     ws = scratch(size("pcab_chamfer_workspace", I(B), I(n), I(m)), dev)
-    call("pcab_chamfer_forward", P(xyz1), P(xyz2), I(B), I(n), I(m), P(dist1), P(dist2), P(idx1), P(idx2), P(ws),
-         Z(ws.numel()), stream())
+    call("pcab_chamfer_forward_brute" if brute else "pcab_chamfer_forward", P(xyz1), P(xyz2), I(B), I(n), I(m), P(dist1), P(dist2),
+         P(idx1), P(idx2), P(ws), Z(ws.numel()), stream())
     return dist1, dist2, idx1, idx2
+
+
+def nearest_neighbours(queries, targets, max_dist=0.0):
+    """(dist[n], idx[n]) of the nearest target of every query through the exact grid search; ``max_dist`` > 0 bounds the
+    search (dist = NaN, idx = -1 where nothing lies strictly within it)."""
+    q = queries.contiguous().float()
+    t = targets.contiguous().float()
+    n, m = q.shape[0], t.shape[0]
+    dist = torch.empty(n, device=q.device)
+    idx = torch.empty(n, dtype=torch.int32, device=q.device)
+    ws = scratch(size("pcab_nn_workspace", I(n), I(m)), q.device)
+    call("pcab_nn_search", P(q), I(n), P(t), I(m), F(max_dist), P(dist), P(idx), P(ws), Z(ws.numel()), stream())
+    return dist, idx

@@ -13,6 +13,7 @@
 // one iteration is  r_i = logsumexp_j(A_pad[i][j] - c_j)  followed by  c_j = logsumexp_i(A_pad[i][j] - r_i).
 #include <cub/cub.cuh>
 #include "common.cuh"
+#include "svd3.cuh"
 #include "pair16.cuh"
 #include "pcab200.h"
 
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(256) k_ego_affinity(const float* __restrict__ 
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       int i = blockIdx.y * 64 + ti + 16 * u, j = blockIdx.x * 64 + tj + 16 * v;
-      float d = fmaxf(-2.f * acc[u][v] + 2.f, 1e-12f);
+      const float raw = -2.f * acc[u][v] + 2.f;
+      const float d = raw != raw ? raw : fmaxf(raw, 1e-12f);  // torch.clamp keeps NaN (all-zero feature rows: 0/0), fmaxf would drop it
       A[((size_t)p * KP + i) * KP + j] = -(d - sp) / den;
     }
 }
@@ -174,7 +176,8 @@ __global__ void k_ego_perm(const float* __restrict__ A, const float* __restrict_
     d += ss;
     d += tx * tx + ty * ty + tz * tz;
     d = fmaxf(d, 1e-12f);
-    float pv = (d < t2) ? expf(A[(size_t)row * KP + j] - ri - c[(size_t)p * KP + j]) : 0.f;
+    const float lp = A[(size_t)row * KP + j] - ri - c[(size_t)p * KP + j];
+    float pv = (d < t2) ? expf(lp) : (lp != lp ? lp : 0.f);  // exp(.) * support: a NaN stays a NaN outside the support too
     perm[(size_t)row * KP + j] = pv;
     ws += pv, ax = fmaf(pv, tx, ax), ay = fmaf(pv, ty, ay), az = fmaf(pv, tz, az);
   }
@@ -195,64 +198,6 @@ __device__ double block_sum(double v, double* sh) {
   double t = 0;
   for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += sh[q];
   return t;
-}
-
-// one-sided Jacobi SVD of a 3x3 (double): M = U diag(S) V^T.  Returns R = V diag(1,1,det(V^T U^T)) U^T.
-__device__ void kabsch_rotation(const double C[3][3], double R[3][3]) {
-  double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) A[i][j] = C[i][j];
-  for (int sweep = 0; sweep < 30; ++sweep) {
-    double off = 0;
-    for (int p = 0; p < 2; ++p)
-      for (int q = p + 1; q < 3; ++q) {
-        double a = 0, b = 0, g = 0;
-        for (int i = 0; i < 3; ++i) a += A[i][p] * A[i][p], b += A[i][q] * A[i][q], g += A[i][p] * A[i][q];
-        off += g * g;
-        if (fabs(g) < 1e-300 || fabs(g) <= 1e-17 * sqrt(a * b)) continue;
-        double zeta = (b - a) / (2.0 * g);
-        double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-        for (int i = 0; i < 3; ++i) {
-          double x = A[i][p], y = A[i][q];
-          A[i][p] = cs * x - sn * y, A[i][q] = sn * x + cs * y;
-          x = V[i][p], y = V[i][q];
-          V[i][p] = cs * x - sn * y, V[i][q] = sn * x + cs * y;
-        }
-      }
-    if (off < 1e-60) break;
-  }
-  // column norms = singular values; order descending
-  double s[3];
-  int idx[3] = {0, 1, 2};
-  for (int j = 0; j < 3; ++j) s[j] = sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
-  for (int a = 0; a < 2; ++a)
-    for (int b = a + 1; b < 3; ++b)
-      if (s[idx[b]] > s[idx[a]]) {
-        int t = idx[a];
-        idx[a] = idx[b], idx[b] = t;
-      }
-  double U[3][3], Vs[3][3];
-  for (int j = 0; j < 3; ++j)
-    for (int i = 0; i < 3; ++i) Vs[i][j] = V[i][idx[j]];
-  for (int j = 0; j < 2; ++j) {
-    double nrm = s[idx[j]];
-    for (int i = 0; i < 3; ++i) U[i][j] = nrm > 0 ? A[i][idx[j]] / nrm : (i == j ? 1.0 : 0.0);
-  }
-  if (s[idx[2]] > 1e-12 * s[idx[0]] && s[idx[2]] > 0) {
-    for (int i = 0; i < 3; ++i) U[i][2] = A[i][idx[2]] / s[idx[2]];
-  } else {  // rank deficient: complete the basis (the determinant factor below removes the sign choice)
-    U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
-    U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
-    U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
-  }
-  auto det3 = [](const double M[3][3]) {
-    return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
-           M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
-  };
-  double d = det3(Vs) * det3(U);
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) R[i][j] = Vs[i][0] * U[j][0] + Vs[i][1] * U[j][1] + d * Vs[i][2] * U[j][2];
 }
 
 // weighted Kabsch per pair; one block of 1024 threads per pair (toolbox/register_utils.py:268-313)
@@ -374,6 +319,35 @@ __global__ void k_ego_losses(const float* __restrict__ pillar_mean, const int* _
   }
 }
 
+// rotation error (toolbox/register_utils.py:19-42): the angle of R_est^T R_gt in degrees.  The reference takes
+// acos((trace - 1) / 2) in float32, which loses half of its digits for the sub-degree angles that occur here; the same
+// angle is evaluated as atan2(|axis part|, (trace - 1) / 2) in double, i.e. at least as close to the exact value.
+// Translation error (:45-56): |t_est - t_gt|.
+__device__ void pose_errors(const float* E, const float* G, double& rot_sum, double& trans_sum) {
+  double Rr[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += (double)E[4 * k + i] * (double)G[4 * k + j];
+      Rr[3 * i + j] = s;
+    }
+  const double cs = fmin(fmax((Rr[0] + Rr[4] + Rr[8] - 1.0) * 0.5, -1.0), 1.0);
+  const double ax = Rr[7] - Rr[5], ay = Rr[2] - Rr[6], az = Rr[3] - Rr[1];
+  rot_sum += 180.0 * atan2(0.5 * sqrt(ax * ax + ay * ay + az * az), cs) / 3.14159265358979323846;
+  float dx = E[3] - G[3], dy = E[7] - G[7], dz = E[11] - G[11];
+  trans_sum += (double)sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+// the two error scalars of models/egomotion.py:451-455 recomputed for refined poses (ICP branch, :439-441)
+__global__ void k_ego_errors(const float* __restrict__ est, const float* __restrict__ gt, int B, int T, float* __restrict__ out2) {
+  if (threadIdx.x || blockIdx.x) return;
+  double rot_sum = 0, trans_sum = 0;
+  for (int f = 0; f < B * T; ++f) pose_errors(est + (size_t)f * 16, gt + (size_t)f * 16, rot_sum, trans_sum);
+  const double n = T;
+  out2[0] = (float)(rot_sum / (B * T) * n / (n - 1));
+  out2[1] = (float)(trans_sum / (B * T) * n / (n - 1));
+}
+
 // sequence assembly + errors; single thread (B*T tiny 4x4 products)
 __global__ void k_ego_finalize(const float* __restrict__ pose, const float* __restrict__ ego_gt,
                                const int* __restrict__ chain_pair /* [B*T], -1 for t=0 */, int B, int T, int chain_mode,
@@ -409,21 +383,7 @@ __global__ void k_ego_finalize(const float* __restrict__ pose, const float* __re
         mm4(Ti, S, M);
         for (int k = 0; k < 16; ++k) G[k] = (float)M[k];
       }
-      // rotation error (toolbox/register_utils.py:19-42): the angle of R_est^T R_gt in degrees.  The reference takes
-      // acos((trace - 1) / 2) in float32, which loses half of its digits for the sub-degree angles that occur here; the same
-      // angle is evaluated as atan2(|axis part|, (trace - 1) / 2) in double, i.e. at least as close to the exact value.
-      double Rr[9];
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-          double s = 0;
-          for (int k = 0; k < 3; ++k) s += (double)E[4 * k + i] * (double)G[4 * k + j];
-          Rr[3 * i + j] = s;
-        }
-      const double cs = fmin(fmax((Rr[0] + Rr[4] + Rr[8] - 1.0) * 0.5, -1.0), 1.0);
-      const double ax = Rr[7] - Rr[5], ay = Rr[2] - Rr[6], az = Rr[3] - Rr[1];
-      rot_sum += 180.0 * atan2(0.5 * sqrt(ax * ax + ay * ay + az * az), cs) / 3.14159265358979323846;
-      float dx = E[3] - G[3], dy = E[7] - G[7], dz = E[11] - G[11];
-      trans_sum += (double)sqrtf(dx * dx + dy * dy + dz * dz);
+      pose_errors(E, G, rot_sum, trans_sum);
     }
   }
   double l1 = 0, l2 = 0;
@@ -441,6 +401,13 @@ __global__ void k_ego_finalize(const float* __restrict__ pose, const float* __re
 size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
+
+extern "C" int pcab_ego_pose_errors(const float* ego_est, const float* ego_gt, int B, int T, float* out2, cudaStream_t stream) {
+  PCAB_REQUIRE(B > 0 && T > 1, "bad sizes");
+  k_ego_errors<<<1, 32, 0, stream>>>(ego_est, ego_gt, B, T, out2);
+  PCAB_CHECK_LAUNCH("pcab_ego_pose_errors");
+  return PCAB_OK;
+}
 
 extern "C" size_t pcab_bg_compact_workspace(long long n_cells) {
   size_t scan_bytes = 0;

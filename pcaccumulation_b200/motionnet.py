@@ -227,7 +227,6 @@ class MotionNet(nn.Module):
             "the fused pillar encoder is specialised for depth 3 / 32 filters / 9 features (reference default)"
         assert unet_cfg["in_channels"] == 32 and cfg["pose_estimation"]["feats_dim"] == 64
         assert cfg["pose_estimation"]["n_kpts"] == N_KPTS and cfg["pose_estimation"]["add_slack"]
-        assert not cfg["model"]["ego_icp"] and not cfg["model"]["tpointnet_icp"], "ICP refinement is out of scope"
         self.pillar_encoder = _PillarEncoderParams(pe_cfg)
         self.unet = _UNetParams(**unet_cfg)
         self.semseg_head = _SegHead2DParams(unet_cfg["in_channels"], 2)
@@ -773,7 +772,8 @@ class MotionNet(nn.Module):
             h = self._conv(W["ego0"], [bev_feats], B * T, Ny, Nx, True, fmt=fmt)
             geo = self._conv(W["ego3"], [h], B * T, Ny, Nx, False, fmt=fmt)
         del h
-        self._ego_motion(W, geo, cell2pillar, prep, pillar_mean, pillar_frame, M, ego_gt, B, T, Ny, Nx, results, fmt)
+        self._ego_motion(W, geo, cell2pillar, prep, pillar_mean, pillar_frame, M, ego_gt, B, T, Ny, Nx, results, fmt,
+                         raw=(pts, pframe, fb_pp))
         if self.keep_stages:
             dec = (lambda t: t) if not fmt else _unpack_p16
             st.update(pillar_mean=pillar_mean, pillar_feats=pillar_feats, bev_feats=dec(bev_feats), geo=dec(geo), fb_est=fb_est)
@@ -906,7 +906,7 @@ class MotionNet(nn.Module):
         ev.record()
         return bg_cells, frame_off, host, ev
 
-    def _ego_motion(self, W, geo, cell2pillar, prep, pillar_mean, pillar_frame, M, ego_gt, B, T, Ny, Nx, results, fmt=0):
+    def _ego_motion(self, W, geo, cell2pillar, prep, pillar_mean, pillar_frame, M, ego_gt, B, T, Ny, Nx, results, fmt=0, raw=None):
         """models/egomotion.py:387-469.  The host only draws the keypoint permutations (H3 protocol:
         ``torch.randperm`` on the CPU generator, in the reference's order) from ONE readback of the
         per-frame background-pillar counts; everything else is batched over all pairs on the device."""
@@ -965,12 +965,54 @@ class MotionNet(nn.Module):
              I(1 if mode == "chain" else 0), P(perm), P(pose_pairs), P(est), P(gt), P(scalars), P(ws), Z(ws.numel()),
              stream())
         results["ego_l1_loss"], results["ego_l2_loss"] = scalars[0], scalars[1]
+        if cfg["model"]["ego_icp"]:
+            if self.keep_stages:
+                self.stages["ego_motion_before_icp"] = est
+            est = self._ego_icp(est, gt, raw, B, T, scalars)
         self._deferred.append((("ego_rot_error", "ego_trans_error"), scalars[2:4]))  # floats are read at the end of forward
         keep = [p for p, (b, anchor, ref, d) in enumerate(pairs) if mode == "chain" or anchor == 0]
         results["perm_matrix"] = [perm[p] for p in keep]
         results["ego_motion_est"], results["ego_motion_gt"] = est, gt
         if self.keep_stages:
             self.stages.update(pose_pairs=pose_pairs, choice=choice, counts=counts)
+
+    def _ego_icp(self, est, gt, raw, B, T, scalars):
+        """models/egomotion.py:9-28,360-384,439-441 (model.ego_icp): every frame's raw background points are registered to
+        the background points of frame 0 of their scene, starting from the estimated pose; the rotation / translation errors
+        are those of the refined poses.  One batched call: problem = (scene, frame), target group = scene."""
+        pts, pframe, fb_pp = raw
+        dev = pts.device
+        pe = self.cfg["pose_estimation"]
+        bg = fb_pp[:, 0] == 0
+        frame_t = pframe % T
+        src_problem = torch.where(bg & (frame_t > 0), pframe, torch.full_like(pframe, -1)).to(torch.int32).contiguous()
+        tgt_group = torch.where(bg & (frame_t == 0), pframe // T, torch.full_like(pframe, -1)).to(torch.int32).contiguous()
+        problem_group = (torch.arange(B * T, device=dev, dtype=torch.int32) // T).contiguous()
+        refined = torch.empty(B, T, 4, 4, device=dev)
+        n = pts.shape[0]
+        ws = scratch(size("pcab_icp_workspace", I(n), I(B * T)), dev)
+        call("pcab_icp_point_to_point", P(pts), P(src_problem), I(n), P(pts), P(tgt_group), I(n), P(problem_group), I(B * T),
+             P(est.contiguous()), F(pe["icp_threshold"]), I(pe["icp_max_iter"]), F(1e-6), F(1e-6), P(refined), P(None), P(ws),
+             Z(ws.numel()), stream())
+        call("pcab_ego_pose_errors", P(refined), P(gt), I(B), I(T), P(scalars[2:4]), stream())
+        return refined
+
+    def _tpn_icp(self, p_pts0, p_seg32, p_inst32, p_time32, final, K, T):
+        """models/alignnet.py:54-112,264-266 (model.tpointnet_icp): per instance, the points of every later frame (moved by
+        the regressed pose) are registered to the instance's frame-0 points; the result is composed onto the pose."""
+        dev = p_pts0.device
+        n = p_pts0.shape[0]
+        rec = torch.empty_like(p_pts0)
+        call("pcab_apply_seg_pose", P(p_pts0), P(p_seg32), P(final), I(n), P(rec), stream())
+        src_problem = torch.where(p_time32 > 0, p_seg32, torch.full_like(p_seg32, -1)).contiguous()
+        tgt_group = torch.where(p_time32 == 0, p_inst32, torch.full_like(p_inst32, -1)).contiguous()
+        problem_group = (torch.arange(K * T, device=dev, dtype=torch.int32) // T).contiguous()
+        upd = torch.empty(K, T, 4, 4, device=dev)
+        ws = scratch(size("pcab_icp_workspace", I(n), I(K * T)), dev)
+        call("pcab_icp_point_to_point", P(rec), P(src_problem), I(n), P(rec), P(tgt_group), I(n), P(problem_group), I(K * T),
+             P(None), F(self.cfg["tpointnet"]["icp_threshold"]), I(50), F(1e-6), F(1e-6), P(upd), P(None), P(ws), Z(ws.numel()),
+             stream())
+        return torch.matmul(upd, final).contiguous()
 
     # ------------------------------------------------------------------------------------------
     def _cluster(self, tp, mos, off, num_points, B, N, dev):
@@ -1054,6 +1096,7 @@ class MotionNet(nn.Module):
         call("pcab_tpn_rows", P(inst_labels), P(t_idx), I(n_points), I(n_extra), I(T), P(mapping), P(pad_frame), P(tp),
              P(seg32), P(inst_new), P(p_idx32), P(p_inst32), P(p_time32), P(p_seg32), P(p_pts), P(ws), Z(ws.numel()), stream())
         inst_labels = inst_new
+        p_pts0 = p_pts  # padded_transformed_points_back (alignnet.py:226)
         if test:
             motion0_fn = lambda: G[None].expand(K, T, 4, 4).contiguous()
         else:
@@ -1110,6 +1153,8 @@ class MotionNet(nn.Module):
             c = pose.reshape(-1, 4, 4)
             final = c if final is None else torch.matmul(c, final)
         final = final.view(K, T, 4, 4).contiguous()
+        if self.cfg["model"]["tpointnet_icp"]:
+            final = self._tpn_icp(p_pts0, p_seg32, p_inst32, p_time32, final, K, T)
         rec_est = torch.empty(n_points, 3, device=dev)
         rec_gt = torch.empty(n_points, 3, device=dev)
         call("pcab_apply_seg_pose", P(tp), P(seg32), P(final), I(n_points), P(rec_est), stream())
