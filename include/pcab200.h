@@ -277,6 +277,33 @@ int pcab_icp_point_to_point(const float* src, const int* src_problem, int n_src,
                             float rel_fitness, float rel_rmse, float* pose_out, float* stats, void* workspace,
                             size_t workspace_bytes, pcab_stream_t stream);
 
+/* ---- FuseLoss forward + gradients w.r.t. the network outputs: libs/loss.py:52-320,
+ *      libs/lovasz_softmax.py:56-94, libs/outlier_loss.py:15-29 ------------------------------------------------------------ */
+/* get_seg_loss (libs/loss.py:113-136) for the FG/BG map (get_fb_loss :165-186) or the motion logits (get_mos_loss :139-163).
+ * logits: [.., 2, hw] float (hw = Ny*Nx for fb_seg_est [B,T,2,Ny,Nx]; hw = 1 for mos_est [N,2]); gt: int64 per item; an item
+ * takes part when sel_float[i] == 1 or sel_a[i] == 1 or sel_b[i] == 1 (NULL arrays are skipped).
+ * out13 = {weighted CE, Lovasz-softmax, intersection[2], union[2], pred_positives[2], gt_positives[2] (raw counts: compute_iou
+ * :17-48 divides by 1e3), n_selected, class weights[2]}.  The workspace keeps what pcab_seg_loss_grad needs. */
+size_t pcab_seg_loss_workspace(long long n_items);
+int pcab_seg_loss(const float* logits, int hw, const long long* gt, const float* sel_float, const long long* sel_a,
+                  const long long* sel_b, long long n_items, float* out13, void* workspace, size_t workspace_bytes,
+                  pcab_stream_t stream);
+/* grad (layout of logits) = d(w_ce * CE + w_lovasz * Lovasz) / d logits; same arguments and workspace as the forward call */
+int pcab_seg_loss_grad(const float* logits, int hw, const long long* gt, const float* sel_float, const long long* sel_a,
+                       const long long* sel_b, long long n_items, const float* out13, float w_ce, float w_lovasz, float* grad,
+                       void* workspace, size_t workspace_bytes, pcab_stream_t stream);
+/* get_offset_loss (libs/loss.py:189-245).  inst_motion_gt = the per-scene [K_b,T,4,4] lists concatenated, inst_offset[b] = first
+ * row of scene b.  out4 = {offset_norm_loss, offset_dir_loss, offset_l2_error, n_foreground}; gt_offset [N,2] may be NULL. */
+size_t pcab_offset_loss_workspace(int n_instances_total);
+int pcab_offset_loss(const float* points, const int* point_batch, const int* point_time, const long long* inst_labels,
+                     const long long* fb_labels, const float* ego_motion_gt, const float* inst_motion_gt, const int* inst_offset,
+                     int n_instances_total, int T, const float* transformed_points, const float* offset_est, long long n_points,
+                     float* gt_offset, float* out4, void* workspace, size_t workspace_bytes, pcab_stream_t stream);
+int pcab_offset_loss_grad(const long long* fb_labels, const float* gt_offset, const float* offset_est, long long n_points,
+                          const float* out4, float w_norm, float w_dir, float* grad /* [N,2] */, pcab_stream_t stream);
+/* OutlierLoss (libs/outlier_loss.py:15-29) over n_mats contiguous [m,m] soft-assignment matrices; scratch1 = one double */
+int pcab_perm_loss(const float* perm, int n_mats, int m, double* scratch1, float* out1, pcab_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

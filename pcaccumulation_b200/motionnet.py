@@ -651,10 +651,16 @@ class MotionNet(nn.Module):
         return idx[:k], k
 
     # ------------------------------------------------------------------------------------------
-    @torch.no_grad()
     def forward(self, input_dict):
-        """Same contract as ``models/motionnet.py:137-262`` (inference; gradients are round-2 work)."""
-        with L.pinned_stream():
+        """Same contract as ``models/motionnet.py:137-262``.  Inference only: the CUDA stages have no backward yet (SURVEY.md
+        section 8 row f1 -- the loss and its gradients w.r.t. the outputs exist, ``pcaccumulation_b200/loss.py``), so a call
+        that a training loop would differentiate (module in train() mode with autograd enabled) fails HERE instead of
+        returning detached losses that silently never update the weights."""
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "pcaccumulation_b200.MotionNet has no backward pass: call it under torch.no_grad() / model.eval() "
+                "(validation and test loops of libs/trainer.py and libs/tester.py); training needs the reference model")
+        with torch.no_grad(), L.pinned_stream():
             return self._forward(input_dict)
 
     def _forward(self, input_dict):

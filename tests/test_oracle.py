@@ -405,3 +405,63 @@ def test_icp_restatement_recovers_a_known_motion_and_follows_open3d_conventions(
     Rk, tk = oracle.kabsch(a, b, torch.ones(1, len(lat)))
     T1, _, _ = oracle.icp_point_to_point(src_l, lat, 0.5, None, 1)
     assert np.abs(T1[:3, :3] - Rk[0].numpy()).max() < 1e-5 and np.abs(T1[:3, 3] - tk[0, :, 0].numpy()).max() < 1e-4
+
+
+def _loss_case(mode="val", scene=5, pts_per_frame=6000):
+    """A val-mode forward of the oracle on a small scene -> (predictions, input_dict) for the loss checks."""
+    from pcaccumulation_b200 import config, fixture, synth
+    from pcaccumulation_b200.motionnet import MotionNet
+
+    cfg = config.workload_config("C1", mode=mode)
+    sd = fixture.fixture_state_dict(MotionNet(cfg).state_dict(), 42)
+    vg = cfg["voxel_generator"]
+    s = dict(synth.make_workload_scene("C1", scene, pts_per_frame=pts_per_frame))
+    p4 = np.concatenate((s["input_points"], s["time_indice"]), 1).astype(np.float32)
+    s.update(oracle.voxelize(p4, vg["voxel_size"], vg["range"], vg["n_sweeps"]))
+    inp = synth.collate([s])
+    torch.manual_seed(1)
+    pred = oracle.OracleMotionNet(cfg, sd).forward(inp)
+    return cfg, sd, inp, pred
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference only exists in the build container")
+def test_fuse_loss_restatement_matches_reference_when_present(tmp_path):
+    """Pins oracle/loss_oracle.py on the UNMODIFIED libs/loss.py:FuseLoss (+ lovasz_softmax, outlier_loss): every stat of the
+    forward and the autograd gradients with respect to the network outputs, on val-mode predictions of the oracle forward."""
+    import importlib
+
+    from oracle import loss_oracle
+
+    ref_loader.load()
+    ref_loss = importlib.import_module("libs.loss")
+    _, _, inp, pred = _loss_case()
+    leaves = {}
+    for k in ("fb_seg_est", "mos_est", "offset_est"):
+        leaves[k] = pred[k].detach().clone().requires_grad_(True)
+    perm = [p.detach().clone().requires_grad_(True) for p in pred["perm_matrix"]]
+
+    def run(fn):
+        p = dict(pred)
+        p.update(leaves)
+        p["perm_matrix"] = perm
+        for t in list(leaves.values()) + perm:
+            t.grad = None
+        stats = fn(p, inp)
+        stats["loss"].backward()
+        return stats, {k: v.grad.clone() for k, v in leaves.items()}, [q.grad.clone() for q in perm]
+
+    cfg_loss = dict(loss_oracle.DEFAULT_WEIGHTS, save_dir=str(tmp_path))
+    want, gw, gpw = run(ref_loss.FuseLoss(cfg_loss))
+    got, gg, gpg = run(lambda p, i: loss_oracle.fuse_loss(p, i))
+    for k, v in want.items():
+        if k.endswith("_metric"):
+            for name in v:
+                assert np.array_equal(v[name], got[k][name]), (k, name)
+        else:
+            a, b = float(v), float(got[k])
+            assert a == b or abs(a - b) <= 1e-6 * max(abs(a), 1e-3), (k, a, b)
+    assert float(want["fb_loss"]) > 0 and float(want["mos_loss"]) > 0 and float(want["offset_loss"]) > 0 and "obj_loss" in want
+    for k in gw:
+        assert float((gw[k] - gg[k]).abs().max()) <= 1e-6 * float(gw[k].abs().max()), k
+    for a, b in zip(gpw, gpg):
+        assert torch.equal(a, b)
