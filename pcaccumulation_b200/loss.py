@@ -117,20 +117,19 @@ class FuseLoss(torch.nn.Module):
                   "w_obj_pose_loss", "obj_gamma"):
             setattr(self, k, config[k])
 
-    # -- libs/loss.py:165-186 / :139-163 ------------------------------------------------------------------------------
-    def get_fb_loss(self, predictions):
+    # -- libs/loss.py:165-186 / :139-163 / :189-245: device terms -> (combined loss, raw outputs) ---------------------------
+    def _fb_term(self, predictions):
         est = predictions["fb_seg_est"]  # [B,T,2,Ny,Nx]
         hw = est.shape[-1] * est.shape[-2]
         occ = predictions["occ_map"].reshape(-1).float().contiguous()
         return _SegLoss.apply(est, hw, _i64(predictions["fb_seg_gt"]), occ, None, None, float(self.w_fb_bce_loss),
                               float(self.w_fb_lovasz_loss))
 
-    def get_mos_loss(self, predictions, input_dict):
+    def _mos_term(self, predictions, input_dict):
         return _SegLoss.apply(predictions["mos_est"], 1, _i64(input_dict["sd_labels"][:, 0]), None, _i64(input_dict["fb_labels"][:, 0]),
                               _i64(predictions["fb_est_per_points"][:, 0]), float(self.w_mos_bce_loss), float(self.w_mos_lovasz_loss))
 
-    # -- libs/loss.py:189-245 -----------------------------------------------------------------------------------------
-    def get_offset_loss(self, input_dict, predictions):
+    def _offset_term(self, input_dict, predictions):
         dev = predictions["offset_est"].device
         ti = input_dict["time_indice"]
         motions = [m.to(dev).float().reshape(m.shape[0], -1, 4, 4) for m in input_dict["inst_motion_gt"]]
@@ -141,6 +140,36 @@ class FuseLoss(torch.nn.Module):
                 _i64(input_dict["inst_labels"][:, 0]), _i64(input_dict["fb_labels"][:, 0]), ego_gt, torch.cat(motions).contiguous(), koff,
                 int(sum(ks)), int(ego_gt.shape[1]), predictions["transformed_points"].detach().float().contiguous())
         return _OffsetLoss.apply(predictions["offset_est"], args, float(self.w_offset_norm_loss), float(self.w_offset_dir_loss))
+
+    # -- the reference's public methods, same return shapes (libs/tester.py:87-93 calls get_mos_loss / evaluate_cluster) ------
+    def _seg_stats(self, out):
+        return {"bce_loss": out[0], "lovasz_loss": out[1], "metric": self._metric(out.tolist())}
+
+    def get_fb_loss(self, predictions):
+        return self._seg_stats(self._fb_term(predictions)[1])
+
+    def get_mos_loss(self, predictions, input_dict):
+        return self._seg_stats(self._mos_term(predictions, input_dict)[1])
+
+    def get_offset_loss(self, input_dict, predictions):
+        _, out, gt_offset = self._offset_term(input_dict, predictions)
+        host = out.tolist()
+        if host[3] > 0:
+            predictions["offset_gt"] = gt_offset[_i64(input_dict["fb_labels"][:, 0]) == 1]
+        return out[0], out[1], (host[2] if host[3] > 0 else 0)
+
+    def evaluate_cluster(self, predictions, input_dict):
+        """libs/loss.py:261-270: per scene, the estimated instances against the labels (scores accumulate in
+        ``self.cluster_eval_offset``, an ``evaluation.ClusterEvaluator``)."""
+        from .evaluation import ClusterEvaluator
+
+        if getattr(self, "cluster_eval_offset", None) is None:
+            self.cluster_eval_offset = ClusterEvaluator(predictions["inst_labels_est"].device)
+        ti = input_dict["time_indice"]
+        for b in range(int(ti[:, 0].max() + 1)):
+            sel = ti[:, 0] == b
+            self.cluster_eval_offset.update(predictions["inst_labels_est"][sel], input_dict["inst_labels"][sel, 0],
+                                            input_dict["sd_labels"][sel, 0])
 
     # -- libs/loss.py:248-258 -----------------------------------------------------------------------------------------
     def get_tpointnet_loss(self, predictions):
@@ -172,14 +201,14 @@ class FuseLoss(torch.nn.Module):
         total = total + perm_loss
         stats["perm_loss"] = perm_loss
 
-        fb_loss, fb_out = self.get_fb_loss(predictions)
+        fb_loss, fb_out = self._fb_term(predictions)
         total = total + fb_loss
         stats["fb_loss"] = fb_loss
-        mos_loss, mos_out = self.get_mos_loss(predictions, input_dict)
+        mos_loss, mos_out = self._mos_term(predictions, input_dict)
         total = total + mos_loss
         stats["mos_loss"] = mos_loss
 
-        offset_loss, off_out, gt_offset = self.get_offset_loss(input_dict, predictions)
+        offset_loss, off_out, gt_offset = self._offset_term(input_dict, predictions)
         total = total + offset_loss
         stats["offset_loss"] = offset_loss
         stats["offset_l1_loss"], stats["offset_dir_loss"] = off_out[0], off_out[1]

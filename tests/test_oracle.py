@@ -465,3 +465,101 @@ def test_fuse_loss_restatement_matches_reference_when_present(tmp_path):
         assert float((gw[k] - gg[k]).abs().max()) <= 1e-6 * float(gw[k].abs().max()), k
     for a, b in zip(gpw, gpg):
         assert torch.equal(a, b)
+
+
+def _load_gpu_results():
+    """tests/golden/gpu_results.npz (tools/make_gpu_results_fixture.py, written on a B200): the results dict of the CUDA forward
+    for one small test-mode scene + the numbers the device loss / evaluation tail computed from it."""
+    g = np.load(os.path.join(GOLDEN, "gpu_results.npz"))
+    inp, pred = {}, {}
+    for k in g.files:
+        if k.startswith("in_") and k != "in_inst_motion_gt":
+            inp[k[3:]] = torch.tensor(g[k])
+        elif k.startswith("out_"):
+            v = g[k]
+            pred[k[4:]] = float(v[0]) if (v.ndim == 1 and v.size == 1 and k[4:] in ("ego_rot_error", "ego_trans_error", "inst_l2_error",
+                                                                                   "dynamic_inst_l2_error")) else torch.tensor(v)
+    inp["inst_motion_gt"] = [torch.tensor(g["in_inst_motion_gt"])]
+    pred["fb_seg_gt"] = pred["fb_seg_gt"].long()
+    pred["occ_map"] = pred["occ_map"].float()
+    p0 = np.zeros(int(np.prod(g["perm0_shape"])), np.float32)
+    p0[g["perm0_idx"]] = g["perm0_val"]
+    pred["perm_matrix"] = [torch.tensor(p0.reshape(tuple(g["perm0_shape"])))]
+    terms = {}
+    for k in g.files:
+        if k.startswith("tpn_"):
+            it, name = k[4:].split("_th_")
+            terms.setdefault(it + "_th", {})[name] = torch.tensor(g[k])
+    pred["tpointnet_loss_terms"] = dict(sorted(terms.items()))
+    for k in ("ego_l1_loss", "ego_l2_loss"):
+        pred[k] = pred[k].reshape(())
+    return g, inp, pred
+
+
+def _check_stats(g, stats, rel=1e-4):
+    for k in g.files:
+        if not k.startswith("stat_"):
+            continue
+        name = k[5:]
+        if "_metric_" in name:
+            m, field = name.split("_metric_")
+            assert np.array_equal(np.asarray(stats[m + "_metric"][field]), g[k]), name
+        else:
+            a, b = float(g[k][0]), float(stats[name])
+            assert abs(a - b) <= rel * max(abs(b), 1e-3), (name, a, b)
+
+
+def test_gpu_results_dict_through_the_oracle_consumers():
+    """The results dict produced on the B200 goes through the CPU restatements of its consumers (FuseLoss, the flow metrics of
+    the test loop, the instance scores): they report what the device consumers reported on the GPU (1e-4 / exact counters)."""
+    from oracle import loss_oracle
+
+    g, inp, pred = _load_gpu_results()
+    T = int(inp["ego_motion_gt"].shape[1])
+    _check_stats(g, loss_oracle.fuse_loss(pred, inp))
+    ev = oracle.flow_eval(inp, pred, T)
+    assert float((ev["epe_per_point"] - torch.tensor(g["eval_epe"])).abs().max()) <= 1e-5
+    for row, name in enumerate(("all", "dynamic", "static")):
+        cnt = ev["sf"][name]
+        assert cnt[0] == int(g["eval_sf"][row, 0]) and all(int(a) == int(b) for a, b in zip(cnt[2:], g["eval_sf"][row, 2:]))
+    mos = g["eval_mos"]
+    assert ev["mos"]["intersection"] == [int(mos[0]), int(mos[3])] and ev["mos"]["pred_positives"] == [int(mos[1]), int(mos[4])]
+    assert ev["mos"]["gt_positives"] == [int(mos[2]), int(mos[5])]
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference only exists in the build container")
+def test_reference_consumers_accept_gpu_results(tmp_path):
+    """The same dict through the UNMODIFIED consumers: libs/loss.py:FuseLoss.forward (everything the training / validation
+    loop reads) and the metric code of the test loop (libs/tester.py:58-93: GT accumulation, end-point errors, get_mos_loss,
+    evaluate_cluster -> toolbox/cluster_eval.py).  Schema (keys, dtypes, shapes) and numbers must both be accepted."""
+    import importlib
+
+    from oracle import loss_oracle
+
+    ns = ref_loader.load()
+    ru = ns["register_utils"]
+    ref_loss = importlib.import_module("libs.loss")
+    g, inp, pred = _load_gpu_results()
+    T = int(inp["ego_motion_gt"].shape[1])
+    fl = ref_loss.FuseLoss(dict(loss_oracle.DEFAULT_WEIGHTS, save_dir=str(tmp_path)))
+    _check_stats(g, fl(pred, inp))
+    # libs/tester.py:58-77
+    pts, t = inp["input_points"], inp["time_indice"][:, 1].long()
+    rec_gt = ru.reconstruct_sequence(ru.ego_motion_compensation(pts, t, inp["ego_motion_gt"].float()[0]), t, inp["inst_labels"][:, 0],
+                                     inp["inst_motion_gt"][0], T)
+    epe = torch.norm((pred["rec_est"] - pts) - (rec_gt - pts), p=2, dim=1)
+    assert float((epe - torch.tensor(g["eval_epe"])).abs().max()) <= 1e-5
+    # libs/tester.py:87-93
+    mos = fl.get_mos_loss(pred, inp)["metric"]
+    dev = g["eval_mos"]
+    assert np.array_equal(mos["intersection"] * 1e3, np.array([dev[0], dev[3]], dtype=np.float64))
+    assert np.array_equal(mos["gt_positives"] * 1e3, np.array([dev[2], dev[5]], dtype=np.float64))
+    fl.evaluate_cluster(pred, inp)
+    ce = fl.cluster_eval_offset
+    c = g["eval_cluster"]
+    assert np.array_equal(ce.total_gt_inst, c[[3, 7]])
+    for k, thr in enumerate(ce.iou_threshold):
+        for cls in (0, 1):
+            tp = float(np.sum([np.sum(x) for x in ce.tpsins[f"@{thr}"][cls]]))
+            fp = float(np.sum([np.sum(x) for x in ce.fpsins[f"@{thr}"][cls]]))
+            assert (tp, fp) == (c[8 + 2 * (2 * k + cls)], c[8 + 2 * (2 * k + cls) + 1]), (thr, cls)
