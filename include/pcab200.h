@@ -228,6 +228,15 @@ int pcab_prep_points(const float* raw_points /* [N,3] */, const long long* time_
                      float crop_z_max, int remove_ground, float ground_height /* incl. slack */, float* points4_out /* [N,4] */,
                      int* time_out, long long* sd_out, long long* fb_out, long long* inst_out, int* count_out /* device */,
                      void* workspace, size_t workspace_bytes, pcab_stream_t stream);
+/* the same with step 1 (training-time augmentation, libs/dataset.py:90-113,167-171) applied first, in float64 like numpy:
+ * p' = ((R p + t) + (u - 0.5) * noise_amp) * scale.  tsfm16: HOST [4,4] float64; noise: DEVICE [n,3] float64 uniforms drawn by
+ * the host in the reference's order, or NULL for the device generator seeded with `seed`. */
+int pcab_prep_points_augmented(const float* raw_points, const long long* time_idx, const long long* sd_labels,
+                               const long long* fb_labels, const long long* inst_labels, int n, const double* tsfm16,
+                               const double* noise, unsigned long long seed, double noise_amp, double scale, double crop_xy,
+                               double crop_z_min, double crop_z_max, int remove_ground, double ground_height, float* points4_out,
+                               int* time_out, long long* sd_out, long long* fb_out, long long* inst_out, int* count_out,
+                               void* workspace, size_t workspace_bytes, pcab_stream_t stream);
 
 /* ---- evaluation tail: libs/tester.py:58-88, toolbox/register_utils.py:59-93, toolbox/sf_eval_utils.py:46-52,71-100,
  *      libs/loss.py:17-48,139-149 ------------------------------------------------------------ */

@@ -947,6 +947,32 @@ def flow_eval(input_dict, predictions, n_frames):
     return out
 
 
+def prep_input_augmented(raw_points, time_indice, sd_labels, fb_labels, inst_labels, ego_motion_gt, inst_motion_gt, cfg):
+    """libs/dataset.py:147-207 WITH step 1 (``self.augmentation``): random rigid transform (:101-111; toolbox/register_utils.py:
+    199-206), jitter + scale (:90-98), conjugated ground-truth motions (:113-133), then steps 2-4.  Random numbers come from
+    numpy's GLOBAL stream in the reference's order, so ``np.random.seed(s)`` before the call replays a reference run."""
+    from scipy.spatial.transform import Rotation
+
+    da, T = cfg["data_aug"], cfg["data"]["n_frames"]
+    euler = [0, 0, np.random.uniform(0, np.pi * da["rot_aug"])]
+    rot = Rotation.from_euler("xyz", euler).as_matrix()
+    shift = [np.random.uniform(-da["augment_shift_range"], da["augment_shift_range"]),
+             np.random.uniform(-da["augment_shift_range"], da["augment_shift_range"]), 0]
+    tsfm = np.eye(4)
+    tsfm[:3, :3], tsfm[:3, 3] = rot, np.array(shift)
+    raw_points = (tsfm[:3, :3] @ raw_points.T + tsfm[:3, 3][:, None]).T
+    raw_points += (np.random.rand(raw_points.shape[0], 3) - 0.5) * da["augment_noise"]
+    raw_points = raw_points * np.random.uniform(da["augment_scale_min"], da["augment_scale_max"])
+    c = tsfm[None].repeat(T, 0)
+    ego_motion_gt = c @ ego_motion_gt @ np.linalg.inv(c)
+    im = inst_motion_gt.reshape(-1, 4, 4)
+    c = tsfm[None].repeat(im.shape[0], 0)
+    inst_motion_gt = (c @ im @ np.linalg.inv(c)).reshape(-1, T, 4, 4)
+    data = prep_input_test_mode(raw_points, time_indice, sd_labels, fb_labels, inst_labels, cfg)
+    data["ego_motion_gt"], data["inst_motion_gt"] = ego_motion_gt, inst_motion_gt
+    return data
+
+
 def prep_input_test_mode(raw_points, time_indice, sd_labels, fb_labels, inst_labels, cfg):
     """libs/dataset.py:163-207, steps 2-4 of ``BaseDataset.prep_input`` (no augmentation): crop, ground removal, voxelise."""
     vg, dc = cfg["voxel_generator"], cfg["data"]

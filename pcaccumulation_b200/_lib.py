@@ -52,7 +52,7 @@ SYMBOLS = [
     "pcab_select_workspace", "pcab_select_indices", "pcab_ungrid", "pcab_stpn_head_pack_size",
     "pcab_init_point_outputs", "pcab_stpn_head", "pcab_stpn_head_tc_pack_floats", "pcab_stpn_head_tc", "pcab_dynamic_flags", "pcab_cluster_workspace", "pcab_cluster_scene",
     "pcab_tpn_relabel", "pcab_tpn_rows_workspace", "pcab_tpn_rows", "pcab_tpn_static_embed", "pcab_tpn_iteration_workspace", "pcab_tpn_iteration", "pcab_embed_segmax_tc", "pcab_tpn_pos_l0", "pcab_apply_seg_pose",
-    "pcab_scatter_rows3", "pcab_tpn_gather", "pcab_pose_error", "pcab_inst_errors", "pcab_prep_points_workspace", "pcab_prep_points", "pcab_flow_eval", "pcab_cluster_eval_workspace", "pcab_cluster_eval", "pcab_chamfer_workspace", "pcab_chamfer_forward", "pcab_chamfer_backward",
+    "pcab_scatter_rows3", "pcab_tpn_gather", "pcab_pose_error", "pcab_inst_errors", "pcab_prep_points_workspace", "pcab_prep_points", "pcab_prep_points_augmented", "pcab_flow_eval", "pcab_cluster_eval_workspace", "pcab_cluster_eval", "pcab_chamfer_workspace", "pcab_chamfer_forward", "pcab_chamfer_backward",
     "pcab_nn_workspace", "pcab_nn_search", "pcab_icp_workspace", "pcab_icp_point_to_point", "pcab_ego_pose_errors", "pcab_chamfer_forward_brute",
     "pcab_seg_loss_workspace", "pcab_seg_loss", "pcab_seg_loss_grad", "pcab_offset_loss_workspace", "pcab_offset_loss",
     "pcab_offset_loss_grad", "pcab_perm_loss",

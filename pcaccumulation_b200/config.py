@@ -32,6 +32,12 @@ _DEFAULT = {
     "stpn": {"feat_dim": 32},
     "tpointnet": {"n_iterations": 1, "min_points": 10, "icp_threshold": 0.25},
     "model": {"ego_icp": False, "tpointnet_icp": False},
+    # configs/default.yaml:44-49 (training-time augmentation) and :99-113 (loss weights)
+    "data_aug": {"augment_noise": 0.01, "augment_shift_range": 0.25, "augment_scale_min": 0.995, "augment_scale_max": 1.005,
+                 "rot_aug": 0.5},
+    "loss": {"w_pose_l1_loss": 1.0, "w_perm_loss": 0.005, "w_mos_bce_loss": 1.0, "w_mos_lovasz_loss": 1.0, "w_fb_bce_loss": 1.0,
+             "w_fb_lovasz_loss": 1.0, "w_offset_norm_loss": 0.5, "w_offset_dir_loss": 0.5, "w_obj_l1_loss": 1.0,
+             "w_obj_pose_loss": 1.0, "w_obj_loss": 0.3, "w_obj_rot_loss": 50, "w_obj_trans_loss": 1.0, "obj_gamma": 0.7},
 }
 
 # configs/waymo/waymo.yaml

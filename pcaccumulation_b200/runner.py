@@ -68,38 +68,82 @@ class SceneRunner:
             d["point_to_voxel_map"] = v["point_to_voxel_map"].to(torch.int64)[:, None]
         return d
 
-    def prep_raw(self, sample):
-        """Steps 2-4 of ``libs/dataset.py:prep_input`` (test mode: no augmentation) on the device.
+    def prep_raw(self, sample, aug=None):
+        """Steps (1-)2-4 of ``libs/dataset.py:prep_input`` on the device.
 
-        ``sample``: the arrays of one ``.npz`` file as CUDA tensors - ``raw_points`` f32 [N,3] and ``time_indice``,
-        ``sd_labels``, ``fb_labels``, ``inst_labels`` i64 [N].  Returns (points4 [M,4] f32, labels dict with [M,1] i64
-        tensors, M): scene crop + ground removal as one stable compaction.
+        ``sample``: the arrays of one ``.npz`` file (numpy or torch) - ``raw_points`` f32 [N,3] and ``time_indice``,
+        ``sd_labels``, ``fb_labels``, ``inst_labels`` [N].  ``aug``: ``dataset.sample_augmentation(...)`` for the training-time
+        augmentation (step 1), None for the validation / test path.  Returns (points4 [M,4] f32, labels dict with [M,1] i64
+        tensors, M): augmentation + scene crop + ground removal as one stable compaction.
         """
-        from ._lib import F, I, P, Z, call, scratch, size, stream
+        import ctypes
+
+        from ._lib import D, F, I, P, Z, call, scratch, size, stream
         dev = self.device
-        raw = sample["raw_points"].to(dev).float().contiguous()
+        raw = torch.as_tensor(sample["raw_points"]).to(dev).float().contiguous()
         n = raw.shape[0]
-        i64 = lambda k: sample[k].to(dev).reshape(-1).to(torch.int64).contiguous()
+        # (named tensors: a temporary handed to P() would be freed -- and its block reused -- before the kernel reads it)
+        ins = {k: torch.as_tensor(sample[k]).to(dev).reshape(-1).to(torch.int64).contiguous()
+               for k in ("time_indice", "sd_labels", "fb_labels", "inst_labels")}
+        i64 = ins.__getitem__
         vg, dc = self.cfg["voxel_generator"], self.cfg["data"]
         p4 = torch.empty(n, 4, device=dev)
         t32 = torch.empty(n, dtype=torch.int32, device=dev)
         outs = {k: torch.empty(n, dtype=torch.int64, device=dev) for k in ("sd_labels", "fb_labels", "inst_labels")}
         count = torch.empty(1, dtype=torch.int32, device=dev)
         ws = scratch(size("pcab_prep_points_workspace", I(n)), dev)
-        call("pcab_prep_points", P(raw), P(i64("time_indice")), P(i64("sd_labels")), P(i64("fb_labels")), P(i64("inst_labels")),
-             I(n), F(vg["crop_range"][0]), F(vg["crop_range"][1]), F(vg["crop_range"][2]), I(int(dc["remove_ground"])),
-             F(dc["ground_height"] + dc["ground_slack"]), P(p4), P(t32), P(outs["sd_labels"]), P(outs["fb_labels"]),
-             P(outs["inst_labels"]), P(count), P(ws), Z(ws.numel()), stream())
+        ground = dc["ground_height"] + dc["ground_slack"]
+        if aug is None:
+            call("pcab_prep_points", P(raw), P(i64("time_indice")), P(i64("sd_labels")), P(i64("fb_labels")), P(i64("inst_labels")),
+                 I(n), F(vg["crop_range"][0]), F(vg["crop_range"][1]), F(vg["crop_range"][2]), I(int(dc["remove_ground"])),
+                 F(ground), P(p4), P(t32), P(outs["sd_labels"]), P(outs["fb_labels"]), P(outs["inst_labels"]), P(count), P(ws),
+                 Z(ws.numel()), stream())
+        else:
+            tsfm = (ctypes.c_double * 16)(*[float(v) for v in np.asarray(aug["tsfm"], dtype=np.float64).reshape(-1)])
+            noise = None if aug.get("noise") is None else torch.as_tensor(aug["noise"], dtype=torch.float64).to(dev).contiguous()
+            assert noise is None or noise.shape == (n, 3)
+            call("pcab_prep_points_augmented", P(raw), P(i64("time_indice")), P(i64("sd_labels")), P(i64("fb_labels")),
+                 P(i64("inst_labels")), I(n), P(tsfm), P(noise), ctypes.c_ulonglong(int(aug.get("seed", 0))), D(aug["noise_amp"]),
+                 D(aug["scale"]), D(vg["crop_range"][0]), D(vg["crop_range"][1]), D(vg["crop_range"][2]), I(int(dc["remove_ground"])),
+                 D(ground), P(p4), P(t32), P(outs["sd_labels"]), P(outs["fb_labels"]), P(outs["inst_labels"]), P(count), P(ws),
+                 Z(ws.numel()), stream())
         m = int(count.item())
         return p4[:m], {k: v[:m, None] for k, v in outs.items()}, m
 
+    def prep_sample(self, sample, augment=False, exact_noise=True):
+        """``BaseDataset.prep_input`` (libs/dataset.py:147-207) for one raw sample -> (points4, labels, M, ego_motion_gt
+        [T,4,4], inst_motion_gt [K,T,4,4]); with ``augment`` the random numbers come from numpy's global stream in the
+        reference's order (``dataset.sample_augmentation``) and the ground-truth motions are conjugated accordingly."""
+        from . import dataset as ds
+
+        ego, inst = np.asarray(sample["ego_motion_gt"]), np.asarray(sample["inst_motion_gt"])
+        aug = None
+        if augment:
+            aug = ds.sample_augmentation(self.cfg["data_aug"], int(np.asarray(sample["raw_points"]).shape[0]), exact_noise)
+            ego, inst = ds.update_transformation_after_data_augmentation(aug["tsfm"], ego, inst, self.T)
+        p4, labels, m = self.prep_raw(sample, aug)
+        return p4, labels, m, ego, inst
+
     @torch.no_grad()
-    def run_raw(self, sample):
-        """Raw sample arrays (as stored by the reference's dataset writers) -> crop / ground removal -> voxelise -> forward."""
-        p4, labels, m = self.prep_raw(sample)
-        ego = sample["ego_motion_gt"].to(self.device).float()[None].contiguous()
-        inst_motion = [sample["inst_motion_gt"].to(self.device).float()] if "inst_motion_gt" in sample else None
+    def run_raw(self, sample, augment=False):
+        """Raw sample arrays (as stored by the reference's dataset writers) -> [augmentation ->] crop / ground removal ->
+        voxelise -> forward."""
+        p4, labels, m, ego, inst = self.prep_sample(sample, augment)
+        ego = torch.as_tensor(ego).to(self.device).float()[None].contiguous()
+        inst_motion = [torch.as_tensor(inst).to(self.device).float()]
         return self.model(self.build_input(p4, [m], labels=labels, ego_motion_gt=ego, inst_motion_gt=inst_motion))
+
+    @torch.no_grad()
+    def run_npz(self, paths, augment=False):
+        """``.npz`` sample files (one per scene of the batch) -> device collate (libs/dataloader.py:7-40) -> forward."""
+        from . import dataset as ds
+
+        parts = [self.prep_sample(ds.load_sample(p), augment) for p in ([paths] if isinstance(paths, str) else paths)]
+        p4 = torch.cat([q[0] for q in parts])
+        labels = {k: torch.cat([q[1][k] for q in parts]) for k in parts[0][1]}
+        ego = torch.stack([torch.as_tensor(q[3]).float() for q in parts]).to(self.device).contiguous()
+        inst_motion = [torch.as_tensor(q[4]).to(self.device).float() for q in parts]
+        return self.model(self.build_input(p4, [q[2] for q in parts], labels=labels, ego_motion_gt=ego, inst_motion_gt=inst_motion))
 
     def warmup(self, batch_size=1):
         """Capture the model's CUDA graphs (see ``MotionNet.warmup``); call after loading weights, before serving."""

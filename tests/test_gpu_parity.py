@@ -1087,3 +1087,61 @@ def test_bev_utilities_on_p16_equal_their_float32_versions(lib):
         call("pcab_ungrid", P(src), I(64), I(fmt), I(20), I(24), P(xyz), P(frame), P(None), I(k), Fl(6.0), Fl(6.0), P(buf), stream())
     torch.cuda.synchronize()
     assert torch.equal(u1, u0)
+
+
+def test_augmented_front_end_and_npz_batches(fixture_weights, tmp_path):
+    """Training-time augmentation on the device (libs/dataset.py:90-113,167-171) replayed from the same seed as the oracle's
+    (= the reference's) numpy stream, then crop / ground removal / voxelisation; and .npz sample files -> device collate ->
+    forward (libs/dataset.py:209-224 + libs/dataloader.py:7-40) equal to the pre-collated input."""
+    from oracle import oracle
+    from pcaccumulation_b200 import config, synth
+    from pcaccumulation_b200.runner import SceneRunner
+
+    cfg = config.workload_config("C1")
+    runner = SceneRunner(cfg)
+    runner.model.load_state_dict(fixture_weights(cfg))
+    samples = []
+    for i in range(2):
+        s = synth.make_workload_scene("C1", 40 + i, pts_per_frame=8000)
+        raw = (s["input_points"] * 1.1).astype(np.float32)  # some points beyond the crop box
+        samples.append({"raw_points": raw, "time_indice": s["time_indice"][:, 0].astype(np.int64),
+                        **{k: s[k][:, 0].astype(np.int64) for k in ("sd_labels", "fb_labels", "inst_labels")},
+                        "ego_motion_gt": s["ego_motion_gt"], "inst_motion_gt": s["inst_motion_gt"]})
+    s0 = samples[0]
+    np.random.seed(21)
+    ref = oracle.prep_input_augmented(s0["raw_points"].copy(), s0["time_indice"], s0["sd_labels"], s0["fb_labels"], s0["inst_labels"],
+                                      s0["ego_motion_gt"].copy(), s0["inst_motion_gt"].copy(), cfg)
+    np.random.seed(21)
+    p4, labels, m, ego, inst = runner.prep_sample(s0, augment=True)
+    assert 0 < m == ref["input_points"].shape[0] < s0["raw_points"].shape[0]
+    want = ref["input_points"].astype(np.float32)
+    got = p4[:, :3].cpu().numpy()
+    ulp = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1 and (ulp == 0).mean() > 0.9999, (int(ulp.max()), float((ulp == 0).mean()))
+    assert np.array_equal(p4[:, 3].cpu().numpy().astype(np.int64), ref["time_indice"][:, 0])
+    for k in ("sd_labels", "fb_labels", "inst_labels"):
+        assert np.array_equal(labels[k].cpu().numpy(), ref[k]), k
+    assert np.array_equal(ego, ref["ego_motion_gt"]) and np.array_equal(inst, ref["inst_motion_gt"])
+    if ulp.max() == 0:
+        d = runner.build_input(p4, [m], labels=labels, reference_schema=True)
+        assert np.array_equal(d["coordinates"][:, 1:].cpu().numpy().astype(np.int32), ref["coordinates"])
+        assert np.array_equal(d["point_to_voxel_map"].cpu().numpy(), ref["point_to_voxel_map"])
+    # device-side jitter: same transform / scale, jitter bounded by the configured amplitude
+    np.random.seed(21)
+    q4, _, mq, _, _ = runner.prep_sample(s0, augment=True, exact_noise=False)
+    assert abs(mq - m) < 0.01 * m
+    # .npz files -> batch of two scenes == the two scenes run one by one
+    paths = []
+    for i, s in enumerate(samples):
+        paths.append(str(tmp_path / f"s{i}.npz"))
+        np.savez_compressed(paths[-1], **{("bbox_tsfm" if k == "inst_motion_gt" else k): v for k, v in s.items()}, sem_labels=s["sd_labels"])
+    torch.manual_seed(1)
+    both = runner.run_npz(paths)
+    n0 = int(both["fb_est_per_points"].shape[0])
+    torch.manual_seed(1)
+    first = runner.run_npz(paths[0])
+    k0 = int(first["fb_est_per_points"].shape[0])
+    assert 0 < k0 < n0 and both["ego_motion_est"].shape[0] == 2
+    assert torch.equal(both["fb_est_per_points"][:k0], first["fb_est_per_points"])
+    assert torch.equal(both["transformed_points"][:k0], first["transformed_points"])
+    assert torch.equal(both["ego_motion_est"][0], first["ego_motion_est"][0])

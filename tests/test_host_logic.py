@@ -234,3 +234,44 @@ def test_tensor_core_weight_packs_reconstruct_the_weights():
     lin = torch.nn.Linear(48, 24)
     s = tc_pack.split_tf32(lin.weight)
     assert s.shape == (48, 48) and torch.equal(s[:24] + s[24:], lin.weight.detach())
+
+
+def test_dataset_helpers_replay_the_reference_random_stream(tmp_path):
+    """pcaccumulation_b200/dataset.py: sample_augmentation draws from numpy's global stream in the order of
+    libs/dataset.py:101-111,90-98 (so a seeded run reproduces the oracle's = the reference's augmentation), the ground-truth
+    motions are conjugated like :113-133, and load_sample reads the reference's .npz sample format."""
+    from oracle import oracle
+    from pcaccumulation_b200 import config
+    from pcaccumulation_b200 import dataset as ds
+
+    cfg = config.workload_config("C1")
+    T = cfg["data"]["n_frames"]
+    rng = np.random.default_rng(0)
+    raw = rng.uniform(-30, 30, (500, 3)).astype(np.float32)
+    raw[:, 2] = rng.uniform(0.5, 5, 500)
+    tt = np.sort(rng.integers(0, T, 500))
+    lab = rng.integers(0, 2, 500)
+    ego = np.stack([np.eye(4) for _ in range(T)]).astype(np.float32)
+    ego[:, 1, 3] = np.arange(T) * 0.3
+    inst = np.stack([ego, ego[::-1].copy()])
+    np.random.seed(4)
+    want = oracle.prep_input_augmented(raw.copy(), tt, lab, lab, lab, ego.copy(), inst.copy(), cfg)
+    np.random.seed(4)
+    aug = ds.sample_augmentation(cfg["data_aug"], 500)
+    e2, i2 = ds.update_transformation_after_data_augmentation(aug["tsfm"], ego, inst, T)
+    assert np.array_equal(e2, want["ego_motion_gt"]) and np.array_equal(i2, want["inst_motion_gt"])
+    # the host-side formula of the augmentation with those numbers gives the oracle's points (the device kernel applies the same)
+    p = (aug["tsfm"][:3, :3] @ raw.T + aug["tsfm"][:3, 3][:, None]).T
+    p += (aug["noise"] - 0.5) * aug["noise_amp"]
+    p = p * aug["scale"]
+    keep = (np.abs(p[:, 0]) < 32) & (np.abs(p[:, 1]) < 32) & (p[:, 2] < 6) & (p[:, 2] > -2) & (p[:, 2] > 0.34)
+    assert np.array_equal(p[keep], want["input_points"])
+    # device-generator variant: same stream positions for everything except the jitter
+    np.random.seed(4)
+    aug2 = ds.sample_augmentation(cfg["data_aug"], 500, exact_noise=False)
+    assert np.array_equal(aug2["tsfm"], aug["tsfm"]) and aug2["noise"] is None
+    path = str(tmp_path / "sample.npz")
+    np.savez_compressed(path, raw_points=raw, time_indice=tt, sd_labels=lab, fb_labels=lab, inst_labels=lab, sem_labels=lab,
+                        ego_motion_gt=ego, bbox_tsfm=inst)
+    s = ds.load_sample(path)
+    assert np.array_equal(s["raw_points"], raw) and np.array_equal(s["inst_motion_gt"], inst) and s["data_path"] == path

@@ -268,6 +268,25 @@ def test_eval_tail_and_data_prep_restatements_match_reference_when_present(tmp_p
     for k in ("input_points", "num_points", "time_indice", "sd_labels", "inst_labels", "fb_labels", "coordinates", "num_voxels",
               "shape", "point_to_voxel_map"):
         assert np.array_equal(np.asarray(want[k]), np.asarray(got[k])), k
+    # the same WITH the training-time augmentation (step 1), replayed from the same seed of numpy's global stream
+    da = cfg["data_aug"]
+    fake_aug = types.SimpleNamespace(**vars(fake))
+    fake_aug.augmentation = True
+    fake_aug.augment_noise, fake_aug.augment_shift_range = da["augment_noise"], da["augment_shift_range"]
+    fake_aug.augment_scale_min, fake_aug.augment_scale_max, fake_aug.rot_aug = da["augment_scale_min"], da["augment_scale_max"], da["rot_aug"]
+    for name in ("_sample_random_tsfm", "apply_data_augmentation", "update_transformation_after_data_augmentation"):
+        setattr(fake_aug, name, types.MethodType(getattr(ds.BaseDataset, name), fake_aug))
+    ego_m = np.stack([np.eye(4) for _ in range(T)]).astype(np.float32)
+    ego_m[:, 0, 3] = np.arange(T) * 0.7
+    inst_m = np.stack([ego_m, ego_m[::-1].copy()])
+    np.random.seed(11)
+    want = ds.BaseDataset.prep_input(fake_aug, raw.copy(), lab, lab, lab, tt, ego_m.copy(), inst_m.copy())
+    np.random.seed(11)
+    got = oracle.prep_input_augmented(raw.copy(), tt, lab, lab, lab, ego_m.copy(), inst_m.copy(), cfg)
+    assert want["input_points"].dtype == np.float64 and 0 < want["input_points"].shape[0] < raw.shape[0]
+    for k in ("input_points", "num_points", "time_indice", "sd_labels", "inst_labels", "fb_labels", "coordinates", "num_voxels",
+              "shape", "point_to_voxel_map", "ego_motion_gt", "inst_motion_gt"):
+        assert np.array_equal(np.asarray(want[k]), np.asarray(got[k])), k
 
 
 def test_eval_tail_and_data_prep_match_reference_golden():
