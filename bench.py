@@ -325,6 +325,25 @@ def main():
         args.warmup = 3
 
     torch.set_num_threads(1)  # the GPU arm's host logic is single-threaded (OpenMP fan-out only slows torch.randperm)
+    # how host threads wait for the GPU.  Measured on a B200 box restricted to 4 host cores (what a rank gets at 8 ranks on 32
+    # cores): spinning (the driver's default) 262 scenes/s, yielding 262, interrupt-driven blocking 234-242 -- the wake-up
+    # latency of ~5 readbacks per scene costs more than the spinning threads do, so the default stays; PCAB_HOST_SYNC overrides.
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    cores_per_rank = cores // max(1, env_int("LOCAL_WORLD_SIZE", world))
+    sync_mode = os.environ.get("PCAB_HOST_SYNC", "auto")
+    if sync_mode == "auto":
+        sync_mode = "default"
+    if sync_mode != "default":
+        from pcaccumulation_b200.runner import set_host_sync_mode
+
+        rc = set_host_sync_mode(sync_mode)
+        if rc != 0:
+            print(f"bench.py: cudaSetDeviceFlags({sync_mode}) -> {rc}", file=sys.stderr)
+    args.host_sync = sync_mode
+    args.cores_per_rank = cores_per_rank
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     import torch.distributed as dist
@@ -525,7 +544,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_desc(args.workload), "batch": arm.batch, "mode": "test",
                        "step": f"one batch of {main_m['scenes_per_step']} independent scenes", "scenes_per_step": main_m["scenes_per_step"],
-                       "distinct_scenes_per_rank": N_SCENES, "scenes_in_flight": max(1, args.in_flight),
+                       "distinct_scenes_per_rank": N_SCENES, "scenes_in_flight": max(1, args.in_flight), "host_sync": args.host_sync, "host_cores_per_rank": args.cores_per_rank,
                        "timed_region_s": main_m["timed_s"], "timed_region_s_e2e": main_m["timed_s_e2e"],
                        "serial_ms_per_forward": ms_serial, "parallelism": f"dp{world} (scene sharding, no data-path collective)",
                        "l2": "per-scene working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",

@@ -15,6 +15,22 @@ from .motionnet import MotionNet
 from .voxel_generator import Voxelization
 
 
+def set_host_sync_mode(mode="blocking"):
+    """How host threads wait for the GPU (readbacks, event waits): ``"blocking"`` sleeps on an interrupt
+    (cudaDeviceScheduleBlockingSync), ``"spin"`` busy-waits (cudaDeviceScheduleSpin), ``"yield"`` yields its time slice.
+    With several scenes in flight per GPU and several ranks per node, spinning waiters compete with the threads that have
+    launches to issue: a rank with fewer host cores than (scenes in flight + 2) should block.  Must be called before the
+    process creates its CUDA context (i.e. before the first CUDA call of torch).  Returns the cudart status (0 = applied)."""
+    import ctypes
+
+    flags = {"spin": 1, "yield": 2, "blocking": 4}[mode]
+    try:
+        cudart = ctypes.CDLL("libcudart.so.12")
+    except OSError:
+        cudart = ctypes.CDLL("libcudart.so")
+    return int(cudart.cudaSetDeviceFlags(ctypes.c_uint(flags)))
+
+
 class SceneRunner:
     def __init__(self, cfg, model=None, device="cuda"):
         self.cfg = cfg
