@@ -123,16 +123,15 @@ __global__ void __launch_bounds__(256) k_warp(const float* __restrict__ bev, con
   const int C = 4 * C4;
   int lane_c = threadIdx.x % C4;  // threads of a pixel cover its channels (four each)
   int pix_per_block = blockDim.x / C4;
-  for (long long pix = (long long)blockIdx.x * pix_per_block + threadIdx.x / C4; pix < total;
-       pix += (long long)gridDim.x * pix_per_block) {
+  // One pixel: the four taps are fetched unconditionally from clamped coordinates with the weight of an out-of-image tap set
+  // to zero (fma(s, 0, r) == r for the finite s that is read instead), so all loads of a pixel -- and of the second pixel
+  // handled in the same iteration -- are in flight together; the accumulation order (and the result bits) is unchanged.
+  auto one = [&](long long pix) {
     int x = (int)(pix % W);
     int y = (int)((pix / W) % H);
     int f = (int)(pix / ((long long)W * H));
     int b = f / T, t = f % T;
-    if (t == 0) {
-      p16::st4<P16>(out, (size_t)pix, C, 4 * lane_c, p16::ld4<P16>(bev, ((size_t)(b * T + T - 1) * H + y) * W + x, C, 4 * lane_c));
-      continue;
-    }
+    if (t == 0) return p16::ld4<P16>(bev, ((size_t)(b * T + T - 1) * H + y) * W + x, C, 4 * lane_c);
     const float* iv = s_inv[f];
     float gx = ((float)x + 0.5f) * vx + x_min;
     float gy = ((float)y + 0.5f) * vy + y_min;
@@ -144,20 +143,32 @@ __global__ void __launch_bounds__(256) k_warp(const float* __restrict__ bev, con
     float wx0 = (fx0 + 1.f) - ix, wx1 = ix - fx0, wy0 = (fy0 + 1.f) - iy, wy1 = iy - fy0;
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
     if (fx0 >= -1.f && fx0 <= (float)W && fy0 >= -1.f && fy0 <= (float)H) {
-      int x0 = (int)fx0, y0 = (int)fy0;
+      const int x0 = (int)fx0, y0 = (int)fy0;
       const size_t fbase = (size_t)f * H * W;
-      auto tap = [&](int xx, int yy, float wgt) {
-        if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
-          const float4 s = p16::ld4<P16>(bev, fbase + (size_t)yy * W + xx, C, 4 * lane_c);
-          r.x = fmaf(s.x, wgt, r.x), r.y = fmaf(s.y, wgt, r.y), r.z = fmaf(s.z, wgt, r.z), r.w = fmaf(s.w, wgt, r.w);
-        }
+      const bool xa = x0 >= 0 && x0 < W, xb = x0 + 1 >= 0 && x0 + 1 < W, ya = y0 >= 0 && y0 < H, yb = y0 + 1 >= 0 && y0 + 1 < H;
+      const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1), cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
+      const float4 s00 = p16::ld4<P16>(bev, fbase + (size_t)cy0 * W + cx0, C, 4 * lane_c);
+      const float4 s01 = p16::ld4<P16>(bev, fbase + (size_t)cy0 * W + cx1, C, 4 * lane_c);
+      const float4 s10 = p16::ld4<P16>(bev, fbase + (size_t)cy1 * W + cx0, C, 4 * lane_c);
+      const float4 s11 = p16::ld4<P16>(bev, fbase + (size_t)cy1 * W + cx1, C, 4 * lane_c);
+      auto acc = [&](const float4& s, float wgt, bool ok) {
+        if (ok) r.x = fmaf(s.x, wgt, r.x), r.y = fmaf(s.y, wgt, r.y), r.z = fmaf(s.z, wgt, r.z), r.w = fmaf(s.w, wgt, r.w);
       };
-      tap(x0, y0, wx0 * wy0);
-      tap(x0 + 1, y0, wx1 * wy0);
-      tap(x0, y0 + 1, wx0 * wy1);
-      tap(x0 + 1, y0 + 1, wx1 * wy1);
+      acc(s00, wx0 * wy0, xa && ya);
+      acc(s01, wx1 * wy0, xb && ya);
+      acc(s10, wx0 * wy1, xa && yb);
+      acc(s11, wx1 * wy1, xb && yb);
     }
-    p16::st4<P16>(out, (size_t)pix, C, 4 * lane_c, r);
+    return r;
+  };
+  const long long step = (long long)gridDim.x * pix_per_block;
+  for (long long pix = (long long)blockIdx.x * pix_per_block + threadIdx.x / C4; pix < total; pix += 2 * step) {
+    const long long pix2 = pix + step;
+    const float4 r0 = one(pix);
+    float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pix2 < total) r1 = one(pix2);
+    p16::st4<P16>(out, (size_t)pix, C, 4 * lane_c, r0);
+    if (pix2 < total) p16::st4<P16>(out, (size_t)pix2, C, 4 * lane_c, r1);
   }
 }
 

@@ -116,23 +116,61 @@ __device__ __forceinline__ int lower_bound(const unsigned int* a, int n, unsigne
   return lo;
 }
 
-// Neighbour search is shared by FOUR lanes per point: lane `part` walks cells part, part+4, part+8 of the 3x3 block, so
-// the serial scan per thread is a quarter as long and four times as many warps are resident to hide its latency
-// (a scene has only ~10^4..10^5 de-duplicated dynamic points: one thread per point leaves the SMs nearly empty).
+// Neighbour search is shared by FOUR lanes per point (a scene has only ~10^4..10^5 de-duplicated dynamic points: one thread
+// per point leaves the SMs nearly empty).  The three cells (cx-1 .. cx+1) of a grid row are consecutive keys, so the 3x3
+// block is THREE contiguous ranges of the cell-sorted order: k_ranges finds them once per point (6 binary searches) and every
+// pass re-reads the 6 ints instead of searching 9 cells again; the four lanes stride through each range together, reading the
+// cell-sorted copy of the coordinates (coalesced).  The float64 distance test of sklearn is only evaluated for pairs within
+// 1e-5 (relative) of the radius; everything else is decided by a float32 squared distance whose rounding error is < 1e-6.
 constexpr int kParts = 4;
 
+struct NbrCtx {
+  const float* pxy;         // coordinates by point id
+  const float2* pxy_s;      // the same in cell-sorted order
+  const int* cval_sorted;   // point id of a sorted slot
+  const int* rng;           // [U][6]: (begin, end) of the three cell rows around a point
+  double eps;
+  float eps2_lo, eps2_hi;
+};
+
 template <typename F>
-__device__ __forceinline__ void for_neighbors(int u, const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
-                                              const int* __restrict__ cval_sorted, int U, unsigned int mykey, double eps,
-                                              int part, F&& fn) {
-  int cx = mykey & 0xffff, cy = mykey >> 16;
-  double x = pxy[2 * u], y = pxy[2 * u + 1];
-  for (int c = part; c < 9; c += kParts) {
-    unsigned int k = cell_key(cx + (c % 3) - 1, cy + (c / 3) - 1);
-    for (int j = lower_bound(ckey_sorted, U, k); j < U && ckey_sorted[j] == k; ++j) {
-      int v = cval_sorted[j];
-      double ex = (double)pxy[2 * v] - x, ey = (double)pxy[2 * v + 1] - y;
-      if (sqrt(ex * ex + ey * ey) <= eps) fn(v);
+__device__ __forceinline__ void for_neighbors(int u, const NbrCtx& c, int part, F&& fn) {
+  const float xf = c.pxy[2 * u], yf = c.pxy[2 * u + 1];
+  const double x = xf, y = yf;
+  const int2* r = reinterpret_cast<const int2*>(c.rng + 6 * (size_t)u);
+#pragma unroll
+  for (int row = 0; row < 3; ++row) {
+    const int2 ab = r[row];
+    for (int j = ab.x + part; j < ab.y; j += kParts) {
+      const float2 q = c.pxy_s[j];
+      const float ex = q.x - xf, ey = q.y - yf;
+      const float d2 = ex * ex + ey * ey;
+      bool in = d2 < c.eps2_lo;
+      if (!in && d2 <= c.eps2_hi) {
+        const double dx = (double)q.x - x, dy = (double)q.y - y;
+        in = sqrt(dx * dx + dy * dy) <= c.eps;
+      }
+      if (in) fn(c.cval_sorted[j]);
+    }
+  }
+}
+
+// cell-sorted coordinates + the three row ranges of every point (slot j of the sorted order = point cval_sorted[j])
+__global__ void k_ranges(const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
+                         const int* __restrict__ cval_sorted, const Counts* __restrict__ cnt, float2* __restrict__ pxy_s,
+                         int* __restrict__ rng, int* __restrict__ key_of) {
+  const int U = cnt->n_unique;
+  const int stride = gridDim.x * blockDim.x;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 3 * U; t += stride) {
+    const int j = t / 3, row = t % 3;
+    const int u = cval_sorted[j];
+    const unsigned int key = ckey_sorted[j];
+    const int cx = key & 0xffff, cy = key >> 16;
+    rng[6 * (size_t)u + 2 * row] = lower_bound(ckey_sorted, U, cell_key(cx - 1, cy + row - 1));
+    rng[6 * (size_t)u + 2 * row + 1] = lower_bound(ckey_sorted, U, cell_key(cx + 2, cy + row - 1));
+    if (row == 0) {
+      pxy_s[j] = make_float2(pxy[2 * u], pxy[2 * u + 1]);
+      key_of[u] = (int)key;
     }
   }
 }
@@ -155,20 +193,14 @@ __device__ __forceinline__ int group_min(int v) {
   return v;
 }
 
-__global__ void k_core(const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
-                       const int* __restrict__ cval_sorted, const Counts* __restrict__ cnt, double eps, int min_samples,
-                       int* __restrict__ key_of /* unsorted cell key per point */, int* __restrict__ core,
+__global__ void k_core(NbrCtx nc, const Counts* __restrict__ cnt, int min_samples, int* __restrict__ core,
                        int* __restrict__ parent) {
   const int U = cnt->n_unique;
-  PCAB_GROUP_LOOP(j, ok, part, U) {
-    int c = 0, u = 0;
-    if (ok) {
-      u = cval_sorted[j];
-      for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, ckey_sorted[j], eps, part, [&](int) { ++c; });
-    }
+  PCAB_GROUP_LOOP(u, ok, part, U) {
+    int c = 0;
+    if (ok) for_neighbors(u, nc, part, [&](int) { ++c; });
     c = group_sum(c);
     if (ok && part == 0) {
-      key_of[u] = (int)ckey_sorted[j];
       core[u] = c >= min_samples;
       parent[u] = u;
     }
@@ -203,15 +235,13 @@ __device__ __forceinline__ int uf_union(int* parent, int a, int b) {
 // Hooking pass: every core point points at its lowest-index core neighbour (itself included).  Pointers only go to
 // smaller indices, so this is a forest; after k_roots has flattened it, a dense cluster consists of a handful of trees
 // (one per local index minimum) and k_union only has to stitch those together.
-__global__ void k_hook_min(const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
-                           const int* __restrict__ cval_sorted, const Counts* __restrict__ cnt, double eps,
-                           const int* __restrict__ key_of, const int* __restrict__ core, int* __restrict__ parent) {
+__global__ void k_hook_min(NbrCtx nc, const Counts* __restrict__ cnt, const int* __restrict__ core, int* __restrict__ parent) {
   const int U = cnt->n_unique;
   PCAB_GROUP_LOOP(u, ok, part, U) {
     int m = INT_MAX;
     const bool is_core = ok && core[u];
     if (is_core)
-      for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, (unsigned int)key_of[u], eps, part, [&](int v) {
+      for_neighbors(u, nc, part, [&](int v) {
         if (core[v]) m = min(m, v);
       });
     m = group_min(m);
@@ -222,17 +252,18 @@ __global__ void k_hook_min(const float* __restrict__ pxy, const unsigned int* __
 // Stitching pass over the flattened forest: a lane remembers the root its point started under (r0) and its current root
 // (ru) and skips every neighbour whose parent pointer equals either - one L2 load per pair.  Only pairs that straddle two
 // trees reach the union-find proper (two dependent pointer chases and a CAS attempt).
-__global__ void k_union(const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
-                        const int* __restrict__ cval_sorted, const Counts* __restrict__ cnt, double eps,
-                        const int* __restrict__ key_of, const int* __restrict__ core, int* parent) {
+__global__ void k_union(NbrCtx nc, const Counts* __restrict__ cnt, const int* __restrict__ core, int* parent) {
   const int U = cnt->n_unique;
   PCAB_GROUP_LOOP(u, ok, part, U) {
     if (!ok || !core[u]) continue;
     const int r0 = __ldcg(parent + u);
     int ru = r0;
-    for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, (unsigned int)key_of[u], eps, part, [&](int v) {
+    for_neighbors(u, nc, part, [&](int v) {
       if (v < u && core[v]) {
-        int pv = __ldcg(parent + v);
+        // pre-check through L1: a stale line can only show an OLDER parent of v, and "parent[v] was ru (or r0) at some moment"
+        // already proves that v is in u's component (components only ever merge), so skipping on it is safe; a mismatch goes
+        // to the union-find proper, which reads through L2
+        int pv = parent[v];
         if (pv != ru && pv != r0) ru = uf_union(parent, ru, pv);
       }
     });
@@ -259,16 +290,15 @@ __global__ void k_roots(const Counts* __restrict__ cnt, const int* __restrict__ 
 }
 
 // label[u]: core -> cluster number of its root; border -> min cluster number among core neighbours; noise -> -1
-__global__ void k_labels(const float* __restrict__ pxy, const unsigned int* __restrict__ ckey_sorted,
-                         const int* __restrict__ cval_sorted, Counts* cnt, double eps, const int* __restrict__ key_of,
-                         const int* __restrict__ core, const int* __restrict__ parent, const int* __restrict__ root_rank,
-                         const int* __restrict__ is_root, int cap, int* __restrict__ label, int* __restrict__ size) {
+__global__ void k_labels(NbrCtx nc, Counts* cnt, const int* __restrict__ core, const int* __restrict__ parent,
+                         const int* __restrict__ root_rank, const int* __restrict__ is_root, int cap, int* __restrict__ label,
+                         int* __restrict__ size) {
   const int U = cnt->n_unique;
   PCAB_GROUP_LOOP(u, ok, part, U) {
     int best = INT_MAX;
     const bool is_core = ok && core[u];
     if (ok && !is_core)
-      for_neighbors(u, pxy, ckey_sorted, cval_sorted, U, (unsigned int)key_of[u], eps, part, [&](int v) {
+      for_neighbors(u, nc, part, [&](int v) {
         if (core[v]) best = min(best, root_rank[parent[v]]);
       });
     best = group_min(best);
@@ -314,9 +344,9 @@ extern "C" size_t pcab_cluster_workspace(int s) {
   if (scan > tmp) tmp = scan;
   // must mirror the take() sequence of pcab_cluster_scene: q, c (12 B/row) | key, key_s (8) | val, val_s, head, rank (4) |
   // pxy (8) | spare, inverse, ckey, ckey_s, cval, cval_s, key_of, core, parent, is_root, root_rank, label, size, keep,
-  // keep_rank (15 x 4) | counts | sort/scan temp
+  // keep_rank (15 x 4) | pxy_s (8) | rng (24) | counts | sort/scan temp
   return 2 * alc((size_t)s * 12) + 2 * alc((size_t)s * 8) + 4 * alc((size_t)s * 4) + alc((size_t)s * 8) +
-         15 * alc((size_t)s * 4) + alc(sizeof(Counts)) + alc(tmp) + 1024;
+         15 * alc((size_t)s * 4) + alc((size_t)s * 8) + alc((size_t)s * 24) + alc(sizeof(Counts)) + alc(tmp) + 1024;
 }
 
 // flags[i] = argmax(mos[n0+i]) == 1 for i in [0, n)
@@ -364,6 +394,8 @@ extern "C" int pcab_cluster_scene(const float* transformed_points, const float* 
   int* size = (int*)take((size_t)s * 4);
   int* keep = (int*)take((size_t)s * 4);
   int* keep_rank = (int*)take((size_t)s * 4);
+  float2* pxy_s = (float2*)take((size_t)s * 8);
+  int* rng = (int*)take((size_t)s * 24);
   Counts* cnt = (Counts*)take(sizeof(Counts));
   size_t sort64 = 0, sort32 = 0, scan = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort64, key, key_s, val, val_s, s);
@@ -386,14 +418,18 @@ extern "C" int pcab_cluster_scene(const float* transformed_points, const float* 
   k_unique<<<g, B, 0, stream>>>(head, rank, val_s, q, s, pxy, inverse, cnt);
   k_cellkeys<<<g, B, 0, stream>>>(pxy, cnt, dedupe_voxel, (float)eps * 1.001f, s, ckey, cval);
   PCAB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, sort32, ckey, ckey_s, cval, cval_s, s, 0, 32, stream));
-  k_core<<<g4, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, min_samples, key_of, core, parent);
-  k_hook_min<<<g4, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, key_of, core, parent);
+  NbrCtx nc;
+  nc.pxy = pxy, nc.pxy_s = pxy_s, nc.cval_sorted = cval_s, nc.rng = rng, nc.eps = eps;
+  nc.eps2_lo = (float)(eps * eps * (1.0 - 1e-5)), nc.eps2_hi = (float)(eps * eps * (1.0 + 1e-5));
+  k_ranges<<<grid_for(3LL * s, B), B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, pxy_s, rng, key_of);
+  k_core<<<g4, B, 0, stream>>>(nc, cnt, min_samples, core, parent);
+  k_hook_min<<<g4, B, 0, stream>>>(nc, cnt, core, parent);
   k_roots<<<g, B, 0, stream>>>(cnt, core, parent, is_root, s);  // flatten the hooking forest
-  k_union<<<g4, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, key_of, core, parent);
+  k_union<<<g4, B, 0, stream>>>(nc, cnt, core, parent);
   k_roots<<<g, B, 0, stream>>>(cnt, core, parent, is_root, s);
   PCAB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, scan, is_root, root_rank, s, stream));
   PCAB_CUDA(cudaMemsetAsync(size, 0, (size_t)s * 4, stream));
-  k_labels<<<g4, B, 0, stream>>>(pxy, ckey_s, cval_s, cnt, eps, key_of, core, parent, root_rank, is_root, s, label, size);
+  k_labels<<<g4, B, 0, stream>>>(nc, cnt, core, parent, root_rank, is_root, s, label, size);
   k_keep<<<g, B, 0, stream>>>(size, cnt, min_p_cluster, s, keep);
   PCAB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, scan, keep, keep_rank, s, stream));
   k_final<<<g, B, 0, stream>>>(label, keep, keep_rank, inverse, sel, n0, s, s, cnt, inst_out);

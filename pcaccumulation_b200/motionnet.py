@@ -13,6 +13,8 @@ in pillar-sorted order so per-pillar reductions are contiguous ranges.
 import ctypes
 import math
 
+import numpy as np
+
 import torch
 import torch.nn as nn
 
@@ -281,9 +283,24 @@ class MotionNet(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):
         self._plist = None
+        self._static_weights = False
         return super()._apply(fn, *args, **kwargs)
 
+    def load_state_dict(self, *args, **kwargs):
+        self._static_weights = False
+        return super().load_state_dict(*args, **kwargs)
+
+    def freeze_weights(self, frozen=True):
+        """Serving mode: promise that the parameters stay as they are, so a forward reuses the packed kernel operands without
+        comparing the (storage, version) of all 195 tensors first (~0.15 ms of interpreter time per scene, held under the GIL
+        that the scenes in flight share).  ``load_state_dict`` / ``.to()`` / ``.half()`` lift the promise; in-place edits of a
+        parameter do NOT -- call ``freeze_weights(False)`` before making them."""
+        self._static_weights = bool(frozen) and self._packed is not None
+        return self
+
     def _weights(self):
+        if getattr(self, "_static_weights", False) and self._packed is not None:
+            return self._packed
         key = self._pack_key()
         if self._packed is not None and key == self._packed_key:
             return self._packed
@@ -484,6 +501,7 @@ class MotionNet(nn.Module):
                 self._graph_input(key, (B * T, Ny, Nx, 32), dev).zero_()
                 self._run_stack(key, fn, capture=True)
         torch.cuda.current_stream().synchronize()
+        self.freeze_weights()  # warmup() is the serving-mode entry: weights are static until load_state_dict / .to()
 
     # ------------------------------------------------------------------------------------------
     # convolution dispatch
@@ -944,21 +962,31 @@ class MotionNet(nn.Module):
             c[n:] = n - 1
             return c
 
-        choice = torch.empty(npairs, 2, N_KPTS, dtype=torch.int32)
-        pair_frames = torch.empty(npairs, 2, dtype=torch.int32)
-        thr2 = torch.empty(npairs, dtype=torch.float32)
-        chain_pair = torch.full((nF,), -1, dtype=torch.int32)
+        # keypoint choices, pair table, squared distance gates and chain table travel in ONE pinned int32 buffer / ONE copy
+        n_choice = npairs * 2 * N_KPTS
+        n_words = n_choice + 2 * npairs + npairs + nF
+        stage = getattr(self, "_ego_stage", None)
+        if stage is None or stage[0].numel() != n_words or stage[1].device != dev:
+            pin = torch.empty(n_words, dtype=torch.int32).pin_memory()
+            stage = self._ego_stage = (pin, torch.empty(n_words, dtype=torch.int32, device=dev), pin.numpy())
+        pin, dbuf, words = stage
+        choice = words[:n_choice].reshape(npairs, 2, N_KPTS)
+        pair_frames = words[n_choice:n_choice + 2 * npairs].reshape(npairs, 2)
+        thr2 = words[n_choice + 2 * npairs:n_choice + 3 * npairs].view(np.float32)
+        chain_pair = words[n_choice + 3 * npairs:]
+        chain_pair[:] = -1
         for p, (b, anchor, ref, duration) in enumerate(pairs):
-            choice[p, 0] = sample(counts[b * T + ref])
-            choice[p, 1] = sample(counts[b * T + anchor])
+            choice[p, 0] = sample(counts[b * T + ref]).numpy()
+            choice[p, 1] = sample(counts[b * T + anchor]).numpy()
             pair_frames[p, 0], pair_frames[p, 1] = b * T + ref, b * T + anchor
             thr2[p] = (duration * cfg["data"]["max_speed"]) ** 2
             if mode == "chain" or anchor == 0:
                 chain_pair[b * T + ref] = p
-        choice_d = choice.to(dev, non_blocking=True)
-        pair_frames_d = pair_frames.to(dev, non_blocking=True)
-        thr2_d = thr2.to(dev, non_blocking=True)
-        chain_pair_d = chain_pair.to(dev, non_blocking=True)
+        dbuf.copy_(pin, non_blocking=True)
+        choice_d = dbuf[:n_choice]
+        pair_frames_d = dbuf[n_choice:n_choice + 2 * npairs]
+        thr2_d = dbuf[n_choice + 2 * npairs:n_choice + 3 * npairs]
+        chain_pair_d = dbuf[n_choice + 3 * npairs:]
         perm = torch.empty(npairs, 1, N_KPTS, N_KPTS, device=dev)
         pose_pairs = torch.empty(npairs, 4, 4, device=dev)
         est = torch.empty(B, T, 4, 4, device=dev)
@@ -980,7 +1008,7 @@ class MotionNet(nn.Module):
         results["perm_matrix"] = [perm[p] for p in keep]
         results["ego_motion_est"], results["ego_motion_gt"] = est, gt
         if self.keep_stages:
-            self.stages.update(pose_pairs=pose_pairs, choice=choice, counts=counts)
+            self.stages.update(pose_pairs=pose_pairs, choice=torch.from_numpy(choice.copy()), counts=counts)
 
     def _ego_icp(self, est, gt, raw, B, T, scalars):
         """models/egomotion.py:9-28,360-384,439-441 (model.ego_icp): every frame's raw background points are registered to
