@@ -467,21 +467,36 @@ def main():
                 entry = {"workload": workload_desc(name), "value": m["value"], "e2e": m["e2e"], "unit": "scenes/s", "timed_s": m["timed_s"],
                          "scenes_timed": 3 * m["scenes_per_step"], "serial_ms_per_forward": s_ms, "batch": a2.batch}
                 if name == "C3":
-                    # Chamfer alone: pair evaluations per second of the brute-force kernel on the full cloud, both directions
+                    # Chamfer alone on the full cloud (est vs gt alignment: a small rigid motion apart), both directions: the exact
+                    # grid search the product uses and the every-pair kernel (the reference kernel's formulation) it is equal to
                     from pcaccumulation_b200.chamfer_distance import chamfer_with_indices
 
                     pts = a2.dev_pts[0][:, :3].contiguous()
-                    chamfer_with_indices(pts[None], pts[None].flip(1))
-                    torch.cuda.synchronize()
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    chamfer_with_indices(pts[None], pts[None].flip(1))
-                    e1.record()
-                    e1.synchronize()
+                    moved = (pts + torch.tensor([0.05, -0.02, 0.01], device=pts.device)).contiguous()
                     n = pts.shape[0]
-                    evals = 2.0 * n * n / (e0.elapsed_time(e1) * 1e-3)
-                    entry["chamfer"] = {"n": n, "m": n, "ms": e0.elapsed_time(e1), "pair_evals_per_s": evals, "fp32_flops_per_s": 8.0 * evals,
-                                        "note": "8 FP32 ops per pair; FP32 FMA-pipe peak measured 62-72 TFLOP/s (tools/ffma_bench.cu)"}
+
+                    def time_chamfer(brute, reps):
+                        chamfer_with_indices(pts[None], moved[None], brute=brute)
+                        torch.cuda.synchronize()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        for _ in range(reps):
+                            out = chamfer_with_indices(pts[None], moved[None], brute=brute)
+                        e1.record()
+                        e1.synchronize()
+                        return e0.elapsed_time(e1) / reps, out
+
+                    ms_grid, o_grid = time_chamfer(False, 10)
+                    ms_brute, o_brute = time_chamfer(True, 1)
+                    same = all(torch.equal(x, y) for x, y in zip(o_grid, o_brute))
+                    entry["chamfer"] = {
+                        "n": n, "m": n, "ms": ms_grid, "algorithmic_pair_evals_per_s": 2.0 * n * n / (ms_grid * 1e-3),
+                        "every_pair_kernel_ms": ms_brute, "every_pair_kernel_pair_evals_per_s": 2.0 * n * n / (ms_brute * 1e-3),
+                        "every_pair_kernel_fp32_flops_per_s": 8.0 * 2.0 * n * n / (ms_brute * 1e-3), "bit_identical": bool(same),
+                        "note": "grid search = exact nearest neighbour over a uniform grid (csrc/nn_grid.cu); every-pair kernel: 8 FP32 ops "
+                                "per pair against the FP32 FMA-pipe peak measured at 62-72 TFLOP/s (tools/ffma_bench.cu)"}
+                    if not same:
+                        raise SystemExit("bench.py: grid Chamfer differs from the every-pair kernel")
                 others[name] = entry
                 a2.close()
                 del a2
