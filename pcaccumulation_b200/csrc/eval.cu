@@ -14,7 +14,7 @@ namespace {
 
 constexpr int kCat = 3;   // 0: all points with t > 0, 1: dynamic (sd == 1), 2: "static" (fb == 1), as collect_scene_stats does
 constexpr int kSf = 6;    // count, sum epe, Acc3DS, Acc3DR, Outlier, ROutlier
-constexpr int kMos = 8;   // class 0/1: intersection, pred positives, gt positives ; [6] = masked points, [7] unused
+constexpr int kMos = 8;   // class 0/1: intersection, pred positives, gt positives ; [6] = masked points, [7] = rows with an out-of-range frame / instance index
 
 struct EvalArgs {
   const float* pts;
@@ -61,9 +61,15 @@ __global__ void __launch_bounds__(256) k_flow_eval(EvalArgs a) {
     const float x = a.pts[3 * i], y = a.pts[3 * i + 1], z = a.pts[3 * i + 2];
     const int t = a.tidx[i];
     float ex, ey, ez, gx, gy, gz;
+    const long long k = a.inst[i];
+    if (t < 0 || t >= a.T || k < 0 || k >= a.K) {
+      // the reference's gathers (toolbox/register_utils.py:66,85) raise an IndexError here: count the row (the host side
+      // raises from summary()) instead of reading out of bounds or silently evaluating against the wrong motion
+      mos[7] += 1;
+      a.epe[i] = a.rel[i] = __int_as_float(0x7fc00000);
+      continue;
+    }
     apply(a.ego_gt + (size_t)t * 16, x, y, z, ex, ey, ez);
-    long long k = a.inst[i];
-    k = k < 0 ? 0 : (k >= a.K ? a.K - 1 : k);
     apply(a.inst_gt + ((size_t)k * a.T + t) * 16, ex, ey, ez, gx, gy, gz);
     const float fx = __fsub_rn(__fsub_rn(a.rec[3 * i], x), __fsub_rn(gx, x));
     const float fy = __fsub_rn(__fsub_rn(a.rec[3 * i + 1], y), __fsub_rn(gy, y));

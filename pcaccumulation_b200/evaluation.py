@@ -58,8 +58,11 @@ class FlowEvaluator:
         """Sum the counters over the ranks of a scene-sharded run (the only collective of the path: a 26-number all-reduce,
         NCCL on GPUs / gloo in the CPU tests).  The per-point dumps stay rank-local, as the reference's per-scene files do."""
         from .dist_utils import reduce_metrics
+        if getattr(self, "_reduced", False):
+            raise RuntimeError("FlowEvaluator.all_reduce() was already called: the counters hold the global sums")
         self.sf = reduce_metrics(self.sf, op="sum")
         self.mos = reduce_metrics(self.mos, op="sum")
+        self._reduced = True
         return self
 
     def per_point_arrays(self):
@@ -69,6 +72,9 @@ class FlowEvaluator:
     def summary(self):
         sf = self.sf.cpu().numpy()
         mos = self.mos.cpu().numpy()
+        if int(mos[7]):
+            raise IndexError(f"{int(mos[7])} points carried a frame index outside [0, n_frames) or an instance label without a "
+                             "ground-truth motion (the reference's gathers raise at toolbox/register_utils.py:66,85)")
         out = {}
         for c, name in enumerate(CATEGORIES):
             n = max(sf[c, 0], 1.0)
@@ -113,7 +119,10 @@ class ClusterEvaluator:
 
     def all_reduce(self):
         from .dist_utils import reduce_metrics
+        if getattr(self, "_reduced", False):
+            raise RuntimeError("ClusterEvaluator.all_reduce() was already called: the counters hold the global sums")
         self.counters = reduce_metrics(self.counters, op="sum")
+        self._reduced = True
         return self
 
     def summary(self):

@@ -28,6 +28,10 @@ class Voxelization:
         points4 = points4.contiguous()
         dev = points4.device
         n = points4.shape[0]
+        if n == 0:  # nothing to voxelise: no launch, no readback of unwritten counters
+            z = lambda *shape: torch.zeros(*shape, dtype=torch.int32, device=dev)
+            return {"coordinates": z(0, 4), "pillar_batch": z(0), "point_to_voxel_map": z(0), "num_voxels": z(batch_size),
+                    "total_voxels": 0, "n_rejected": 0}
         cells = int(batch_size) * self.max_voxels
         m_cap = min(n, cells)
         coords = torch.empty(m_cap, 4, dtype=torch.int32, device=dev)

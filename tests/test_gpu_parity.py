@@ -698,6 +698,24 @@ def test_flow_evaluator_matches_oracle(fixture_weights):
     assert 0.0 <= summ["all"]["Acc3DS"] <= summ["all"]["Acc3DR"] <= 1.0 and summ["mos"]["masked_points"] == ref["mos"]["masked"]
     arrays = ev.per_point_arrays()
     assert arrays["epe_per_point"].dtype == np.float16 and arrays["epe_per_point"].shape[0] == int(sel.sum())
+    # rows whose frame index / instance label has no ground-truth motion: the reference's gathers raise an IndexError; the
+    # kernel counts them (no out-of-bounds read, no silent evaluation against another instance's motion), summary() raises
+    bad = dict(inp)
+    bad["inst_labels"] = inp["inst_labels"].clone()
+    bad["inst_labels"][:7, 0] = int(inp["inst_motion_gt"][0].shape[0]) + 3
+    bad["time_indice"] = inp["time_indice"].clone()
+    bad["time_indice"][7:10, 1] = T
+    with pytest.raises(IndexError):
+        oracle.flow_eval(bad, pred, T)
+    ev2 = FlowEvaluator(T)
+    epe2, _ = ev2.update(cuda_dict(bad), {k: v.cuda() for k, v in pred.items()})
+    assert int(ev2.mos.cpu()[7]) == 10 and bool(torch.isnan(epe2[:10]).all()) and bool(torch.isfinite(epe2[10:]).all())
+    with pytest.raises(IndexError):
+        ev2.summary()
+    # an empty cloud is not an error for the voxeliser
+    from pcaccumulation_b200.voxel_generator import Voxelization
+    e = Voxelization(vg).voxelize_batch(torch.empty(0, 4, device="cuda"))
+    assert e["total_voxels"] == 0 and e["coordinates"].shape == (0, 4) and e["n_rejected"] == 0
 
 
 # -------------------------------------------------------------------------------------------------------------
