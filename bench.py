@@ -325,6 +325,8 @@ def main():
         args.warmup = 3
 
     torch.set_num_threads(1)  # the GPU arm's host logic is single-threaded (OpenMP fan-out only slows torch.randperm)
+    if os.environ.get("PCAB_SWITCH_INTERVAL"):
+        sys.setswitchinterval(float(os.environ["PCAB_SWITCH_INTERVAL"]))
     # how host threads wait for the GPU.  Measured on a B200 box restricted to 4 host cores (what a rank gets at 8 ranks on 32
     # cores): spinning (the driver's default) 262 scenes/s, yielding 262, interrupt-driven blocking 234-242 -- the wake-up
     # latency of ~5 readbacks per scene costs more than the spinning threads do, so the default stays; PCAB_HOST_SYNC overrides.

@@ -1163,3 +1163,25 @@ def test_augmented_front_end_and_npz_batches(fixture_weights, tmp_path):
     assert torch.equal(both["fb_est_per_points"][:k0], first["fb_est_per_points"])
     assert torch.equal(both["transformed_points"][:k0], first["transformed_points"])
     assert torch.equal(both["ego_motion_est"][0], first["ego_motion_est"][0])
+
+
+def test_pillar_index_is_a_stable_sort_with_rejected_points_last(lib):
+    """pcab_pillar_index: only the significant bits of the pillar ids are sorted; points the voxeliser rejected (id -1) must
+    still come out as one run behind the last pillar, and equal ids keep their stream order (bit-identical pillar means)."""
+    from pcaccumulation_b200._lib import I, P, Z, call, scratch, size, stream
+
+    rng = np.random.default_rng(12)
+    for n, m in ((5000, 37), (200_000, 70_000), (64, 1), (300_000, 262_144)):
+        ids = rng.integers(0, m, n).astype(np.int32)
+        ids[rng.random(n) < 0.05] = -1
+        ids[: min(n, m)] = np.arange(min(n, m))  # every pillar occupied (ids < m)
+        p2v = torch.tensor(ids).cuda()
+        order = torch.empty(n, dtype=torch.int32, device="cuda")
+        pstart = torch.empty(m + 1, dtype=torch.int32, device="cuda")
+        ws = scratch(size("pcab_pillar_index_workspace", I(n)), torch.device("cuda"))
+        call("pcab_pillar_index", P(p2v), I(n), I(m), P(order), P(pstart), P(ws), Z(ws.numel()), stream())
+        key = np.where(ids < 0, m, ids)
+        want = np.argsort(key, kind="stable").astype(np.int32)
+        assert np.array_equal(order.cpu().numpy(), want), (n, m)
+        starts = np.searchsorted(key[want], np.arange(m + 1), side="left").astype(np.int32)
+        assert np.array_equal(pstart.cpu().numpy(), starts), (n, m)
