@@ -2,9 +2,9 @@
 """Benchmark: scenes/sec of the per-scene hot path (voxelise -> MotionNet.forward, test mode) on B200.
 
 Contract (one JSON line on rank 0):  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C2]
-  * a "step" is one BATCH of ``--scenes-per-step`` (default 24) independent scenes of the workload through the full
+  * a "step" is one BATCH of ``--scenes-per-step`` (default 32) independent scenes of the workload through the full
     pipeline (voxelise + forward), ``--in-flight`` of them at a time per GPU; W warm-up steps, then EXACTLY K timed steps
-    (K = 20 -> 480 scenes, > 2 s of device time).  At N > 1 each rank processes its own scenes (no data-path collective,
+    (K = 20 -> 640 scenes, > 2 s of device time).  At N > 1 each rank processes its own scenes (no data-path collective,
     weak scaling) and the time is the max over ranks (NCCL all-reduce of the CUDA-event time);
   * workloads = BASELINE.json configs: C2 (default, the configuration the metric is quoted on) Waymo-shaped 5 x ~150k points,
     288^2; C3 nuScenes-shaped 10 x 35k + the Chamfer alignment errors of models/tpointnet.py:145-163 on the full cloud inside
@@ -302,7 +302,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--scenes-per-step", type=int, default=24, help="independent scenes per step (one step = one batch of scenes)")
+    ap.add_argument("--scenes-per-step", type=int, default=32, help="independent scenes per step (one step = one batch of scenes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short C3 / C4 / C5 measurements of the default run")
