@@ -1020,12 +1020,15 @@ class MotionNet(nn.Module):
         bg = fb_pp[:, 0] == 0
         frame_t = pframe % T
         src_problem = torch.where(bg & (frame_t > 0), pframe, torch.full_like(pframe, -1)).to(torch.int32).contiguous()
-        tgt_group = torch.where(bg & (frame_t == 0), pframe // T, torch.full_like(pframe, -1)).to(torch.int32).contiguous()
+        # targets: only the anchor frames' background points go into the search grid (a fifth of the cloud at T = 5)
+        anchor = bg & (frame_t == 0)
+        tgt = pts[anchor].contiguous()
+        tgt_group = (pframe[anchor] // T).to(torch.int32).contiguous()
         problem_group = (torch.arange(B * T, device=dev, dtype=torch.int32) // T).contiguous()
         refined = torch.empty(B, T, 4, 4, device=dev)
-        n = pts.shape[0]
-        ws = scratch(size("pcab_icp_workspace", I(n), I(B * T)), dev)
-        call("pcab_icp_point_to_point", P(pts), P(src_problem), I(n), P(pts), P(tgt_group), I(n), P(problem_group), I(B * T),
+        n, m = pts.shape[0], tgt.shape[0]
+        ws = scratch(size("pcab_icp_workspace", I(m), I(B * T)), dev)
+        call("pcab_icp_point_to_point", P(pts), P(src_problem), I(n), P(tgt), P(tgt_group), I(m), P(problem_group), I(B * T),
              P(est.contiguous()), F(pe["icp_threshold"]), I(pe["icp_max_iter"]), F(1e-6), F(1e-6), P(refined), P(None), P(ws),
              Z(ws.numel()), stream())
         call("pcab_ego_pose_errors", P(refined), P(gt), I(B), I(T), P(scalars[2:4]), stream())
