@@ -230,6 +230,8 @@ __device__ __forceinline__ void apply34(const float* M, float x, float y, float 
   oz = M[8] * x + M[9] * y + M[10] * z + M[11];
 }
 
+constexpr int kRep = 64;  // replicas of the per-instance sums (contention of the double atomics)
+
 // rec = bbox_tsfm[inst, t] (ego_gt[b, t] p): sums per (scene, instance)
 __global__ void k_offset_centres(const float* __restrict__ pts, const int* __restrict__ pbatch, const int* __restrict__ ptime,
                                  const long long* __restrict__ inst, const float* __restrict__ ego_gt,
@@ -252,10 +254,20 @@ __global__ void k_offset_centres(const float* __restrict__ pts, const int* __res
       an += 1.0;
     }
     if ((int)(threadIdx.x & 31) == leader) {
-      double* s = sums + 4 * k;
+      // ... and the warps spread over kRep replicas of the table (the background instance alone collects ~10^5 warp sums)
+      double* s = sums + 4 * ((size_t)k * kRep + ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (kRep - 1)));
       atomicAdd(s, ax), atomicAdd(s + 1, ay), atomicAdd(s + 2, az), atomicAdd(s + 3, an);
     }
   }
+}
+
+__global__ void k_offset_fold(const double* __restrict__ rep, int k_total, double* __restrict__ sums) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 4 * k_total) return;
+  const int k = t >> 2, c = t & 3;
+  double a = 0;
+  for (int r = 0; r < kRep; ++r) a += rep[4 * ((size_t)k * kRep + r) + c];  // fixed order: the centres do not depend on timing
+  sums[t] = a;
 }
 
 // acc: sum |dx|, sum |dy|, sum |d|_2, sum (1 - cos), count
@@ -402,7 +414,10 @@ extern "C" int pcab_seg_loss_grad(const float* logits, int hw, const long long* 
   return PCAB_OK;
 }
 
-extern "C" size_t pcab_offset_loss_workspace(int n_instances_total) { return al((size_t)(n_instances_total > 0 ? n_instances_total : 1) * 32) + al(64) + 256; }
+extern "C" size_t pcab_offset_loss_workspace(int n_instances_total) {
+  const size_t k = (size_t)(n_instances_total > 0 ? n_instances_total : 1);
+  return al(k * 32) + al(k * kRep * 32) + al(64) + 256;
+}
 
 // out4 = {offset_norm_loss, offset_dir_loss, offset_l2_error, n_foreground}; gt_offset [N,2] (every point; the reference keeps
 // the rows of the foreground points as predictions['offset_gt']) may be NULL
@@ -415,11 +430,13 @@ extern "C" int pcab_offset_loss(const float* points, const int* point_batch, con
   PCAB_REQUIRE(workspace_bytes >= pcab_offset_loss_workspace(n_instances_total), "workspace too small");
   char* base = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   double* sums = (double*)base;
-  double* acc = (double*)(base + al((size_t)n_instances_total * 32));
-  PCAB_CUDA(cudaMemsetAsync(sums, 0, (size_t)n_instances_total * 32, stream));
+  double* rep = (double*)(base + al((size_t)n_instances_total * 32));
+  double* acc = (double*)(base + al((size_t)n_instances_total * 32) + al((size_t)n_instances_total * kRep * 32));
+  PCAB_CUDA(cudaMemsetAsync(rep, 0, (size_t)n_instances_total * kRep * 32, stream));
   PCAB_CUDA(cudaMemsetAsync(acc, 0, 64, stream));
   k_offset_centres<<<grid_for(n_points, 256), 256, 0, stream>>>(points, point_batch, point_time, inst_labels, ego_motion_gt,
-                                                               inst_motion_gt, inst_offset, T, n_points, sums);
+                                                               inst_motion_gt, inst_offset, T, n_points, rep);
+  k_offset_fold<<<cdiv(4LL * n_instances_total, 128), 128, 0, stream>>>(rep, n_instances_total, sums);
   k_offset_terms<<<grid_for(n_points, 256), 256, 0, stream>>>(point_batch, inst_labels, fb_labels, inst_offset, sums, transformed_points,
                                                              offset_est, n_points, gt_offset, acc);
   k_offset_final<<<1, 1, 0, stream>>>(acc, out4);
