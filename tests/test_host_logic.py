@@ -144,9 +144,22 @@ def _gloo_eval_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ev = FlowEvaluator(5, device="cpu", keep_per_point=False)  # counters only: no kernel call in this test
     ev.sf += torch.arange(18, dtype=torch.float64).view(3, 6) * (rank + 1)
-    ev.mos += torch.arange(8) * (10 ** rank)
+    m = torch.arange(8)
+    m[7] = 0  # [7] counts rows with an out-of-range frame / instance index: summary() raises when it is not zero
+    ev.mos += m * (10 ** rank)
     ev.all_reduce()
     q.put((rank, ev.sf.tolist(), ev.mos.tolist(), ev.summary()["all"]["count"]))
+    try:
+        ev.all_reduce()  # the counters already hold the global sums
+        q.put((rank, "second all_reduce did not raise"))
+    except RuntimeError:
+        pass
+    ev.mos[7] = 3
+    try:
+        ev.summary()
+        q.put((rank, "summary() accepted invalid rows"))
+    except IndexError:
+        pass
     dist.destroy_process_group()
 
 
@@ -163,8 +176,11 @@ def test_flow_evaluator_counters_all_reduce_gloo_world2():
     [p.join(timeout=60) for p in procs]
     want_sf = (torch.arange(18, dtype=torch.float64).view(3, 6) * 3).tolist()
     want_mos = (torch.arange(8) * 11).tolist()
+    want_mos[7] = 0
     for r in res:
+        assert len(r) == 4, r
         assert r[1] == want_sf and r[2] == want_mos and r[3] == 0
+    assert q.empty(), q.get()
 
 
 def test_oracle_evaluation_tail_and_data_prep_properties():
