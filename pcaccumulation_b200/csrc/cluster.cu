@@ -116,13 +116,13 @@ __device__ __forceinline__ int lower_bound(const unsigned int* a, int n, unsigne
   return lo;
 }
 
-// Neighbour search is shared by FOUR lanes per point (a scene has only ~10^4..10^5 de-duplicated dynamic points: one thread
+// Neighbour search is shared by EIGHT lanes per point (a scene has only ~10^4..10^5 de-duplicated dynamic points: one thread
 // per point leaves the SMs nearly empty).  The three cells (cx-1 .. cx+1) of a grid row are consecutive keys, so the 3x3
 // block is THREE contiguous ranges of the cell-sorted order: k_ranges finds them once per point (6 binary searches) and every
-// pass re-reads the 6 ints instead of searching 9 cells again; the four lanes stride through each range together, reading the
+// pass re-reads the 6 ints instead of searching 9 cells again; the eight lanes stride through each range together, reading the
 // cell-sorted copy of the coordinates (coalesced).  The float64 distance test of sklearn is only evaluated for pairs within
 // 1e-5 (relative) of the radius; everything else is decided by a float32 squared distance whose rounding error is < 1e-6.
-constexpr int kParts = 4;
+constexpr int kParts = 8;
 
 struct NbrCtx {
   const float* pxy;         // coordinates by point id
@@ -304,10 +304,22 @@ __global__ void k_labels(NbrCtx nc, Counts* cnt, const int* __restrict__ core, c
     best = group_min(best);
     if (ok && part == 0) {
       int l = is_core ? root_rank[parent[u]] : (best != INT_MAX ? best : -1);
-      label[u] = l;
-      if (l >= 0) atomicAdd(size + l, 1);
+      label[u] = l;  // (cluster sizes: k_sizes)
       if (u == 0) cnt->n_clusters = root_rank[cap - 1] + is_root[cap - 1];
     }
+  }
+}
+
+// size[l] = number of points labelled l.  One thread per point, lanes with equal labels combine before the atomic (all
+// points of a big cluster would otherwise hit one counter).
+__global__ void k_sizes(const int* __restrict__ label, const Counts* __restrict__ cnt, int cap, int* __restrict__ size) {
+  const int U = cnt->n_unique;
+  const int stride = gridDim.x * blockDim.x;
+  for (int u0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); u0 < U; u0 += stride) {
+    const int u = u0 + (threadIdx.x & 31);
+    const int l = u < U ? label[u] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, l);
+    if (l >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(size + l, __popc(peers));
   }
 }
 
@@ -430,6 +442,7 @@ extern "C" int pcab_cluster_scene(const float* transformed_points, const float* 
   PCAB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, scan, is_root, root_rank, s, stream));
   PCAB_CUDA(cudaMemsetAsync(size, 0, (size_t)s * 4, stream));
   k_labels<<<g4, B, 0, stream>>>(nc, cnt, core, parent, root_rank, is_root, s, label, size);
+  k_sizes<<<g, B, 0, stream>>>(label, cnt, s, size);
   k_keep<<<g, B, 0, stream>>>(size, cnt, min_p_cluster, s, keep);
   PCAB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, scan, keep, keep_rank, s, stream));
   k_final<<<g, B, 0, stream>>>(label, keep, keep_rank, inverse, sel, n0, s, s, cnt, inst_out);
