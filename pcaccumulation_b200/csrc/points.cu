@@ -426,9 +426,14 @@ __global__ void k_scatter_rows3(const float* __restrict__ src, const int* __rest
 // ---------------------------------------------------------------------------------------------
 __global__ void k_tpn_hist(const long long* __restrict__ inst, const long long* __restrict__ tidx, int n, int T,
                            int* __restrict__ frame_count) {
-  int stride = gridDim.x * blockDim.x;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
-    atomicAdd(frame_count + (int)inst[j] * T + (int)tidx[j], 1);
+  // points arrive in stream order, i.e. long runs of one (instance, frame): lanes with the same bin combine before the atomic
+  const int stride = gridDim.x * blockDim.x;
+  for (int j0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); j0 < n; j0 += stride) {
+    const int j = j0 + (threadIdx.x & 31);
+    const int bin = j < n ? (int)inst[j] * T + (int)tidx[j] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (bin >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(frame_count + bin, __popc(peers));
+  }
 }
 
 // single block: mapping (old id -> new id or -1), first non-empty frame, pad source frame (or -1), totals {K, P}

@@ -55,9 +55,11 @@ __global__ void k_flag(const int* __restrict__ cell_of, const int* __restrict__ 
 __global__ void k_assign(const int* __restrict__ cell_of, const int* __restrict__ flag, const int* __restrict__ rank,
                          int n, VoxGeom g, int* __restrict__ first, int* __restrict__ coords,
                          int* __restrict__ pillar_batch, int* __restrict__ num_voxels, int* __restrict__ total) {
-  int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    if (flag[i]) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {  // warp-uniform trip count
+    const int i = i0 + (threadIdx.x & 31);
+    int b = -1;
+    if (i < n && flag[i]) {
       int id = rank[i];
       int c = cell_of[i];
       int t = c % g.nt;
@@ -67,12 +69,15 @@ __global__ void k_assign(const int* __restrict__ cell_of, const int* __restrict_
       int y = r % g.grid[1];
       r /= g.grid[1];
       int z = r % g.grid[2];
-      int b = r / g.grid[2];
+      b = r / g.grid[2];
       reinterpret_cast<int4*>(coords)[id] = make_int4(z, y, x, t);
       pillar_batch[id] = b;
       first[c] = -id - 2;  // reuse the table as cell -> pillar id (encoded negative)
-      atomicAdd(num_voxels + b, 1);
     }
+    // pillars per scene: the new pillars of a warp that belong to the same scene add up before the atomic (with one scene
+    // per call every new pillar would otherwise hit the same counter)
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    if (b >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(num_voxels + b, __popc(peers));
     if (i == n - 1) *total = rank[i] + flag[i];
   }
 }
