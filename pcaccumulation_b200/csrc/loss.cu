@@ -30,6 +30,29 @@ __device__ __forceinline__ size_t logit_addr(long long item, int c, int hw) {
   return (size_t)(item / hw) * (2 * (size_t)hw) + (size_t)(item % hw) + (size_t)c * hw;
 }
 
+// sum over the block, then ONE atomic per block and counter (a few hundred thousand warp-level double atomics on a handful of
+// addresses would cost more than the pass itself).  All threads of the block must call it; blockDim.x <= 1024.
+template <int NV>
+__device__ __forceinline__ void block_atomic_add(double* dst, const double (&v)[NV]) {
+  __shared__ double s_part[32][NV];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double s = warp_sum_d(v[k]);
+    if (lane == 0) s_part[warp][k] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = lane < nwarp ? s_part[lane][k] : 0.0;
+      s = warp_sum_d(s);
+      if (lane == 0 && s != 0.0) atomicAdd(dst + k, s);
+    }
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void softmax2(float z0, float z1, float& p0, float& p1, float& l0, float& l1) {
   const float m = fmaxf(z0, z1);
   const float e0 = expf(z0 - m), e1 = expf(z1 - m);
@@ -75,11 +98,7 @@ __global__ void k_seg_prepare(const float* __restrict__ logits, int hw, const lo
     acc[5 + pred] += 1.0;
     if (y == pred && (y == 0 || y == 1)) acc[7 + pred] += 1.0;
   }
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const double s = warp_sum_d(acc[k]);
-    if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(C + k, s);
-  }
+  block_atomic_add<9>(C, acc);
 }
 
 // Lovasz extension of one class over the sorted errors: sum_i e_i * (J_i - J_{i-1}),  J_i = 1 - (G - c_i) / (G + (i+1) - c_i)
@@ -99,8 +118,8 @@ __global__ void k_lovasz(const float* __restrict__ err_sorted, const int* __rest
     }
     acc += (double)err_sorted[i] * (J - Jp);
   }
-  acc = warp_sum_d(acc);
-  if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(out, acc);
+  const double a1[1] = {acc};
+  block_atomic_add<1>(out, a1);
 }
 
 // d(lovasz_c)/d(p_c,i) = g_rank(i) * sign(p_c,i - fg_i): scattered back through the sort permutation
@@ -290,11 +309,7 @@ __global__ void k_offset_terms(const int* __restrict__ pbatch, const long long* 
     a[3] += 1.f - ((gx / gn) * (ex / en) + (gy / gn) * (ey / en));
     a[4] += 1.0;
   }
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const double v = warp_sum_d(a[k]);
-    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(acc + k, v);
-  }
+  block_atomic_add<5>(acc, a);
 }
 
 __global__ void k_offset_final(const double* __restrict__ acc, float* __restrict__ out) {
