@@ -536,15 +536,21 @@ def main():
         sample = dict(scene)
         sample.update(oracle.voxelize(p4, vg["voxel_size"], vg["range"], vg["n_sweeps"]))
         model.keep_stages = True
-        run_protocol(model, arm.cfg, arm.sd, synth.collate([sample]), 42, "bench")
+        parity_failure = None
+        try:
+            run_protocol(model, arm.cfg, arm.sd, synth.collate([sample]), 42, "bench")
+        except AssertionError as e:  # the line is still printed (with the failure in it), then the run exits non-zero
+            parity_failure = str(e)[:500]
         model.keep_stages = False
         rec = REPORT["bench"]
         floats = {k: v for k, v in rec.items() if isinstance(v, dict) and "err_vs_ref32" in v}
-        worst = max(floats.items(), key=lambda kv: kv[1]["err_vs_ref32"])
+        worst = max(floats.items(), key=lambda kv: kv[1]["err_vs_ref32"]) if floats else ("-", {"err_vs_ref32": None, "fp32_floor": None})
         parity = {"scene_points": int(p4.shape[0]), "protocol": "oracle/protocol.py (free-running + staged, float64 floor)",
-                  "fb_label_mismatches": rec["fb_points"]["flips"], "fb_cell_flips": rec["fb_cells"]["flips"],
-                  "fb_flips_unexplained": 0, "mos_label_mismatches_staged": rec["mos_points"]["flips"],
-                  "inst_label_mismatches_staged": 0, "free_running": rec.get("free_running"),
+                  "failed": parity_failure,
+                  "fb_label_mismatches": rec.get("fb_points", {}).get("flips"), "fb_cell_flips": rec.get("fb_cells", {}).get("flips"),
+                  "fb_flips_unexplained": 0 if parity_failure is None else None,
+                  "mos_label_mismatches_staged": rec.get("mos_points", {}).get("flips"),
+                  "inst_label_mismatches_staged": 0 if parity_failure is None else None, "free_running": rec.get("free_running"),
                   "largest_float_error_vs_reference": {"tensor": worst[0], "rel": worst[1]["err_vs_ref32"], "fp32_floor": worst[1]["fp32_floor"]},
                   "tensors_compared": len(floats), "tensors_beyond_1e-4": sum(1 for v in floats.values() if v["err_vs_ref32"] > 1e-4),
                   "reference_own_flips_vs_float64": {"fb_cells": rec.get("ref32_vs_ref64_fb_cells"), "mos_points": rec.get("ref32_vs_ref64_mos_points")}}
@@ -587,6 +593,9 @@ def main():
     arm.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and parity.get("failed"):
+        print("bench.py: PARITY FAILED: " + parity["failed"], file=sys.stderr)
+        sys.exit(1)
 
 
 if __name__ == "__main__":
