@@ -426,15 +426,26 @@ def main():
 
     # kernel launch census of one forward (our kernels only: everything that is not an ATen kernel / memcpy / memset)
     launches_per_fwd = 0
+    conv_gpu_share = None  # share of the convolution kernels in the GPU time of one forward (CUPTI; compare with the ncu launch list)
     try:
         from torch.profiler import ProfilerActivity, profile
 
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             arm.serial(0)
             torch.cuda.synchronize()
+        t_all = t_conv = 0.0
         for e in prof.key_averages():
-            if e.device_type == torch.autograd.DeviceType.CUDA and "at::" not in e.key and "Memcpy" not in e.key and "Memset" not in e.key:
+            if e.device_type != torch.autograd.DeviceType.CUDA:
+                continue
+            t = float(getattr(e, "device_time_total", None) or getattr(e, "cuda_time_total", 0.0) or 0.0)
+            if "Memcpy" not in e.key and "Memset" not in e.key:
+                t_all += t
+                if "k_conv" in e.key:
+                    t_conv += t
+            if "at::" not in e.key and "Memcpy" not in e.key and "Memset" not in e.key:
                 launches_per_fwd += e.count
+        if t_all > 0:
+            conv_gpu_share = t_conv / t_all
     except Exception:
         pass
     sampler.stop_flag = True
@@ -582,6 +593,7 @@ def main():
                          "algorithmic_flops_per_launch": g_flops / max(g_launch, 1), "algorithmic_bytes_per_launch": g_bytes / max(g_launch, 1),
                          "algorithmic_flops_per_forward_in_stacks": g_flops, "algorithmic_flops_per_forward_all_convs": all_flops,
                          "stack_replay_ms": stack_ms, "conv_share_of_serial_forward": g_ms / ms_serial,
+                         "conv_share_of_gpu_time": conv_gpu_share,
                          "how": "CUDA events around 20 back-to-back replays of each captured stack (backbone UNet + merged head conv; "
                                 "Conv3d x4 + STPN UNet); the replays include the 9 pooling launches (~2% of the time)",
                          "peak_source": peak_src},
